@@ -1,0 +1,61 @@
+// Adadelta over one flat fp32 buffer (replaces tf.train.AdadeltaOptimizer.apply_gradients,
+// reference trainer.py:16-27; TF recurrence).  HBM-bound: 4 reads +
+// 3 writes of 4 B per parameter; float4-vectorised, grid-stride.
+#include "common.cuh"
+
+namespace fvta {
+
+__device__ __forceinline__ void adadelta_one(float& v, float g, float& a, float& au, float mask, float lr,
+                                             float rho, float eps, float gs) {
+  g *= gs;
+  const float na = rho * a + (1.f - rho) * g * g;
+  const float upd = sqrtf(au + eps) * rsqrtf(na + eps) * g;
+  const float nau = rho * au + (1.f - rho) * upd * upd;
+  if (mask != 0.f) {
+    a = na;
+    v = v - lr * upd;
+    au = nau;
+  }
+}
+
+__global__ void adadelta_kernel(int64_t n, float* __restrict__ var, const float* __restrict__ grad,
+                                float* __restrict__ accum, float* __restrict__ accum_update,
+                                const float* __restrict__ mask, float lr, float rho, float eps, float gs) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = reinterpret_cast<float4*>(var)[i];
+    const float4 g = reinterpret_cast<const float4*>(grad)[i];
+    float4 a = reinterpret_cast<float4*>(accum)[i];
+    float4 u = reinterpret_cast<float4*>(accum_update)[i];
+    float4 m = mask ? reinterpret_cast<const float4*>(mask)[i] : make_float4(1.f, 1.f, 1.f, 1.f);
+    adadelta_one(v.x, g.x, a.x, u.x, m.x, lr, rho, eps, gs);
+    adadelta_one(v.y, g.y, a.y, u.y, m.y, lr, rho, eps, gs);
+    adadelta_one(v.z, g.z, a.z, u.z, m.z, lr, rho, eps, gs);
+    adadelta_one(v.w, g.w, a.w, u.w, m.w, lr, rho, eps, gs);
+    reinterpret_cast<float4*>(var)[i] = v;
+    reinterpret_cast<float4*>(accum)[i] = a;
+    reinterpret_cast<float4*>(accum_update)[i] = u;
+  }
+  // tail (n not a multiple of 4)
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = var[i], a = accum[i], u = accum_update[i];
+    adadelta_one(v, grad[i], a, u, mask ? mask[i] : 1.f, lr, rho, eps, gs);
+    var[i] = v; accum[i] = a; accum_update[i] = u;
+  }
+}
+
+}  // namespace fvta
+
+extern "C" int fvta_adadelta(int64_t n, float* var, const float* grad, float* accum, float* accum_update,
+                             const float* update_mask, float lr, float rho, float eps, float grad_scale,
+                             void* stream) {
+  if (n < 0 || (n > 0 && (!var || !grad || !accum || !accum_update))) return FVTA_E_BADARG;
+  if (n == 0) return FVTA_OK;
+  const int threads = 256;
+  int64_t want = (n / 4 + threads - 1) / threads;
+  int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+  fvta::adadelta_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(n, var, grad, accum, accum_update,
+                                                                     update_mask, lr, rho, eps, grad_scale);
+  return fvta::check_launch("adadelta_kernel");
+}

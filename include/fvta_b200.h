@@ -1,0 +1,174 @@
+/*
+ * fvta_b200.h -- C ABI of the B200-native FVTA hot path (libfvta_b200.so).
+ *
+ * The reference (JunweiLiang/FVTA_MemexQA) has no FFI: its hot path sits behind Python call
+ * signatures executed by TensorFlow.  Each entry point below replaces the TensorFlow ops of
+ * one reference function; the citation is the reference file:line it stands in for.  The
+ * Python host layer (fvta_memexqa_b200/ops.py) binds these with ctypes and re-exposes the
+ * reference's own signatures (attention_3d, attention, Trainer.step, ...).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; all tensors are
+ *     contiguous row-major fp32 (masks: uint8, 0/1; indices: int32);
+ *   - the caller owns every buffer; nothing here allocates, frees or synchronises;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: FVTA_OK (0) or a negative FVTA_E_* code; never throws;
+ *   - re-entrant across streams and devices; no global state.
+ */
+#ifndef FVTA_B200_H
+#define FVTA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVTA_OK 0
+#define FVTA_E_BADARG (-1)      /* null pointer / non-positive dimension */
+#define FVTA_E_UNSUPPORTED (-2) /* unknown simiMatrix / warp_type (reference: sys.exit / raise) */
+#define FVTA_E_WORKSPACE (-3)   /* workspace too small */
+#define FVTA_E_LAUNCH (-4)      /* cudaGetLastError() != cudaSuccess after a launch */
+#define FVTA_E_SHAPE (-5)       /* shape outside what the kernels were built for */
+
+int fvta_version(void);
+/* Last CUDA error string seen by this library on the calling thread ("" if none). */
+const char* fvta_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Focal visual-text attention: time-warp gate + similarity + masks + two-level softmax +
+ * weighted sum.  Replaces model_v2.py:953-1009 (time warp), :301-341 (time_indication_func),
+ * :210-298 (attention_3d), :23-48 (softmax/softsel), utils.py:210-213 (exp_mask).
+ * With K=1, use_time_warp=0 it is model_v2.py:125-201 `attention` (bidirect=False).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t N;             /* QA samples */
+  int32_t K;             /* modalities ("sequences"): 6, or 5 with --no_photo; 1 for attention() */
+  int32_t T;             /* M * JMAX context positions per modality */
+  int32_t D;             /* 2 * hidden_size */
+  int32_t JQ;            /* question positions */
+  int32_t simi;          /* --simiMatrix 1..4 (model_v2.py:241-257) */
+  int32_t add_tanh;      /* --add_tanh */
+  int32_t use_time_warp; /* --use_time_warp */
+  int32_t warp_type;     /* --warp_type 1..5 (model_v2.py:301-341) */
+  int32_t window;        /* ceil(window_t) for warp_type 5 (model_v2.py:333-337); 3 */
+  int32_t time_warp_att; /* --use_time_warp_att (model_v2.py:269-275) */
+  int32_t has_mask;      /* 0: hinfo_mask/hq_mask are None (exp_mask skipped, model_v2.py:263) */
+} FvtaAttnDesc;
+
+typedef struct {
+  const float* att_W; /* att_logits/W [rows,1], rows = 3D,2D,4D,0 for simi 1..4 */
+  const float* att_b; /* att_logits/b [1] */
+  const float* WH_W;  /* time_warp/WH/W [2D,D]  (model_v2.py:986) */
+  const float* WH_b;  /* time_warp/WH/b [D] */
+  const float* WC_W;  /* time_warp/WC/W [D,1]   (model_v2.py:989) */
+  const float* WC_b;  /* time_warp/WC/b [1] */
+} FvtaAttnParams;
+
+typedef struct {      /* gradients, same shapes as FvtaAttnParams; each is OVERWRITTEN */
+  float* att_W;
+  float* att_b;
+  float* WH_W;
+  float* WH_b;
+  float* WC_W;
+  float* WC_b;
+} FvtaAttnGrads;
+
+/* Bytes of scratch the fwd/bwd calls need, and floats of `stats` fwd saves for bwd. */
+size_t fvta_attn_workspace_bytes(const FvtaAttnDesc* desc);
+size_t fvta_attn_stats_floats(const FvtaAttnDesc* desc);
+
+/*
+ * hall      [N,K,T,D]   un-warped context tensor (model_v2.py:905-912 reshaped :974)
+ * hall_mask [N,K,T]     uint8
+ * hq        [N,JQ,D]    question encoder outputs; hq_mask [N,JQ] uint8
+ * lq        [N,D]       question final state (only read when use_time_warp)
+ * g1_all    [N,D]       out: attended vector            (attention_3d's h_a)
+ * a_logits  [N,K,T,JQ]  out, nullable: masked logits    (attention_3d's a_logits)
+ * c_col     [N,T]       out, nullable: tanh(z) = any column of model.C (model_v2.py:995)
+ * warp_h    [N,K,T,D]   out, nullable: gated context    (model.warp_h, model_v2.py:1009)
+ * stats     fvta_attn_stats_floats() floats, out: softmax statistics for the backward
+ */
+int fvta_attn_fwd(const FvtaAttnDesc* desc, const float* hall, const uint8_t* hall_mask,
+                  const float* hq, const uint8_t* hq_mask, const float* lq,
+                  const FvtaAttnParams* params, float* g1_all, float* a_logits, float* c_col,
+                  float* warp_h, float* stats, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/*
+ * Backward of fvta_attn_fwd w.r.t. hall, hq, lq and the parameters, given d_g1_all [N,D].
+ * (The reference differentiates only through g1_all: a_logits is returned for visualisation.)
+ * d_hall [N,K,T,D], d_hq [N,JQ,D], d_lq [N,D] and every non-null member of `grads` are
+ * overwritten.  d_lq may be null when use_time_warp == 0.
+ */
+int fvta_attn_bwd(const FvtaAttnDesc* desc, const float* hall, const uint8_t* hall_mask,
+                  const float* hq, const uint8_t* hq_mask, const float* lq,
+                  const FvtaAttnParams* params, const float* stats, const float* d_g1_all,
+                  float* d_hall, float* d_hq, float* d_lq, const FvtaAttnGrads* grads,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Bidirectional LSTM reader over packed variable-length sequences.
+ * Replaces tf.nn.bidirectional_dynamic_rnn(BasicLSTMCell(d)) at the eight call sites
+ * model_v2.py:694-823 (gate order i,j,f,o; forget_bias 1; zero outputs past the length;
+ * final state = state at the last valid step; backward direction reverses the valid prefix).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B;     /* sequences */
+  int32_t J;     /* padded length */
+  int32_t In;    /* input width */
+  int32_t d;     /* hidden size */
+} FvtaLstmDesc;
+
+size_t fvta_bilstm_workspace_bytes(const FvtaLstmDesc* desc);
+size_t fvta_bilstm_reserve_floats(const FvtaLstmDesc* desc);
+
+/*
+ * x       [B,J,In]; lens [B] int32
+ * kernel_fw/bw [In+d,4d], bias_fw/bw [4d]   (the reference shares one cell: pass the same
+ *                                            pointers for both directions)
+ * out     [B,J,2d]  fw in [:d], bw in [d:], zeros past the length
+ * last    [B,2d]    final h of each direction
+ * reserve fvta_bilstm_reserve_floats() floats kept for the backward (gate activations, c)
+ */
+int fvta_bilstm_fwd(const FvtaLstmDesc* desc, const float* x, const int32_t* lens,
+                    const float* kernel_fw, const float* bias_fw, const float* kernel_bw,
+                    const float* bias_bw, float* out, float* last, float* reserve,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * d_out [B,J,2d], d_last [B,2d] (either nullable = zero) -> d_x [B,J,In] (overwritten),
+ * d_kernel_fw/bw [In+d,4d], d_bias_fw/bw [4d] ACCUMULATED (+=) so that the shared-weight case
+ * and the seven text call sites can add into one gradient slot.
+ */
+int fvta_bilstm_bwd(const FvtaLstmDesc* desc, const float* x, const int32_t* lens,
+                    const float* kernel_fw, const float* kernel_bw, const float* out,
+                    const float* reserve, const float* d_out, const float* d_last, float* d_x,
+                    float* d_kernel_fw, float* d_bias_fw, float* d_kernel_bw, float* d_bias_bw,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * fp32 GEMM with fused epilogue: C[M,N] = act(A[M,K] @ B[K,N] + bias[N]).
+ * Replaces `linear` (model_v2.py:75-100: tf.matmul + bias + optional tanh).
+ * act: 0 none, 1 tanh, 2 relu.  trans_a/trans_b: operand stored transposed.
+ * accumulate != 0: C += (no bias/act) -- used for weight gradients.
+ * ---------------------------------------------------------------------------------------- */
+int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t trans_a,
+              const float* B, int32_t ldb, int32_t trans_b, const float* bias, int32_t act,
+              float* C, int32_t ldc, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Adadelta over one flat buffer.  Replaces tf.train.AdadeltaOptimizer(lr).apply_gradients
+ * (trainer.py:16-27; TF defaults rho=0.95, eps=1e-8).  `update_mask` (nullable) is 1.0 where
+ * the slot is trainable-and-has-a-gradient, 0.0 otherwise (window_t is never updated).
+ * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).
+ * ---------------------------------------------------------------------------------------- */
+int fvta_adadelta(int64_t n, float* var, const float* grad, float* accum, float* accum_update,
+                  const float* update_mask, float lr, float rho, float eps, float grad_scale,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVTA_B200_H */

@@ -1,0 +1,161 @@
+"""GPU parity: fvta_attn_fwd / fvta_attn_bwd (through the C ABI) vs the CPU oracle.
+
+Tolerance (BASELINE.json north_star): fp32, 1e-4 relative on attention logits, g1_all and
+gradients.  Oracle = oracle/collapsed.py in fp64 on the same fp32 inputs (itself checked
+against oracle/literal.py in tests/test_oracle.py).
+"""
+import pytest
+import torch
+
+from oracle import collapsed
+from fvta_memexqa_b200 import ops
+from tests.helpers import attn_case, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def run_gpu_fwd(cfg, params, inp, dev, **want):
+    acfg = ops.AttnConfig(cfg.simiMatrix, cfg.add_tanh, cfg.use_time_warp, cfg.warp_type, 3.0,
+                          cfg.use_time_warp_att)
+    N, K, M, JMAX, D = inp["hall"].shape
+    p = {k: v.to(dev) for k, v in params.items()}
+    out = ops.attn_forward(
+        acfg, inp["hall"].reshape(N, K, M * JMAX, D).to(dev), inp["hall_mask"].reshape(N, K, -1).to(dev),
+        inp["hq"].to(dev), inp["q_mask"].to(dev), inp["lq"].to(dev),
+        p.get("attention/all/att_logits/W"), p.get("attention/all/att_logits/b"),
+        p.get("time_warp/WH/W"), p.get("time_warp/WH/b"), p.get("time_warp/WC/W"), p.get("time_warp/WC/b"),
+        **want)
+    return out, p
+
+
+def oracle64(cfg, params, inp):
+    p64 = {k: v.double() for k, v in params.items()}
+    return collapsed.fvta_attention(inp["hall"].double(), inp["hall_mask"], inp["hq"].double(),
+                                    inp["q_mask"], inp["lq"].double(), p64, cfg)
+
+
+def oracle32(cfg, params, inp):
+    return collapsed.fvta_attention(inp["hall"], inp["hall_mask"], inp["hq"], inp["q_mask"], inp["lq"],
+                                    params, cfg)
+
+
+def case_tol(ref32, ref64, key, mask=None):
+    """1e-4 relative, widened only where fp32 itself cannot do better: wide windows (warp types
+    1/3/4 give gates up to T) make S = g*P + g^2*r_h + ... cancel catastrophically, and the fp32
+    CPU oracle then differs from the fp64 one by more than 1e-4 too."""
+    return max(TOL, 3.0 * rel_err(ref32[key], ref64[key], mask))
+
+
+CASES = [
+    # N, K, M, JMAX, D, JQ, simi, tanh, warp, wtype, twa
+    (2, 6, 2, 5, 6, 4, 2, True, True, 5, False),       # tiny, T < 32, D%4 != 0
+    (3, 6, 4, 64, 100, 25, 2, True, True, 5, False),   # the C2 shape (README FVTA flags)
+    (2, 6, 3, 17, 100, 25, 1, False, True, 3, False),  # ragged T, simi 1, past window
+    (2, 6, 2, 40, 36, 13, 3, True, True, 4, True),     # simi 3, future window, time_warp_att
+    (2, 5, 2, 33, 100, 32, 4, True, True, 5, False),   # cosine, K=5 (--no_photo)
+    (2, 6, 2, 48, 100, 25, 2, True, False, 1, False),  # no time warp (FVTA_no_timewarp ablation)
+    (2, 6, 2, 40, 256, 32, 2, True, True, 5, False),   # D > 128: chunked path
+    (2, 6, 2, 6, 20, 5, 2, True, True, 1, False),      # warp type 1 (cnt = T; kept small: g^2 terms
+                                                       # of O(T^2) make S ill-conditioned in fp32)
+    (1, 6, 2, 40, 132, 8, 2, False, True, 2, False),   # chunked with a ragged last chunk
+    (2, 1, 1, 25, 100, 1, 2, True, False, 1, False),   # question-attention shape (K=1, JQ=1)
+    (1, 6, 2, 64, 64, 64, 2, True, True, 5, False),    # JQ = 64 accumulators
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_attn_fwd_parity(cuda_device, case):
+    N, K, M, JMAX, D, JQ, simi, tanh, warp, wtype, twa = case
+    cfg, params, inp = attn_case(N, K, M, JMAX, D, JQ, simi, tanh, warp, wtype, twa, seed=N + D)
+    out, _ = run_gpu_fwd(cfg, params, inp, cuda_device, want_logits=True, want_c=True, want_warp_h=True)
+    ref = oracle64(cfg, params, inp)
+    ref32 = oracle32(cfg, params, inp)
+    valid = (ref["att_logits"] > -1e29).double()
+    assert rel_err(out["g1_all"], ref["g1_all"]) < case_tol(ref32, ref, "g1_all")
+    assert rel_err(out["a_logits"], ref["att_logits"], valid) < case_tol(ref32, ref, "att_logits", valid)
+    # masked entries are exactly float32(-1e30), as exp_mask leaves them
+    a = out["a_logits"].cpu()
+    assert torch.all(a[valid == 0] == torch.tensor(-1e30, dtype=torch.float32))
+    if warp:
+        assert rel_err(out["c_col"], ref["c"]) < TOL
+        assert rel_err(out["warp_h"].reshape(ref["warp_h"].shape), ref["warp_h"]) < TOL
+
+
+def test_attn_fwd_fully_masked_and_zero(cuda_device):
+    """Known answers (SURVEY 8c pin 4): all-zero context -> g1_all = 0 and uniform softmax;
+    a fully masked sample still yields finite output (uniform over all T, beta = 1/K)."""
+    cfg, params, inp = attn_case(2, 6, 2, 20, 100, 25, seed=3)
+    inp["hall"].zero_()
+    inp["hall_mask"][1] = False
+    out, _ = run_gpu_fwd(cfg, params, inp, cuda_device, want_logits=True)
+    assert torch.isfinite(out["g1_all"]).all()
+    assert out["g1_all"].abs().max().item() == 0.0
+    ref = oracle64(cfg, params, inp)
+    assert rel_err(out["g1_all"], ref["g1_all"]) < TOL or ref["g1_all"].abs().max() == 0
+
+
+def test_attn_fwd_single_valid_position(cuda_device):
+    """Single valid position in one modality: r_k equals the gated row of that position."""
+    cfg, params, inp = attn_case(1, 6, 1, 40, 100, 25, seed=5, density=1.0, q_density=1.0)
+    inp["hall_mask"][:] = False
+    inp["hall_mask"][0, 2, 0, 7] = True
+    inp["hall"] = inp["hall"] * inp["hall_mask"].unsqueeze(-1)
+    out, _ = run_gpu_fwd(cfg, params, inp, cuda_device, want_warp_h=True)
+    ref = oracle64(cfg, params, inp)
+    assert rel_err(out["g1_all"], ref["g1_all"]) < TOL
+    wh = out["warp_h"].cpu().reshape(1, 6, 40, 100)[0, 2, 7]
+    # beta-weighted: every other modality is fully masked (beta_k ~ 0)
+    assert rel_err(out["g1_all"][0], wh.double()) < 1e-3
+
+
+BWD_CASES = [
+    (2, 6, 2, 5, 6, 4, 2, True, True, 5, False),
+    (3, 6, 4, 64, 100, 25, 2, True, True, 5, False),   # C2 shape
+    (2, 6, 3, 17, 100, 25, 1, False, True, 5, False),
+    (2, 6, 2, 40, 36, 13, 3, True, True, 5, True),     # simi 3 + time_warp_att
+    (2, 5, 2, 33, 100, 32, 4, True, True, 5, False),   # cosine
+    (2, 6, 2, 48, 100, 25, 2, True, False, 1, False),  # no time warp
+    (2, 6, 2, 40, 256, 32, 2, True, True, 2, False),   # chunked D
+    (2, 1, 1, 25, 100, 1, 2, True, False, 1, False),   # question-attention shape
+    (2, 6, 2, 24, 100, 25, 2, False, True, 5, False),  # no tanh: maxima not saturated
+]
+
+
+@pytest.mark.parametrize("case", BWD_CASES, ids=[str(c) for c in BWD_CASES])
+def test_attn_bwd_parity(cuda_device, case):
+    N, K, M, JMAX, D, JQ, simi, tanh, warp, wtype, twa = case
+    cfg, params, inp = attn_case(N, K, M, JMAX, D, JQ, simi, tanh, warp, wtype, twa, seed=3 * N + D)
+    dev = cuda_device
+    out, p = run_gpu_fwd(cfg, params, inp, dev)
+    g = torch.Generator().manual_seed(5)
+    dg1 = torch.randn(N, D, generator=g)
+    gr = ops.attn_backward(out, dg1.to(dev), p.get("attention/all/att_logits/W"),
+                           p.get("attention/all/att_logits/b"), p.get("time_warp/WH/W"),
+                           p.get("time_warp/WH/b"), p.get("time_warp/WC/W"), p.get("time_warp/WC/b"))
+
+    def oracle_grads(dtype):
+        pp = {k: v.to(dtype).clone().requires_grad_(True) for k, v in params.items()}
+        hall = inp["hall"].to(dtype).clone().requires_grad_(True)
+        hq = inp["hq"].to(dtype).clone().requires_grad_(True)
+        lq = inp["lq"].to(dtype).clone().requires_grad_(True)
+        o = collapsed.fvta_attention(hall, inp["hall_mask"], hq, inp["q_mask"], lq, pp, cfg)
+        (o["g1_all"] * dg1.to(dtype)).sum().backward()
+        res = {"d_hall": hall.grad.reshape(N, K, -1, D), "d_hq": hq.grad, "d_lq": lq.grad}
+        names = {"d_att_W": "attention/all/att_logits/W", "d_att_b": "attention/all/att_logits/b",
+                 "d_WH_W": "time_warp/WH/W", "d_WH_b": "time_warp/WH/b", "d_WC_W": "time_warp/WC/W",
+                 "d_WC_b": "time_warp/WC/b"}
+        for kk, nme in names.items():
+            res[kk] = pp[nme].grad if nme in pp else None
+        return res
+
+    ref = oracle_grads(torch.float64)
+    ref32 = oracle_grads(torch.float32)
+    for key, r in ref.items():
+        if r is None or gr.get(key) is None:
+            continue
+        if r.abs().max() == 0:
+            assert gr[key].abs().max().item() == 0.0, key
+            continue
+        tol = max(TOL, 3.0 * rel_err(ref32[key], r))
+        assert rel_err(gr[key], r) < tol, (key, rel_err(gr[key], r), tol)
