@@ -1,0 +1,319 @@
+// Bidirectional LSTM reader over padded variable-length sequences (fp32, sm_100a).
+//
+// Replaces tf.nn.bidirectional_dynamic_rnn(BasicLSTMCell(d), sequence_length=...) at the eight
+// call sites model_v2.py:694-823.  Semantics encoded:
+//   gates = [x, h] @ kernel + bias, order i, j, f, o;  c' = c*sigmoid(f+1) + sigmoid(i)*tanh(j);
+//   h' = tanh(c')*sigmoid(o);  zero initial state;  outputs are zero past the length;
+//   the final state is the state at the last valid step;  the backward direction walks the
+//   valid prefix in reverse and writes each output at its original position.
+//
+// Forward = one input-projection GEMM per distinct weight set (all timesteps at once) +
+// one persistent recurrent kernel: a CTA owns kSG sequences of one direction for all their
+// timesteps, keeps W_h, h and c in shared memory and never leaves the SM between steps.
+// Backward = the mirrored recurrent kernel (BPTT) producing d gates, then GEMMs for d_x and
+// the weight gradients.
+#include "common.cuh"
+
+namespace fvta {
+
+constexpr int kSG = 8;          // sequences per CTA
+constexpr int kResW = 6;        // reserve floats per (dir, b, t) in units of d: i, j, f, o, c, h_prev
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+struct LstmSmemPlan {
+  bool w_in_smem;
+  int wstride;  // 4d+1 when in smem (odd: conflict-free for both access patterns)
+  size_t bytes;
+};
+__host__ __device__ inline LstmSmemPlan lstm_smem_plan(int d) {
+  LstmSmemPlan p;
+  size_t w = (size_t)d * (4 * d + 1) * sizeof(float);
+  size_t rest = (size_t)kSG * (d + d + 4 * d) * sizeof(float) + 64;
+  p.w_in_smem = (w + rest) <= 200 * 1024;
+  p.wstride = p.w_in_smem ? 4 * d + 1 : 4 * d;
+  p.bytes = (p.w_in_smem ? w : 0) + rest;
+  return p;
+}
+
+// grid (ceil(B/kSG), 2); block: multiple of 32
+__global__ void bilstm_rec_fwd(FvtaLstmDesc L, const int32_t* __restrict__ lens, const float* __restrict__ xp_fw,
+                               const float* __restrict__ xp_bw, const float* __restrict__ wh_fw,
+                               const float* __restrict__ wh_bw, float* __restrict__ out,
+                               float* __restrict__ last, float* __restrict__ reserve) {
+  extern __shared__ __align__(16) float sm[];
+  const int d = L.d, G = 4 * d;
+  const LstmSmemPlan plan = lstm_smem_plan(d);
+  const int dir = blockIdx.y;
+  const float* wh_g = dir == 0 ? wh_fw : wh_bw;   // [d][4d] rows In.. of the kernel
+  const float* xp = dir == 0 ? xp_fw : xp_bw;     // [B*J][4d]
+  float* w_s = sm;
+  float* h_s = sm + (plan.w_in_smem ? (size_t)d * plan.wstride : 0);  // [kSG][d]
+  float* c_s = h_s + kSG * d;                                         // [kSG][d]
+  float* g_s = c_s + kSG * d;                                         // [kSG][4d]
+  __shared__ int len_s[kSG];
+  const int b0 = blockIdx.x * kSG;
+  if (plan.w_in_smem)
+    for (int i = threadIdx.x; i < d * G; i += blockDim.x) w_s[(i / G) * plan.wstride + (i % G)] = wh_g[i];
+  for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) { h_s[i] = 0.f; c_s[i] = 0.f; }
+  if (threadIdx.x < kSG) len_s[threadIdx.x] = (b0 + threadIdx.x < L.B) ? min(lens[b0 + threadIdx.x], L.J) : 0;
+  __syncthreads();
+  int maxlen = 0;
+#pragma unroll
+  for (int s = 0; s < kSG; ++s) maxlen = max(maxlen, len_s[s]);
+  const float* W = plan.w_in_smem ? w_s : wh_g;
+  const int ws = plan.wstride;
+
+  for (int step = 0; step < maxlen; ++step) {
+    // gate pre-activations: g_s[s][g] = xp[b][t][g] + sum_e h[s][e] * Wh[e][g]
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      float acc[kSG];
+#pragma unroll
+      for (int s = 0; s < kSG; ++s) {
+        const int len = len_s[s];
+        const int t = dir == 0 ? step : len - 1 - step;
+        acc[s] = (step < len) ? xp[((size_t)(b0 + s) * L.J + t) * G + g] : 0.f;
+      }
+      for (int e = 0; e < d; ++e) {
+        const float w = W[(size_t)e * ws + g];
+#pragma unroll
+        for (int s = 0; s < kSG; ++s) acc[s] = fmaf(h_s[s * d + e], w, acc[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < kSG; ++s) g_s[s * G + g] = acc[s];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) {
+      const int s = i / d, e = i - s * d;
+      const int len = len_s[s];
+      if (step < len) {
+        const int b = b0 + s;
+        const int t = dir == 0 ? step : len - 1 - step;
+        const float* gs = g_s + s * G;
+        const float ig = sigmoidf_(gs[e]);
+        const float jg = tanhf(gs[d + e]);
+        const float fg = sigmoidf_(gs[2 * d + e] + 1.0f);  // forget_bias = 1.0 [TF]
+        const float og = sigmoidf_(gs[3 * d + e]);
+        const float hp = h_s[i];
+        const float c = fmaf(c_s[i], fg, ig * jg);
+        const float h = tanhf(c) * og;
+        c_s[i] = c;
+        h_s[i] = h;
+        out[((size_t)b * L.J + t) * 2 * d + dir * d + e] = h;
+        float* r = reserve + (((size_t)dir * L.B + b) * L.J + t) * kResW * d;
+        r[e] = ig; r[d + e] = jg; r[2 * d + e] = fg; r[3 * d + e] = og; r[4 * d + e] = c; r[5 * d + e] = hp;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) {
+    const int s = i / d, e = i - s * d;
+    if (b0 + s < L.B) last[(size_t)(b0 + s) * 2 * d + dir * d + e] = h_s[i];
+  }
+}
+
+// BPTT.  dgates [2][B*J][4d] must be zero-initialised (padded steps stay zero).
+__global__ void bilstm_rec_bwd(FvtaLstmDesc L, const int32_t* __restrict__ lens, const float* __restrict__ wh_fw,
+                               const float* __restrict__ wh_bw, const float* __restrict__ reserve,
+                               const float* __restrict__ d_out, const float* __restrict__ d_last,
+                               float* __restrict__ dgates) {
+  extern __shared__ __align__(16) float sm[];
+  const int d = L.d, G = 4 * d;
+  const LstmSmemPlan plan = lstm_smem_plan(d);
+  const int dir = blockIdx.y;
+  const float* wh_g = dir == 0 ? wh_fw : wh_bw;
+  float* w_s = sm;
+  float* dh_s = sm + (plan.w_in_smem ? (size_t)d * plan.wstride : 0);  // [kSG][d]
+  float* dc_s = dh_s + kSG * d;                                        // [kSG][d]
+  float* dg_s = dc_s + kSG * d;                                        // [kSG][4d]
+  __shared__ int len_s[kSG];
+  const int b0 = blockIdx.x * kSG;
+  if (plan.w_in_smem)
+    for (int i = threadIdx.x; i < d * G; i += blockDim.x) w_s[(i / G) * plan.wstride + (i % G)] = wh_g[i];
+  for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) { dh_s[i] = 0.f; dc_s[i] = 0.f; }
+  if (threadIdx.x < kSG) len_s[threadIdx.x] = (b0 + threadIdx.x < L.B) ? min(lens[b0 + threadIdx.x], L.J) : 0;
+  __syncthreads();
+  int maxlen = 0;
+#pragma unroll
+  for (int s = 0; s < kSG; ++s) maxlen = max(maxlen, len_s[s]);
+  const float* W = plan.w_in_smem ? w_s : wh_g;
+  const int ws = plan.wstride;
+  float* dgd = dgates + (size_t)dir * L.B * L.J * G;
+
+  for (int step = maxlen - 1; step >= 0; --step) {
+    for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) {
+      const int s = i / d, e = i - s * d;
+      const int len = len_s[s];
+      float dgi = 0.f, dgj = 0.f, dgf = 0.f, dgo = 0.f;
+      if (step < len) {
+        const int b = b0 + s;
+        const int t = dir == 0 ? step : len - 1 - step;
+        const float* r = reserve + (((size_t)dir * L.B + b) * L.J + t) * kResW * d;
+        const float ig = r[e], jg = r[d + e], fg = r[2 * d + e], og = r[3 * d + e], c = r[4 * d + e];
+        float c_prev = 0.f;
+        if (step > 0) {
+          const int tp = dir == 0 ? t - 1 : t + 1;
+          c_prev = reserve[(((size_t)dir * L.B + b) * L.J + tp) * kResW * d + 4 * d + e];
+        }
+        float dh = dh_s[i];
+        if (d_out) dh += d_out[((size_t)b * L.J + t) * 2 * d + dir * d + e];
+        if (d_last && step == len - 1) dh += d_last[(size_t)b * 2 * d + dir * d + e];
+        const float tc = tanhf(c);
+        const float dc = fmaf(dh * og, 1.f - tc * tc, dc_s[i]);
+        dgo = dh * tc * og * (1.f - og);
+        dgi = dc * jg * ig * (1.f - ig);
+        dgj = dc * ig * (1.f - jg * jg);
+        dgf = dc * c_prev * fg * (1.f - fg);
+        dc_s[i] = dc * fg;
+        float* o = dgd + ((size_t)b * L.J + t) * G;
+        o[e] = dgi; o[d + e] = dgj; o[2 * d + e] = dgf; o[3 * d + e] = dgo;
+      }
+      float* gs = dg_s + s * G;
+      gs[e] = dgi; gs[d + e] = dgj; gs[2 * d + e] = dgf; gs[3 * d + e] = dgo;
+    }
+    __syncthreads();
+    // d h_prev[s][e] = sum_g dgates[s][g] * Wh[e][g]
+    for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) {
+      const int s = i / d, e = i - s * d;
+      if (step < len_s[s]) {
+        const float* gs = dg_s + s * G;
+        const float* wr = W + (size_t)e * ws;
+        float acc = 0.f;
+        for (int g = 0; g < G; ++g) acc = fmaf(gs[g], wr[g], acc);
+        dh_s[i] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// out[n] += sum_m A[m][n]
+__global__ void colsum_accumulate(int M, int N, const float* __restrict__ A, int lda, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (n < N)
+    for (int m = blockIdx.y * 8 + w; m < M; m += gridDim.y * 8) acc += A[(size_t)m * lda + n];
+  red[w][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (w == 0 && n < N) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x & 31];
+    atomicAdd(out + n, s);
+  }
+}
+
+}  // namespace fvta
+
+using namespace fvta;
+
+static int lstm_validate(const FvtaLstmDesc* L) {
+  if (!L) return FVTA_E_BADARG;
+  if (L->B <= 0 || L->J <= 0 || L->In <= 0 || L->d <= 0) return FVTA_E_BADARG;
+  return FVTA_OK;
+}
+
+// workspace: xp_fw [B*J*4d], xp_bw [B*J*4d] (forward) or dgates [2][B*J*4d] (backward)
+extern "C" size_t fvta_bilstm_workspace_bytes(const FvtaLstmDesc* L) {
+  if (lstm_validate(L)) return 0;
+  return (size_t)2 * L->B * L->J * 4 * L->d * sizeof(float);
+}
+extern "C" size_t fvta_bilstm_reserve_floats(const FvtaLstmDesc* L) {
+  if (lstm_validate(L)) return 0;
+  return (size_t)2 * L->B * L->J * kResW * L->d;
+}
+
+extern "C" int fvta_bilstm_fwd(const FvtaLstmDesc* desc, const float* x, const int32_t* lens,
+                               const float* kernel_fw, const float* bias_fw, const float* kernel_bw,
+                               const float* bias_bw, float* out, float* last, float* reserve, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  int rc = lstm_validate(desc);
+  if (rc) return rc;
+  const FvtaLstmDesc L = *desc;
+  if (!x || !lens || !kernel_fw || !bias_fw || !kernel_bw || !bias_bw || !out || !last || !reserve || !workspace)
+    return FVTA_E_BADARG;
+  if (workspace_bytes < fvta_bilstm_workspace_bytes(desc)) return FVTA_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = 4 * L.d, BJ = L.B * L.J;
+  float* xp_fw = (float*)workspace;
+  float* xp_bw = xp_fw + (size_t)BJ * G;
+  // input projection for every timestep at once: xp = x @ kernel[:In] + bias
+  rc = fvta_gemm(BJ, G, L.In, x, L.In, 0, kernel_fw, G, 0, bias_fw, 0, xp_fw, G, 0, stream);
+  if (rc) return rc;
+  const bool shared = (kernel_bw == kernel_fw && bias_bw == bias_fw);
+  if (!shared) {
+    rc = fvta_gemm(BJ, G, L.In, x, L.In, 0, kernel_bw, G, 0, bias_bw, 0, xp_bw, G, 0, stream);
+    if (rc) return rc;
+  } else {
+    xp_bw = xp_fw;
+  }
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)BJ * 2 * L.d * sizeof(float), st);
+  if (e != cudaSuccess) { set_last_error("bilstm memset", e); return FVTA_E_LAUNCH; }
+  // padded steps of `reserve` feed 0 * h_prev products in the backward GEMMs: keep them finite
+  e = cudaMemsetAsync(reserve, 0, fvta_bilstm_reserve_floats(desc) * sizeof(float), st);
+  if (e != cudaSuccess) { set_last_error("bilstm memset", e); return FVTA_E_LAUNCH; }
+  const LstmSmemPlan plan = lstm_smem_plan(L.d);
+  e = cudaFuncSetAttribute(bilstm_rec_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.bytes);
+  if (e != cudaSuccess) { set_last_error("bilstm_rec_fwd smem attr", e); return FVTA_E_LAUNCH; }
+  int threads = round_up(G < 1024 ? G : 1024, 32);
+  dim3 grid((L.B + kSG - 1) / kSG, 2);
+  bilstm_rec_fwd<<<grid, threads, plan.bytes, st>>>(L, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+                                                   kernel_bw + (size_t)L.In * G, out, last, reserve);
+  return check_launch("bilstm_rec_fwd");
+}
+
+extern "C" int fvta_bilstm_bwd(const FvtaLstmDesc* desc, const float* x, const int32_t* lens,
+                               const float* kernel_fw, const float* kernel_bw, const float* out,
+                               const float* reserve, const float* d_out, const float* d_last, float* d_x,
+                               float* d_kernel_fw, float* d_bias_fw, float* d_kernel_bw, float* d_bias_bw,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  (void)out;
+  int rc = lstm_validate(desc);
+  if (rc) return rc;
+  const FvtaLstmDesc L = *desc;
+  if (!x || !lens || !kernel_fw || !kernel_bw || !reserve || !d_x || !d_kernel_fw || !d_bias_fw ||
+      !d_kernel_bw || !d_bias_bw || !workspace)
+    return FVTA_E_BADARG;
+  if (workspace_bytes < fvta_bilstm_workspace_bytes(desc)) return FVTA_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = 4 * L.d, BJ = L.B * L.J;
+  float* dg = (float*)workspace;  // [2][BJ][G]
+  cudaError_t e = cudaMemsetAsync(dg, 0, (size_t)2 * BJ * G * sizeof(float), st);
+  if (e != cudaSuccess) { set_last_error("bilstm bwd memset", e); return FVTA_E_LAUNCH; }
+  const LstmSmemPlan plan = lstm_smem_plan(L.d);
+  e = cudaFuncSetAttribute(bilstm_rec_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.bytes);
+  if (e != cudaSuccess) { set_last_error("bilstm_rec_bwd smem attr", e); return FVTA_E_LAUNCH; }
+  int threads = round_up((kSG * L.d) < 1024 ? (kSG * L.d) : 1024, 32);
+  dim3 grid((L.B + kSG - 1) / kSG, 2);
+  bilstm_rec_bwd<<<grid, threads, plan.bytes, st>>>(L, lens, kernel_fw + (size_t)L.In * G,
+                                                   kernel_bw + (size_t)L.In * G, reserve, d_out, d_last, dg);
+  rc = check_launch("bilstm_rec_bwd");
+  if (rc) return rc;
+  const float* dg_fw = dg;
+  const float* dg_bw = dg + (size_t)BJ * G;
+  // d_x = dg_fw @ Wx_fw^T + dg_bw @ Wx_bw^T
+  rc = fvta_gemm(BJ, L.In, G, dg_fw, G, 0, kernel_fw, G, 1, nullptr, 0, d_x, L.In, 0, stream);
+  if (rc) return rc;
+  rc = fvta_gemm(BJ, L.In, G, dg_bw, G, 0, kernel_bw, G, 1, nullptr, 0, d_x, L.In, 1, stream);
+  if (rc) return rc;
+  const float* res_fw = reserve;
+  const float* res_bw = reserve + (size_t)BJ * kResW * L.d;
+  const float* dgs[2] = {dg_fw, dg_bw};
+  const float* ress[2] = {res_fw, res_bw};
+  float* dks[2] = {d_kernel_fw, d_kernel_bw};
+  float* dbs[2] = {d_bias_fw, d_bias_bw};
+  for (int dir = 0; dir < 2; ++dir) {
+    // d kernel[:In] += x^T @ dg ;  d kernel[In:] += h_prev^T @ dg ;  d bias += colsum(dg)
+    rc = fvta_gemm(L.In, G, BJ, x, L.In, 1, dgs[dir], G, 0, nullptr, 0, dks[dir], G, 1, stream);
+    if (rc) return rc;
+    rc = fvta_gemm(L.d, G, BJ, ress[dir] + 5 * L.d, kResW * L.d, 1, dgs[dir], G, 0, nullptr, 0,
+                   dks[dir] + (size_t)L.In * G, G, 1, stream);
+    if (rc) return rc;
+    dim3 cg((G + 31) / 32, 64);
+    colsum_accumulate<<<cg, 256, 0, st>>>(BJ, G, dgs[dir], G, dbs[dir]);
+    rc = check_launch("colsum_accumulate");
+    if (rc) return rc;
+  }
+  return FVTA_OK;
+}

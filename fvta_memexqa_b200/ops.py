@@ -139,3 +139,164 @@ def adadelta_step(var, grad, accum, accum_update, update_mask, lr, rho=0.95, eps
     rc = lib.fvta_adadelta(var.numel(), _ptr(var), _ptr(grad), _ptr(accum), _ptr(accum_update),
                            _ptr(update_mask), lr, rho, eps, grad_scale, _stream())
     check(rc, "fvta_adadelta")
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMM / linear
+# ---------------------------------------------------------------------------------------------
+ACT = {None: 0, "none": 0, "tanh": 1, "relu": 2}
+
+
+def gemm(A, B, bias=None, act=None, trans_a=False, trans_b=False, out=None, accumulate=False):
+    """fvta_gemm: act(op(A) @ op(B) + bias); A, B 2-D contiguous fp32 CUDA tensors."""
+    lib = _lib.load()
+    f32 = torch.float32
+    A, B, bias = _req(A, f32, "A"), _req(B, f32, "B"), _req(bias, f32, "bias")
+    M, K = (A.shape[1], A.shape[0]) if trans_a else (A.shape[0], A.shape[1])
+    K2, N = (B.shape[1], B.shape[0]) if trans_b else (B.shape[0], B.shape[1])
+    if K != K2:
+        raise _lib.FvtaError("gemm: inner dimensions differ (%d vs %d)" % (K, K2))
+    if out is None:
+        out = torch.empty(M, N, dtype=f32, device=A.device)
+    rc = lib.fvta_gemm(M, N, K, _ptr(A), A.shape[1], int(trans_a), _ptr(B), B.shape[1], int(trans_b),
+                       _ptr(bias), ACT[act], _ptr(out), out.shape[1], int(accumulate), _stream())
+    check(rc, "fvta_gemm")
+    return out
+
+
+class LinearFn(torch.autograd.Function):
+    """`linear` of the reference (model_v2.py:75-100): flatten, x @ W + b, optional tanh."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, add_tanh):
+        flat = x.reshape(-1, x.shape[-1])
+        y = gemm(flat, W, b, "tanh" if add_tanh else None)
+        ctx.save_for_backward(flat, W, y)
+        ctx.add_tanh = add_tanh
+        ctx.xshape = x.shape
+        return y.reshape(*x.shape[:-1], W.shape[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        flat, W, y = ctx.saved_tensors
+        dy = dy.reshape(-1, W.shape[1]).contiguous()
+        if ctx.add_tanh:
+            dy = dy * (1.0 - y * y)
+        dx = gemm(dy, W, trans_b=True).reshape(ctx.xshape)
+        dW = gemm(flat, dy, trans_a=True)
+        db = dy.sum(0)
+        return dx, dW, db, None
+
+
+def linear(x, W, b, add_tanh=False):
+    return LinearFn.apply(x, W, b, add_tanh)
+
+
+# ---------------------------------------------------------------------------------------------
+# BiLSTM reader
+# ---------------------------------------------------------------------------------------------
+def _lstm_desc(x, kernel):
+    B, J, In = x.shape
+    d = kernel.shape[1] // 4
+    if kernel.shape[0] != In + d:
+        raise _lib.FvtaError("bilstm: kernel rows %d != In + d = %d" % (kernel.shape[0], In + d))
+    return FvtaLstmDesc(B=B, J=J, In=In, d=d)
+
+
+def bilstm_forward(x, lens, kernel_fw, bias_fw, kernel_bw=None, bias_bw=None):
+    """fvta_bilstm_fwd.  x [B,J,In] fp32, lens [B] int32.  Passing no bw weights shares fw's
+    (the reference hands the same cell object to both directions)."""
+    lib = _lib.load()
+    f32 = torch.float32
+    x = _req(x, f32, "x")
+    lens = _req(lens, torch.int32, "lens")
+    kernel_fw, bias_fw = _req(kernel_fw, f32, "kernel_fw"), _req(bias_fw, f32, "bias_fw")
+    if kernel_bw is None:
+        kernel_bw, bias_bw = kernel_fw, bias_fw
+    else:
+        kernel_bw, bias_bw = _req(kernel_bw, f32, "kernel_bw"), _req(bias_bw, f32, "bias_bw")
+    desc = _lstm_desc(x, kernel_fw)
+    B, J, d = desc.B, desc.J, desc.d
+    dev = x.device
+    out = torch.empty(B, J, 2 * d, dtype=f32, device=dev)
+    last = torch.empty(B, 2 * d, dtype=f32, device=dev)
+    if B == 0 or J == 0:
+        return out.zero_(), last.zero_(), None, desc
+    reserve = torch.empty(lib.fvta_bilstm_reserve_floats(ctypes.byref(desc)), dtype=f32, device=dev)
+    ws_bytes = lib.fvta_bilstm_workspace_bytes(ctypes.byref(desc))
+    ws = torch.empty(ws_bytes // 4, dtype=f32, device=dev)
+    rc = lib.fvta_bilstm_fwd(ctypes.byref(desc), _ptr(x), _ptr(lens), _ptr(kernel_fw), _ptr(bias_fw),
+                             _ptr(kernel_bw), _ptr(bias_bw), _ptr(out), _ptr(last), _ptr(reserve), _ptr(ws),
+                             ws_bytes, _stream())
+    check(rc, "fvta_bilstm_fwd")
+    return out, last, reserve, desc
+
+
+class BiLSTMFn(torch.autograd.Function):
+    """bidirectional_dynamic_rnn(cell, cell, x, sequence_length) with shared fw/bw weights
+    (model_v2.py:694 etc.).  Returns (outputs [B,J,2d], final h [B,2d])."""
+
+    @staticmethod
+    def forward(ctx, x, lens, kernel, bias):
+        out, last, reserve, desc = bilstm_forward(x, lens, kernel, bias)
+        ctx.save_for_backward(x, lens, kernel, out, reserve)
+        ctx.desc = desc
+        ctx.mark_non_differentiable(lens)
+        return out, last
+
+    @staticmethod
+    def backward(ctx, d_out, d_last):
+        lib = _lib.load()
+        x, lens, kernel, out, reserve = ctx.saved_tensors
+        desc = ctx.desc
+        f32 = torch.float32
+        d_x = torch.empty_like(x)
+        d_kernel = torch.zeros_like(kernel)
+        d_bias = torch.zeros(kernel.shape[1], dtype=f32, device=x.device)
+        if reserve is None:
+            return d_x.zero_(), None, d_kernel, d_bias
+        d_out = _req(d_out, f32, "d_out") if d_out is not None else None
+        d_last = _req(d_last, f32, "d_last") if d_last is not None else None
+        ws_bytes = lib.fvta_bilstm_workspace_bytes(ctypes.byref(desc))
+        ws = torch.empty(ws_bytes // 4, dtype=f32, device=x.device)
+        xc = x.contiguous()
+        rc = lib.fvta_bilstm_bwd(ctypes.byref(desc), _ptr(xc), _ptr(lens), _ptr(kernel), _ptr(kernel), _ptr(out),
+                                 _ptr(reserve), _ptr(d_out), _ptr(d_last), _ptr(d_x), _ptr(d_kernel),
+                                 _ptr(d_bias), _ptr(d_kernel), _ptr(d_bias), _ptr(ws), ws_bytes, _stream())
+        check(rc, "fvta_bilstm_bwd")
+        return d_x, None, d_kernel, d_bias
+
+
+def bilstm(x, lens, kernel, bias):
+    return BiLSTMFn.apply(x, lens, kernel, bias)
+
+
+# ---------------------------------------------------------------------------------------------
+# attention as an autograd op
+# ---------------------------------------------------------------------------------------------
+class FvtaAttentionFn(torch.autograd.Function):
+    """Time-warp gate + attention_3d (model_v2.py:953-1024) as one differentiable op.
+    Inputs: hall [N,K,T,D], hall_mask, hq, hq_mask, lq, W, b, WH_W, WH_b, WC_W, WC_b.
+    Outputs: g1_all [N,D] (differentiable), a_logits / c_col / warp_h (visualisation; no grad)."""
+
+    @staticmethod
+    def forward(ctx, cfg, want, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W, WH_b, WC_W, WC_b):
+        fwd = attn_forward(cfg, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W, WH_b, WC_W, WC_b,
+                           want_logits=want[0], want_c=want[1], want_warp_h=want[2])
+        ctx.fwd = fwd
+        ctx.params = (W, b, WH_W, WH_b, WC_W, WC_b)
+        ctx.has_lq = lq is not None
+        outs = [fwd["g1_all"]]
+        for key in ("a_logits", "c_col", "warp_h"):
+            t = fwd[key] if fwd[key] is not None else torch.empty(0, device=hall.device)
+            ctx.mark_non_differentiable(t)
+            outs.append(t)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, d_g1, *_unused):
+        W, b, WH_W, WH_b, WC_W, WC_b = ctx.params
+        g = attn_backward(ctx.fwd, d_g1, W, b, WH_W, WH_b, WC_W, WC_b)
+        ctx.fwd = None
+        return (None, None, g["d_hall"], None, g["d_hq"], None, g["d_lq"] if ctx.has_lq else None,
+                g["d_att_W"], g["d_att_b"], g["d_WH_W"], g["d_WH_b"], g["d_WC_W"], g["d_WC_b"])
