@@ -1,0 +1,113 @@
+"""GPU parity of the whole FVTA step (embeddings -> reader -> context tensor -> attention ->
+question attention -> output -> loss -> gradients -> Adadelta) against the CPU oracle, through
+the reference-shaped API (get_model / Trainer.step / Tester.step).
+
+Tolerances (BASELINE.json north_star): 1e-4 relative in fp32 for logits, loss, gradients and
+post-update weights; argmax of yp identical."""
+import pytest
+import torch
+
+from oracle import full as oracle_full
+from fvta_memexqa_b200.config import fvta_config, set_shapes
+from fvta_memexqa_b200.data import TensorBatch
+from fvta_memexqa_b200.model import get_model
+from fvta_memexqa_b200.params import NEVER_UPDATED
+from fvta_memexqa_b200.synthetic import make_feed
+from fvta_memexqa_b200.tester import Tester
+from fvta_memexqa_b200.trainer import Trainer
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def tiny_config(**kw):
+    cfg = fvta_config(batch_size=3, hidden_size=4, char_emb_size=6, char_out_size=5, image_feat_dim=11,
+                      image_trans_dim=7, **kw)
+    set_shapes(cfg, M=2, JI=2, JXP=3, JD=4, JXA=3, JT=2, JG=2, JQ=4, JA=3, W=6, word_vocab_size=20,
+               char_vocab_size=15, word_emb_size=8)
+    return cfg
+
+
+def run_case(cfg, block, n_ex=None, steps=2, glove=10):
+    feed = make_feed(cfg, seed=5, num_examples=n_ex, glove_vocab=glove)
+    model = get_model(cfg)
+    trainer = Trainer(model, cfg)
+    p0 = {k: v.detach().cpu().double() for k, v in model.params.as_dict().items()}
+    # randomise biases so bias-gradient bugs cannot hide behind zeros
+    g = torch.Generator().manual_seed(1)
+    for k in p0:
+        if k.endswith("/b") or k.endswith("/bias"):
+            p0[k] = torch.randn(p0[k].shape, generator=g, dtype=torch.float64) * 0.1
+            model.params.view(k).copy_(p0[k].float())
+    p0 = {k: model.params.view(k).detach().cpu().double() for k in p0}
+    feed64 = {k: (v.double() if v.is_floating_point() else v) for k, v in feed.items()}
+    batch = TensorBatch(feed, cfg.batch_size if n_ex is None else n_ex)
+
+    # inference parity first (Tester.step trims padded rows)
+    tester = Tester(model, cfg)
+    yp = tester.step(None, ((), batch))
+    ref = oracle_full.forward(feed64, p0, cfg, block=block)
+    assert yp.shape[0] == batch.num_examples
+    assert rel_err(torch.as_tensor(yp), ref["yp"][:batch.num_examples]) < TOL
+    assert (torch.as_tensor(yp).argmax(1) == ref["yp"][:batch.num_examples].argmax(1)).all()
+
+    params, state = p0, {}
+    for s in range(steps):
+        loss, _, _ = trainer.step(None, ((), batch))
+        rloss, rgrads, params, state, _ = oracle_full.train_step(feed64, params, state, cfg, block=block,
+                                                                 never_updated=NEVER_UPDATED)
+        assert abs(loss - rloss.item()) <= TOL * max(1.0, abs(rloss.item())), (s, loss, rloss.item())
+        # gradients that are analytically ~0 (e.g. the bias of a softmax logit) are pure rounding
+        # noise: measure every error against at least 1e-3 of the largest gradient in the model
+        gmax = max(g.abs().max().item() for g in rgrads.values() if g is not None)
+        for k, gref in rgrads.items():
+            if gref is None:
+                continue
+            got = model.params.grad(k).detach().cpu().double()
+            err = (got - gref).abs().max().item()
+            scale = max(gref.abs().max().item(), 1e-3 * gmax)
+            assert err < 5 * TOL * scale + 2e-7, (s, k, err, scale)
+        for k in params:
+            assert rel_err(model.params.view(k), params[k]) < 5 * TOL, (s, k)
+    assert model.global_step == steps
+    return model
+
+
+def test_tiny_step_vs_literal_oracle(cuda_device):
+    """Tiny shape (SURVEY 8c pin 3) against the op-for-op literal oracle, incl. a short batch."""
+    run_case(tiny_config(), "literal", n_ex=2)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(),                                           # README FVTA flags
+    dict(use_question_att=False),                     # FVTA_no_question_att ablation
+    dict(use_time_warp=False),                        # FVTA_no_timewarp ablation
+    dict(no_photo=True),                              # FVTA_no_photo ablation (K=5)
+    dict(simiMatrix=4),                               # FVTA cosine
+    dict(simiMatrix=1, add_tanh=False, use_eu_output=True),
+    dict(simiMatrix=3, warp_type=3, use_time_warp_att=True),
+    dict(wd=0.002),
+    dict(use_char=False, use_image_trans=False),
+], ids=lambda kw: ",".join("%s=%s" % kv for kv in kw.items()) or "fvta")
+def test_tiny_step_flag_matrix(cuda_device, kw):
+    run_case(tiny_config(**kw), "literal", steps=1)
+
+
+def test_c2_step_vs_collapsed_oracle(cuda_device):
+    """C2 shape (README training flags, N=4 to keep the CPU oracle in seconds)."""
+    cfg = fvta_config(batch_size=4)
+    run_case(cfg, "collapsed", steps=1, glove=50)
+
+
+def test_step_vis_surface(cuda_device):
+    cfg = tiny_config()
+    model = get_model(cfg)
+    feed = make_feed(cfg, seed=2, num_examples=2, glove_vocab=10)
+    out = Tester(model, cfg).step_vis(None, ((), TensorBatch(feed, 2)))
+    assert len(out) == 28
+    yp, C, C_win, att_logits, q_att = out[:5]
+    T = 2 * 6
+    assert yp.shape == (2, 4) and C.shape == (2, T, T) and att_logits.shape == (2, 6, T, 4)
+    # tester.py:27-28 trim() turns every non-ndarray (the scalar window) into -1
+    assert q_att.shape == (2, 4, 1) and C_win == -1
