@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- FVTA QA samples/sec fwd+bwd (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one full training step of the FVTA model (README.MD:222-226 flags) at the C2 shape
+(N=32 QAs per GPU, M=4 albums x JI=8 photos, JQ=25, hidden 50, fp32):
+embeddings -> BiLSTM reader -> context tensor -> time-warp gate + focal attention -> question
+attention -> output -> loss -> backward -> (NCCL all-reduce of the flat gradient) -> Adadelta.
+
+One JSON line is printed by rank 0:
+  value       whole-job samples/s with the batch already resident in HBM
+  e2e         the same through Trainer.step (the reference-facing call) from PINNED HOST tensors,
+              host->device copies and the loss read-back inside the timed region
+  roofline    the focal-attention forward (fvta_attn_fwd) at the C3-max microbenchmark shape
+              (64 albums x 64 photos, JQ 32; 315 MB of context > L2), algorithmic bytes / time
+  cpu_baseline  the literal CPU oracle (a port: TensorFlow cannot run here) on the host cores
+`--impl reference` times that CPU oracle alone, on the same config/metric.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "FVTA QA samples/sec fwd+bwd"
+UNIT = "samples/s"
+PER_GPU_BATCH = 32
+
+
+def workload_config(n_gpus):
+    return {"workload": "C2: FVTA training step (fwd+bwd+Adadelta), README.MD:222-226 flags, "
+                        "batch 32 per GPU, M=4 JI=8 JXP=8 JD=10 JXA=8 JT=4 JG=4 JQ=25 JA=5 W=16, hidden 50, "
+                        "idim 2537, K=6 T=256 D=100",
+            "global_batch": PER_GPU_BATCH * n_gpus, "per_gpu_batch": PER_GPU_BATCH,
+            "parallelism": "dp%d" % n_gpus,
+            "l2": "flushed between steps (256 MiB memset, inside the timed region)",
+            "mask_density": "MemexQA-shaped (SURVEY 8d length distributions)"}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.samples:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU oracle arm (cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_step(n_samples, seed=0):
+    """One bounded CPU sample of the workload: the LITERAL oracle (op-for-op TF graph incl. the
+    [K,T,T,4d] time-warp tensors) run as the README runs FVTA -- micro-batches of 1
+    (README.MD:146-148) -- fwd+bwd per QA, gradients accumulated, one Adadelta update.
+    Returns seconds."""
+    import torch
+    from oracle import full as oracle_full
+    from oracle.tf_ops import adadelta_update
+    from fvta_memexqa_b200.config import fvta_config
+    from fvta_memexqa_b200.params import ParamStore, NEVER_UPDATED
+    from fvta_memexqa_b200.synthetic import make_feed
+    cfg = fvta_config(batch_size=1)
+    ps = ParamStore(cfg, seed=1234)
+    params = {k: v.clone() for k, v in ps.as_dict().items()}
+    feeds = [make_feed(cfg, seed=1234 + seed * 100 + i, glove_vocab=300) for i in range(n_samples)]
+    t0 = time.perf_counter()
+    acc = {}
+    for feed in feeds:
+        leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        out = oracle_full.forward(feed, leaves, cfg, is_train=True, block="literal")
+        names = [k for k in leaves if k not in NEVER_UPDATED]
+        grads = torch.autograd.grad(out["loss"], [leaves[k] for k in names], allow_unused=True)
+        for k, g in zip(names, grads):
+            if g is not None:
+                acc[k] = acc.get(k, 0) + g / n_samples
+    for k, g in acc.items():
+        z = torch.zeros_like(params[k])
+        params[k], _, _ = adadelta_update(params[k], g, z, z, cfg.init_lr)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_samples = 4
+    for i in range(args.warmup):
+        cpu_reference_step(1, seed=100 + i)
+    times = [cpu_reference_step(n_samples, seed=i) for i in range(args.steps)]
+    total = sum(times)
+    value = n_samples * args.steps / total
+    sample = ("%d QAs per step in micro-batches of 1 (README.MD:146-148), literal torch-CPU restatement of "
+              "model_v2.py incl. the [K,T,T,4d] time-warp tensors, fwd+bwd+Adadelta; TensorFlow 1.x "
+              "cannot run in this image" % n_samples)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# roofline leg: focal attention forward at the C3-max shape
+# ------------------------------------------------------------------------------------------
+def attention_roofline(dev, iters=10, with_logits=False):
+    import torch
+    from fvta_memexqa_b200 import ops
+    from fvta_memexqa_b200.config import fvta_config
+    from fvta_memexqa_b200.params import ParamStore
+    N, K, M, JI, JXP, D, JQ = 4, 6, 64, 64, 8, 100, 32
+    T = M * JI * JXP
+    cfg = fvta_config(batch_size=N)
+    ps = ParamStore(cfg, seed=7, device=dev)
+    p = ps.as_dict()
+    g = torch.Generator(device=dev).manual_seed(1)
+    hall = torch.randn(N, K, T, D, device=dev, generator=g)
+    hmask = torch.ones(N, K, T, dtype=torch.bool, device=dev)       # mask density 1.0
+    hq = torch.randn(N, JQ, D, device=dev, generator=g)
+    qmask = torch.ones(N, JQ, dtype=torch.bool, device=dev)
+    lq = torch.randn(N, D, device=dev, generator=g)
+    acfg = ops.AttnConfig(2, True, True, 5, 3.0, False)
+
+    def call():
+        return ops.attn_forward(acfg, hall, hmask, hq, qmask, lq, p["attention/all/att_logits/W"],
+                                p["attention/all/att_logits/b"], p["time_warp/WH/W"], p["time_warp/WH/b"],
+                                p["time_warp/WC/W"], p["time_warp/WC/b"], want_logits=with_logits)
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e-3)
+    t = statistics.mean(times)
+    # algorithmic bytes of the attention forward
+    bytes_alg = 4 * N * K * T * D + N * K * T + 4 * N * JQ * D + N * JQ + 4 * N * D + 4 * N * D
+    if with_logits:
+        bytes_alg += 4 * N * K * T * JQ
+    peak, how = measured_peaks()
+    achieved = bytes_alg / t / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "attn_fwd_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "kernel": "fvta_attn_fwd (attn_tile_fwd + prep + combine)",
+            "workload": "C3-max: N=4 K=6 T=64*64*8=32768 D=100 JQ=32, mask density 1.0, working set "
+                        "%.0f MB > L2" % (bytes_alg / 1e6),
+            "algorithmic_bytes": bytes_alg, "launch_ms": t * 1e3, "peak_source": how}
+
+
+# ------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------
+def run_own(args):
+    import torch
+    from fvta_memexqa_b200 import _lib
+    from fvta_memexqa_b200.config import fvta_config
+    from fvta_memexqa_b200.data import SyntheticDataset
+    from fvta_memexqa_b200.dp import DataParallel
+    from fvta_memexqa_b200.model import get_model
+    from fvta_memexqa_b200.trainer import Trainer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the FVTA path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle)")
+    lib = _lib.load()
+    dp = DataParallel()
+    rank, world = dp.rank, dp.world_size
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dp.device = dev
+
+    cfg = fvta_config(batch_size=PER_GPU_BATCH, seed=1234)
+    model = get_model(cfg)
+    dp.broadcast_params(model.params.flat)
+    trainer = Trainer(model, cfg, dp=dp if world > 1 else None)
+    data = SyntheticDataset(cfg, num_examples=PER_GPU_BATCH * 4, seed=1234 + 1000 * rank, pin=True)
+    batches = list(data.get_batches(PER_GPU_BATCH, num_steps=4, shuffle=False))
+    dfeeds = [model.to_device(model.get_feed_dict(b[1], is_train=True)) for b in batches]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    h2d = batches[0][1].h2d_bytes()
+    if not args.no_graph:
+        # the whole device step replays as ONE CUDA graph (static shapes; see Trainer.enable_graph)
+        snap = [t.clone() for t in (model.params.flat, model.params.accum, model.params.accum_update)]
+        trainer.enable_graph(batches[0][1].feed)
+        for t, s0 in zip((model.params.flat, model.params.accum, model.params.accum_update), snap):
+            t.copy_(s0)
+        device_step = trainer.graph_step
+    else:
+        device_step = trainer._device_step
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dp.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg -------------------------------------------------------------
+    for i in range(args.warmup):
+        flush.zero_()
+        device_step(dfeeds[i % len(dfeeds)])
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.fvta_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        flush.zero_()
+        loss = device_step(dfeeds[i % len(dfeeds)])
+    e1.record()
+    sync_all()
+    launches = lib.fvta_launch_count() - l0
+    if not args.no_graph:
+        launches = trainer.launches_per_step * args.steps   # replayed graph nodes
+    t_dev = dp.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end leg: Trainer.step from pinned host tensors, loss read back -----------
+    for i in range(max(1, args.warmup // 2)):
+        trainer.step(None, batches[i % len(batches)])
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        flush.zero_()
+        loss_val, _, _ = trainer.step(None, batches[i % len(batches)])
+    e1.record()
+    sync_all()
+    t_e2e = dp.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    if rank != 0:
+        return
+    total = PER_GPU_BATCH * world * args.steps
+    line = {"metric": METRIC, "value": total / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": 1000.0 * t_e2e / args.steps},
+            "gpu_launches": int(launches), "final_loss": loss_val}
+    line["config"]["execution"] = "eager launches" if args.no_graph else "one CUDA graph per step"
+    if world == 1:
+        line["roofline"] = attention_roofline(dev)
+        line["roofline_with_logits"] = attention_roofline(dev, with_logits=True)
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            n = 6
+            cpu_reference_step(1, seed=99)
+            t = cpu_reference_step(n)
+            line["cpu_baseline"] = {
+                "value": n / t, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d QAs, micro-batches of 1 (README.MD:146-148), literal torch-CPU oracle of "
+                          "model_v2.py (TensorFlow 1.x cannot run here), fwd+bwd+Adadelta, %.1f s" % (n, t)}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", type=str, default="fvta_b200", choices=["fvta_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="launch kernels eagerly")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,7 @@ ERRORS = {0: "FVTA_OK", -1: "FVTA_E_BADARG", -2: "FVTA_E_UNSUPPORTED", -3: "FVTA
 SYMBOLS = {
     "fvta_version": (ctypes.c_int, []),
     "fvta_last_error": (ctypes.c_char_p, []),
+    "fvta_launch_count": (ctypes.c_ulonglong, []),
     "fvta_attn_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(FvtaAttnDesc)]),
     "fvta_attn_stats_floats": (ctypes.c_size_t, [ctypes.POINTER(FvtaAttnDesc)]),
     "fvta_attn_fwd": (ctypes.c_int, [ctypes.POINTER(FvtaAttnDesc), c_float_p, c_u8_p, c_float_p, c_u8_p,

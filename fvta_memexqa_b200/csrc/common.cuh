@@ -10,8 +10,11 @@
 namespace fvta {
 
 void set_last_error(const char* what, cudaError_t e);
+void count_launch();
 
+// Called once after every kernel launch of this library.
 inline int check_launch(const char* what) {
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_error(what, e);

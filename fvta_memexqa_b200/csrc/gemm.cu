@@ -17,7 +17,8 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                    const float* __restrict__ B, int ldb,
                                                    const float* __restrict__ bias, int act,
-                                                   float* __restrict__ C, int ldc, int accumulate) {
+                                                   float* __restrict__ C, int ldc, int accumulate,
+                                                   int k_per_split) {
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -29,7 +30,11 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  // split-K (accumulate mode only): blockIdx.z owns K range [kbeg, kend) and adds atomically
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(K, kbeg + k_per_split);
+  const bool atomic_out = gridDim.z > 1;
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
     // A tile: BM x BK
     for (int i = tid; i < BM * BK; i += 256) {
       int m, k;
@@ -37,7 +42,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
       else    { k = i % BK; m = i / BK; }   // A stored [M, lda]: k fastest
       const int gm = m0 + m, gk = k0 + k;
       float v = 0.f;
-      if (gm < M && gk < K) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      if (gm < M && gk < kend) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
       As[k][m] = v;
     }
     for (int i = tid; i < BN * BK; i += 256) {
@@ -46,7 +51,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
       else    { n = i % BN; k = i / BN; }   // B stored [K, ldb]: n fastest
       const int gn = n0 + n, gk = k0 + k;
       float v = 0.f;
-      if (gn < N && gk < K) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+      if (gn < N && gk < kend) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
       Bs[k][n] = v;
     }
     __syncthreads();
@@ -74,7 +79,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
       float v = acc[i][j];
       float* c = C + (size_t)gm * ldc + gn;
       if (accumulate) {
-        *c += v;
+        if (atomic_out) atomicAdd(c, v);
+        else *c += v;
       } else {
         if (bias) v += bias[gn];
         if (act == 1) v = tanhf(v);
@@ -98,9 +104,21 @@ extern "C" int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
   if (grid.y > 65535) return FVTA_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
-  if (!trans_a && !trans_b) gemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate);
-  else if (!trans_a && trans_b) gemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate);
-  else if (trans_a && !trans_b) gemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate);
-  else gemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate);
+  // Weight-gradient GEMMs are short and fat (M, N ~ 200, K = tokens): split K over the SMs.
+  int kps = K > 0 ? K : 1;
+  if (accumulate && K >= 512) {
+    const int tiles = (int)(grid.x * grid.y);
+    int splits = (2 * 148 + tiles - 1) / tiles;
+    const int max_splits = (K + 127) / 128;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 1) {
+      kps = round_up((K + splits - 1) / splits, BK);
+      grid.z = (K + kps - 1) / kps;
+    }
+  }
+  if (!trans_a && !trans_b) gemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate, kps);
+  else if (!trans_a && trans_b) gemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate, kps);
+  else if (trans_a && !trans_b) gemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate, kps);
+  else gemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate, kps);
   return check_launch("gemm_kernel");
 }

@@ -45,7 +45,10 @@ class SyntheticDataset:
     def _batch(self, b, n_ex):
         key = (b % self.distinct, n_ex)
         if key not in self._cache:
-            feed = make_feed(self.config, seed=self.seed + 17 * key[0], num_examples=n_ex)
+            cfg = self.config
+            # fixed-size photo table so every batch has identical shapes (CUDA-graph replay)
+            pool = cfg.batch_size * cfg.max_num_albums * cfg.max_num_photos
+            feed = make_feed(cfg, seed=self.seed + 17 * key[0], num_examples=n_ex, num_photos_pool=pool)
             self._cache[key] = TensorBatch(feed, n_ex, pin=self.pin)
         return self._cache[key]
 

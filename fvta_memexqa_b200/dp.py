@@ -1,0 +1,72 @@
+"""Data parallelism over the QA batch (north_star d): one process per GPU, every parameter
+replicated, rank r trains on its own shard of the batch, and the ONE flat fp32 gradient
+buffer (ParamStore.grad_flat) is sum-all-reduced by NCCL over NVLink once per step; the
+1/world_size factor that turns the sum of per-rank batch-means into the global batch-mean
+(model_v2.py:1090 reduce_mean) is folded into the Adadelta kernel's ``grad_scale``.
+
+The reference is single-device (model_v2.py:14); this is the only place the path shards
+(SURVEY section 8e).  Padded shapes must be pinned to the global batch maxima so that a
+G-GPU step equals the 1-GPU step on the concatenated batch.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class DataParallel:
+    def __init__(self, backend=None, device=None):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = device
+        if self.world_size > 1 and not dist.is_initialized():
+            if backend is None:
+                backend = "nccl" if torch.cuda.is_available() else "gloo"
+            if backend == "nccl":
+                torch.cuda.set_device(self.local_rank)
+                self.device = torch.device("cuda", self.local_rank)
+                dist.init_process_group(backend, device_id=self.device)
+            else:
+                dist.init_process_group(backend)
+
+    def shard(self, n_global):
+        """Half-open range of global sample indices this rank owns."""
+        per = n_global // self.world_size
+        rem = n_global % self.world_size
+        lo = self.rank * per + min(self.rank, rem)
+        return lo, lo + per + (1 if self.rank < rem else 0)
+
+    def all_reduce_grads(self, grad_flat):
+        """Sum-all-reduce the flat gradient buffer in place; returns the scale (1/world) the
+        optimizer must apply."""
+        if self.world_size > 1:
+            dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM)
+        return 1.0 / self.world_size
+
+    def mean_loss(self, loss):
+        return loss
+
+    def global_mean(self, t):
+        """All-reduced mean of a scalar tensor (reporting only)."""
+        if self.world_size > 1:
+            t = t.detach().clone()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t = t / self.world_size
+        return t
+
+    def broadcast_params(self, flat):
+        if self.world_size > 1:
+            dist.broadcast(flat, src=0)
+
+    def barrier(self):
+        if self.world_size > 1:
+            dist.barrier()
+
+    def max_over_ranks(self, value):
+        if self.world_size == 1:
+            return value
+        dev = self.device if self.device is not None else "cpu"
+        t = torch.tensor([value], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())

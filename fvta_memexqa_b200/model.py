@@ -243,12 +243,15 @@ class Model:
         ids = ids.long()
         table = v["emb/word/var/word_emb_mat"]
         # word table = concat(trainable [VW], fed GloVe) (model_v2.py:596) without the concat
+        # F.embedding, not advanced indexing: its backward is the sorted segmented reduction
+        # (plain index backward serialises on the heavily repeated ids)
+        emb = torch.nn.functional.embedding
         is_new = ids < VW
-        A = torch.where(is_new.unsqueeze(-1), table[ids.clamp(max=VW - 1)],
-                        glove[(ids - VW).clamp(min=0)])
+        A = torch.where(is_new.unsqueeze(-1), emb(ids.clamp(max=VW - 1), table),
+                        emb((ids - VW).clamp(min=0), glove))
         if not cfg.use_char:
             return A
-        Ac = v["emb/var/char_emb"][ids_c.long()]                       # [..., J, W, cdim]
+        Ac = emb(ids_c.long(), v["emb/var/char_emb"])                  # [..., J, W, cdim]
         if is_train and cfg.keep_prob < 1.0:                           # conv1d input dropout (:60-61)
             Ac = torch.nn.functional.dropout(Ac, 1.0 - cfg.keep_prob, True)
         filt = v["emb/conv/conv1d/filter"]                             # [1,5,cdim,cwdim]
@@ -291,7 +294,7 @@ class Model:
         if cfg.use_image_trans:
             feats = ops.linear(feats, v["emb/image/image_transform/image_trans_linear/W"],
                                v["emb/image/image_transform/image_trans_linear/b"], cfg.add_tanh)
-        xpis = feats[f["pis"].long()]
+        xpis = torch.nn.functional.embedding(f["pis"].long(), feats)
 
         hq, lq = self._read(x["q"], f["q_mask"], "text")
         hat, _ = self._read(x["at"], f["at_mask"], "text")

@@ -41,12 +41,61 @@ class Trainer:
         self.global_step = m.global_step
         return loss
 
+    # ---------------------------------------------------------------- CUDA-graph execution
+    def enable_graph(self, example_feed, warmup=3):
+        """Capture the whole device step (forward, backward, all-reduce, Adadelta) into one CUDA
+        graph over static input buffers.  At the reference shape the step is ~100 short kernels
+        and launch-latency bound, so replaying a graph is the difference between the GPU and
+        the Python interpreter setting the pace.  Requires pinned padded shapes: every later
+        batch must have exactly the shapes of ``example_feed``."""
+        m = self.model
+        self._static = {k: (v.clone() if isinstance(v, torch.Tensor) else v)
+                        for k, v in m.to_device(example_feed).items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._device_step(self._static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+        lib = _lib.load()
+        self._graph = torch.cuda.CUDAGraph()
+        n0 = lib.fvta_launch_count()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self._device_step(self._static)
+        self.launches_per_step = int(lib.fvta_launch_count() - n0)   # library kernels in the graph
+        m.global_step -= warmup + 1      # warm-up and capture do not count as training steps
+        # ...but they did move the weights: the caller snapshots/restores if that matters
+        self.global_step = m.global_step
+        return self
+
+    def _load_static(self, feed):
+        for k, v in feed.items():
+            dst = self._static.get(k)
+            if isinstance(dst, torch.Tensor):
+                if dst.shape != v.shape:
+                    raise ValueError("graph step: %s has shape %s, captured %s (pin the padded shapes)"
+                                     % (k, tuple(v.shape), tuple(dst.shape)))
+                dst.copy_(v, non_blocking=True)
+
+    def graph_step(self, feed):
+        """Replay the captured step on a new batch (host or device tensors).  Returns the loss
+        tensor (device)."""
+        self._load_static(feed)
+        self._graph.replay()
+        self.model.global_step += 1
+        self.global_step = self.model.global_step
+        return self._static_loss
+
     def step(self, sess, batch, get_summary=False):
         """trainer.py:30-40.  ``sess`` is accepted for signature parity (the reference asserts
         a tf.Session; here it is an opaque context and may be None)."""
         batchIdx, batch_data = batch
         feed = self.model.get_feed_dict(batch_data, is_train=True)
-        dfeed = self.model.to_device(feed)
-        loss = self._device_step(dfeed)
+        if getattr(self, "_graph", None) is not None:
+            loss = self.graph_step(feed)
+        else:
+            loss = self._device_step(self.model.to_device(feed))
         self.loss = loss
         return float(loss.detach()), None, None   # (loss, summary, train_op)

@@ -35,6 +35,8 @@ extern "C" {
 int fvta_version(void);
 /* Last CUDA error string seen by this library on the calling thread ("" if none). */
 const char* fvta_last_error(void);
+/* Kernels this library has launched in this process so far (diagnostic; bench.py's gpu_launches). */
+unsigned long long fvta_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Focal visual-text attention: time-warp gate + similarity + masks + two-level softmax +
