@@ -35,7 +35,7 @@ def window_count(T, warp_type, window_t=3.0, dtype=torch.float32):
     if warp_type == 4:
         return T - t
     if warp_type == 5:
-        w = float(int(math.ceil(float(window_t))))
+        w = float(int(math.ceil(float(window_t.detach() if hasattr(window_t, 'detach') else window_t))))
         return torch.clamp(t, max=w) + torch.clamp(T - 1 - t, max=w) + 1
     raise Exception("time warping type not implemented")
 

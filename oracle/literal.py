@@ -103,7 +103,7 @@ def time_indication_func(C, warp_type=1, window_t=3.0):
         return future * C, None
     if warp_type == 5:
         import math
-        w = int(math.ceil(float(window_t)))
+        w = int(math.ceil(float(window_t.detach() if hasattr(window_t, 'detach') else window_t)))
         win = matrix_band_part(T, w, w, C.dtype).unsqueeze(0).repeat(N, 1, 1)
         return win * C, window_t
     raise Exception("time warping type not implemented")

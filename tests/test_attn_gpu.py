@@ -159,3 +159,33 @@ def test_attn_bwd_parity(cuda_device, case):
             continue
         tol = max(TOL, 3.0 * rel_err(ref32[key], r))
         assert rel_err(gr[key], r) < tol, (key, rel_err(gr[key], r), tol)
+
+
+def test_attn_golden_c2(cuda_device):
+    """The committed golden vectors (tests/golden/attn_c2.npz, made by tools/make_golden.py from
+    the fp64 oracle) at the C2 shape: forward outputs and every gradient."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "attn_c2.npz"))
+    cfg, params, inp = attn_case(2, 6, 4, 64, 100, 25, seed=77)
+    inp = dict(inp, hall=torch.as_tensor(z["hall"]), hall_mask=torch.as_tensor(z["hall_mask"]),
+               hq=torch.as_tensor(z["hq"]), q_mask=torch.as_tensor(z["q_mask"]), lq=torch.as_tensor(z["lq"]))
+    for k in list(params):
+        if "param/" + k in z.files:
+            params[k] = torch.as_tensor(z["param/" + k])
+    out, p = run_gpu_fwd(cfg, params, inp, cuda_device, want_logits=True, want_c=True)
+    assert rel_err(out["g1_all"], torch.as_tensor(z["g1_all"])) < TOL
+    assert rel_err(out["c_col"], torch.as_tensor(z["c"])) < TOL
+    ref_a = torch.as_tensor(z["att_logits"]).double()
+    valid = (ref_a > -1e29).double()
+    assert rel_err(out["a_logits"].reshape(ref_a.shape), ref_a, valid) < TOL
+    gr = ops.attn_backward(out, torch.as_tensor(z["d_g1_all"]).float().to(cuda_device),
+                           p.get("attention/all/att_logits/W"), p.get("attention/all/att_logits/b"),
+                           p.get("time_warp/WH/W"), p.get("time_warp/WH/b"), p.get("time_warp/WC/W"),
+                           p.get("time_warp/WC/b"))
+    pairs = {"d_hall": z["d_hall"].reshape(2, 6, 256, 100), "d_hq": z["d_hq"], "d_lq": z["d_lq"],
+             "d_att_W": z["grad/attention/all/att_logits/W"], "d_att_b": z["grad/attention/all/att_logits/b"],
+             "d_WH_W": z["grad/time_warp/WH/W"], "d_WH_b": z["grad/time_warp/WH/b"],
+             "d_WC_W": z["grad/time_warp/WC/W"], "d_WC_b": z["grad/time_warp/WC/b"]}
+    for k, ref in pairs.items():
+        assert rel_err(gr[k], torch.as_tensor(ref).double()) < 2 * TOL, k
