@@ -122,10 +122,13 @@ __global__ void __launch_bounds__(256) attn_tile_bwd(
   }
   const float* st = stats + ((size_t)n * d.K + k) * kStatW;
   const float Mk = st[0], Lk = st[1], sk = st[2], tiesk = st[3];
+  const int amax_t = (int)st[5], amax_j = (int)st[6];
   const float* dr = drow + ((size_t)n * d.K + k) * 4;
   const float dsk = dr[0], rdr = dr[1], beta = dr[2];
   const float ml = d.time_warp_att ? m * g : m;
-  const float alpha = in_range ? expf(ml - Mk) / Lk : 0.f;
+  // a fully masked sequence has a uniform softmax over all T (the forward may encode that with
+  // denormal-scale weights; do not divide them here)
+  const float alpha = !in_range ? 0.f : (sk <= -1e29f ? 1.f / (float)d.T : expf(ml - Mk) / Lk);
   const float e = beta * hg;                 // h . d r_k
   const float dml = alpha * (g * e - rdr);   // softmax over T
   float dg = alpha * e;                      // r_k = sum alpha * g * h
@@ -145,7 +148,9 @@ __global__ void __launch_bounds__(256) attn_tile_bwd(
       const float a = row_logit(c1, acc[j], c0v, col_s[j], tanh_on, d.has_mask, mh && qm_s[j] != 0.f, th);
       float da = 0.f;
       if (a == m) da += dm_each;
-      if (a == sk) da += ds_each;
+      // a unique maximum is routed by the position the forward recorded (robust to the forward
+      // and this recompute using different arithmetic); ties are split by value equality
+      if (tiesk == 1.f ? (t == amax_t && j == amax_j) : (a == sk)) da += ds_each;
       dS = tanh_on ? da * (1.f - th * th) : da;
     }
     dSsum += dS;

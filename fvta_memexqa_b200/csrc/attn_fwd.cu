@@ -7,7 +7,7 @@
 //   attn_prep_coef / attn_prep_q : O(D*D + N*JQ*D)  parameter folding
 //   attn_tile_fwd                : one pass over hall -- gate, similarity, mask, tile softmax,
 //                                  tile weighted sum                     <- the HBM-bound kernel
-//   attn_combine_fwd             : merges tile partials, cross-sequence softmax, g1_all
+//   attn_combine_stats / _o      : merge tile partials, cross-sequence softmax, g1_all
 //
 // Math (as written in the reference, including its t1==t2 time-warp degeneracy):
 //   z[n,t]  = sum_k u.h[n,k,t]^2 + K*((b_WH+lq[n]).W_WC + b_WC),  u = W_WH[:D] @ W_WC
@@ -19,6 +19,7 @@
 //   s_k     = max_{t,j} a;  beta = softmax_k s;  g1_all = sum_k beta_k r_k
 #include "common.cuh"
 #include "attn_tile.cuh"
+#include <stdlib.h>
 
 namespace fvta {
 
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256) attn_tile_fwd(
   const bool mh = in_range && (!d.has_mask || hall_mask[((size_t)n * d.K + k) * d.T + t]);
   const bool tanh_on = d.add_tanh && d.simi != 4;
   float m = -INFINITY;
-  int rowcnt = 0;
+  int rowcnt = 0, jm = 0;
   float* arow = (a_logits != nullptr && in_range)
                     ? a_logits + (((size_t)n * d.K + k) * d.T + t) * d.JQ : nullptr;
 #pragma unroll
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(256) attn_tile_fwd(
       float th;
       const float a = row_logit(c1, acc[j], c0v, col_s[j], tanh_on, d.has_mask, mh && qm_s[j] != 0.f, th);
       if (arow) arow[j] = a;
-      if (a > m) { m = a; rowcnt = 1; }
+      if (a > m) { m = a; rowcnt = 1; jm = j; }
       else if (a == m) { rowcnt++; }
     }
   }
@@ -192,6 +193,11 @@ __global__ void __launch_bounds__(256) attn_tile_fwd(
   float smax_in = in_range ? m : -INFINITY;
   float smax = warp_max(smax_in);
   float ties = warp_sum((in_range && m == smax) ? (float)rowcnt : 0.f);
+  // position of the (first) maximum: lowest lane holding it
+  const unsigned hit = __ballot_sync(0xffffffffu, in_range && m == smax);
+  const int src = hit ? __ffs(hit) - 1 : 0;
+  const float am_t = (float)(t0 + src);
+  const float am_j = (float)__shfl_sync(0xffffffffu, jm, src);
   float ml = d.time_warp_att ? m * g : m;  // model_v2.py:269-275
   float mloc = in_range ? ml : -INFINITY;
   float M = warp_max(mloc);
@@ -199,8 +205,8 @@ __global__ void __launch_bounds__(256) attn_tile_fwd(
   float l = warp_sum(w);
   wg_s[threadIdx.x] = w * g;
   if (tt == 0) {
-    float* ps = part_stat + (((size_t)n * nt + tile) * d.K + k) * 4;
-    ps[0] = M; ps[1] = l; ps[2] = smax; ps[3] = ties;
+    float* ps = part_stat + (((size_t)n * nt + tile) * d.K + k) * kPartW;
+    ps[0] = M; ps[1] = l; ps[2] = smax; ps[3] = ties; ps[4] = am_t; ps[5] = am_j; ps[6] = 0.f; ps[7] = 0.f;
   }
   __syncwarp();
 
@@ -238,34 +244,36 @@ __global__ void __launch_bounds__(256) attn_tile_fwd(
 }
 
 // ---------------------------------------------------------------------------------------
-// combine: grid N, block K warps.  Merges the tile partials of each modality, then the
-// cross-sequence softmax and g1_all.  Saves stats for the backward.
+// combine, stage 1: grid N, block K warps.  Per modality: global max / sum of the tile
+// softmax partials, s_k and its tie count, then the cross-sequence softmax beta.
 // ---------------------------------------------------------------------------------------
-__global__ void attn_combine_fwd(FvtaAttnDesc d, const float* __restrict__ part_stat,
-                                 const float* __restrict__ part_o, float* __restrict__ g1_all,
-                                 float* __restrict__ stats, int nt, int Dp) {
-  extern __shared__ float sm[];
-  float* s_s = sm;            // [K]
-  float* beta_s = sm + 32;    // [K]
+__global__ void attn_combine_stats(FvtaAttnDesc d, const float* __restrict__ part_stat,
+                                   float* __restrict__ stats, int nt) {
+  __shared__ float s_s[32];
   const int n = blockIdx.x;
   const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* ps = part_stat + (size_t)n * nt * d.K * 4;
+  const float* ps = part_stat + (size_t)n * nt * d.K * kPartW;
   float M = -INFINITY, s = -INFINITY;
   for (int i = lane; i < nt; i += 32) {
-    const float* e = ps + ((size_t)i * d.K + k) * 4;
+    const float* e = ps + ((size_t)i * d.K + k) * kPartW;
     M = fmaxf(M, e[0]);
     s = fmaxf(s, e[2]);
   }
   M = warp_max(M);
   s = warp_max(s);
   float L = 0.f, ties = 0.f;
+  int first = 0x7fffffff;  // lowest tile holding the maximum -> its recorded position
   for (int i = lane; i < nt; i += 32) {
-    const float* e = ps + ((size_t)i * d.K + k) * 4;
+    const float* e = ps + ((size_t)i * d.K + k) * kPartW;
     L += e[1] * expf(e[0] - M);
-    if (e[2] == s) ties += e[3];
+    if (e[2] == s) { ties += e[3]; first = min(first, i); }
   }
   L = warp_sum(L);
   ties = warp_sum(ties);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+  const float* ef = ps + ((size_t)(first < nt ? first : 0) * d.K + k) * kPartW;
+  const float am_t = ef[4], am_j = ef[5];
   if (lane == 0) s_s[k] = s;
   __syncthreads();
   float smax = -INFINITY;
@@ -274,28 +282,54 @@ __global__ void attn_combine_fwd(FvtaAttnDesc d, const float* __restrict__ part_
   for (int kk = 0; kk < d.K; ++kk) den += expf(s_s[kk] - smax);
   const float beta = expf(s - smax) / den;
   if (lane == 0) {
-    beta_s[k] = beta;
     float* st = stats + ((size_t)n * d.K + k) * kStatW;
-    st[0] = M; st[1] = L; st[2] = s; st[3] = ties; st[4] = beta; st[5] = 0.f; st[6] = 0.f; st[7] = 0.f;
+    st[0] = M; st[1] = L; st[2] = s; st[3] = ties; st[4] = beta; st[5] = am_t; st[6] = am_j; st[7] = 0.f;
   }
-  // r_k[:] = sum_tiles o * exp(M_tile - M) / L
-  float* r = stats + attn_stats_r_offset(d) + ((size_t)n * d.K + k) * d.D;
-  const float invL = 1.f / L;
-  for (int c = lane; c < d.D; c += 32) {
+}
+
+// combine, stage 2: grid (ceil(D/32), N), block 32 x 8.  r_k[:] = sum_tiles o * exp(M_tile - M) / L
+// (lane = feature, the 8 warps stride over the tiles), then g1_all = sum_k beta_k r_k.
+__global__ void attn_combine_o(FvtaAttnDesc d, const float* __restrict__ part_stat,
+                               const float* __restrict__ part_o, float* __restrict__ g1_all,
+                               float* __restrict__ stats, int nt, int Dp) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* ps = part_stat + (size_t)n * nt * d.K * kPartW;
+  float g1 = 0.f;
+  for (int k = 0; k < d.K; ++k) {
+    const float* st = stats + ((size_t)n * d.K + k) * kStatW;
+    const float M = st[0], invL = 1.f / st[1], beta = st[4];
     float o = 0.f;
-    for (int i = 0; i < nt; ++i) {
-      const float sc = expf(ps[((size_t)i * d.K + k) * 4] - M);
-      o = fmaf(part_o[(((size_t)n * nt + i) * d.K + k) * Dp + c], sc, o);
+    if (c < d.D)
+      for (int i = w; i < nt; i += 8) {
+        const float sc = expf(ps[((size_t)i * d.K + k) * kPartW] - M);
+        o = fmaf(part_o[(((size_t)n * nt + i) * d.K + k) * Dp + c], sc, o);
+      }
+    red[w][lane] = o;
+    __syncthreads();
+    if (w == 0 && c < d.D) {
+      float r = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r += red[i][lane];
+      r *= invL;
+      stats[attn_stats_r_offset(d) + ((size_t)n * d.K + k) * d.D + c] = r;
+      g1 = fmaf(beta, r, g1);
     }
-    r[c] = o * invL;
+    __syncthreads();
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < d.D; c += blockDim.x) {
-    float o = 0.f;
-    for (int kk = 0; kk < d.K; ++kk)
-      o = fmaf(beta_s[kk], stats[attn_stats_r_offset(d) + ((size_t)n * d.K + kk) * d.D + c], o);
-    g1_all[(size_t)n * d.D + c] = o;
-  }
+  if (w == 0 && c < d.D) g1_all[(size_t)n * d.D + c] = g1;
+}
+
+int attn_combine_launch(const FvtaAttnDesc& d, const float* part_stat, const float* part_o, float* g1_all,
+                        float* stats, int nt, int Dp, cudaStream_t st) {
+  attn_combine_stats<<<d.N, d.K * 32, 0, st>>>(d, part_stat, stats, nt);
+  int rc = check_launch("attn_combine_stats");
+  if (rc) return rc;
+  dim3 grid((d.D + 31) / 32, d.N);
+  attn_combine_o<<<grid, 256, 0, st>>>(d, part_stat, part_o, g1_all, stats, nt, Dp);
+  return check_launch("attn_combine_o");
 }
 
 size_t attn_tile_smem_bytes(const FvtaAttnDesc& d, int JQP, int Dp) {
@@ -333,6 +367,17 @@ int attn_prep_launch(const FvtaAttnDesc& d, const AttnLayout& L, const FvtaAttnP
   return check_launch("attn_prep_q");
 }
 
+int attn_fwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hall, const uint8_t* hall_mask,
+                    const uint8_t* hq_mask, float* ws, float* g1_all, float* a_logits, float* c_col, float* stats,
+                    cudaStream_t st);
+
+// FVTA_FORCE_FFMA=1 pins the CUDA-core forward (A/B measurements, debugging)
+static bool fvta_force_ffma() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FVTA_FORCE_FFMA"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 }  // namespace fvta
 
 using namespace fvta;
@@ -367,6 +412,11 @@ extern "C" int fvta_attn_fwd(const FvtaAttnDesc* desc, const float* hall, const 
   float* ws = (float*)workspace;
   rc = attn_prep_launch(d, L, *params, hq, lq, ws, st);
   if (rc) return rc;
+  if (warp_h == nullptr && !fvta_force_ffma()) {
+    // tensor-core path (attn_fwd_tc.cu) when the shape/flags are covered; 1 = not covered
+    rc = attn_fwd_tc_try(d, L, hall, hall_mask, hq_mask, ws, g1_all, a_logits, c_col, stats, st);
+    if (rc <= 0) return rc;
+  }
   switch (L.JQP) {
     case 4: rc = launch_tile_fwd<1>(d, L, hall, hall_mask, hq_mask, ws, a_logits, c_col, warp_h, st); break;
     case 8: rc = launch_tile_fwd<2>(d, L, hall, hall_mask, hq_mask, ws, a_logits, c_col, warp_h, st); break;
@@ -377,7 +427,5 @@ extern "C" int fvta_attn_fwd(const FvtaAttnDesc* desc, const float* hall, const 
     default: return FVTA_E_SHAPE;
   }
   if (rc) return rc;
-  attn_combine_fwd<<<d.N, d.K * 32, 64 * sizeof(float), st>>>(d, ws + L.part_stat, ws + L.part_o, g1_all,
-                                                               stats, L.nt, L.Dp);
-  return check_launch("attn_combine_fwd");
+  return attn_combine_launch(d, ws + L.part_stat, ws + L.part_o, g1_all, stats, L.nt, L.Dp, st);
 }

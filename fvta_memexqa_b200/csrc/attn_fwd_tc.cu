@@ -1,0 +1,485 @@
+// Focal visual-text attention forward on the 5th-generation tensor cores (sm_100a only).
+//
+// Same math, same outputs and the same tile-partial / combine protocol as attn_fwd.cu, but the
+// question x context contraction P[t,j] = h[t,:] . qeff[j,:] -- the part that makes the FFMA
+// version compute-bound at JQ/2 = 16 flop/B -- runs as tcgen05.mma tiles with the accumulator
+// in TMEM, and the context tile arrives by TMA.  One pass over hall:
+//
+//   TMA warp      : 3-stage ring of fp32 context tiles  [K modalities x TB positions x D]
+//                   (cp.async.bulk.tensor.3d, mbarrier complete_tx)
+//   4 math warps  : one thread per context row.  pass 1: gate / row statistics and the split of
+//                   the row into fp16 (hi, lo*2^11) operands written in the 128B-swizzled K-major
+//                   layout UMMA reads;   epilogue: TMEM -> registers, logits, mask, row max,
+//                   softmax weight;   pass 2: weighted sum of the (still resident) fp32 tile
+//   MMA warp      : one elected thread issues, per 16-wide k-step,
+//                     D[:, 0:64] += A_hi . [B_hi ; B_lo]^T   and   D[:,64:96] += A_lo . B_hi^T
+//                   so P = D0 + (D1 + D2) * 2^-11 carries ~22 mantissa bits (fp32 accumulate):
+//                   the 1e-4 parity bar holds where single-pass tf32/bf16 would not.
+//
+// The softmax over T needs no online rescaling here: this kernel is used when the logits are
+// bounded by 1 (tanh or cosine), so exp(m - 1) cannot overflow and every tile uses the fixed
+// reference maximum 1.  Masked rows get the weight 2^-100 instead of exp(-1e30 - 1) = 0: it is
+// absorbed exactly by any unmasked weight and reproduces TF's uniform softmax over a fully
+// masked sequence.
+#include "common.cuh"
+#include "attn_tile.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+namespace fvta {
+
+int attn_combine_launch(const FvtaAttnDesc& d, const float* part_stat, const float* part_o, float* g1_all,
+                        float* stats, int nt, int Dp, cudaStream_t st);
+
+constexpr int kTcThreads = 192;  // warps 0-3 math, warp 4 TMA, warp 5 MMA
+constexpr int kTcStages = 3;
+constexpr int kTcJQP = 32;       // question positions per tile (N of the MMA = 64 + 32)
+constexpr int kTcTmemCols = 256; // 2 accumulator buffers x 128 columns (96 used)
+constexpr float kLoScale = 2048.f;
+constexpr float kMaskedWeight = 7.888609052210118e-31f;  // 2^-100
+
+struct TcPlan {
+  int TB;           // context positions per tile
+  int rows;         // K * TB <= 128
+  int KC;           // 64-wide fp16 K chunks (128-byte swizzle lines) = ceil(D / 64)
+  int ksteps;       // 16-wide MMA k-steps = ceil(D / 16)
+  int stage_bytes;  // fp32 tile, rounded to 128 B
+  int tiles;        // tiles per sample
+  int slabs;        // CTAs per sample
+  size_t smem;      // dynamic shared memory
+};
+
+__host__ __device__ inline size_t tc_smem_bytes(int KC, int stage_bytes, int Dp) {
+  size_t b = 1024;                                  // alignment slack
+  b += (size_t)2 * KC * 16384;                      // A_hi, A_lo
+  b += (size_t)KC * 8192;                           // [B_hi ; B_lo]
+  b += (size_t)kTcStages * stage_bytes;             // fp32 ring
+  b += (size_t)(3 * Dp + 2 * kTcJQP + 2 * 128 + 5 * 128) * sizeof(float);
+  b += 256;                                         // barriers, tmem pointer
+  return b;
+}
+
+static bool tc_make_plan(const FvtaAttnDesc& d, TcPlan& p) {
+  if ((d.D & 3) != 0 || d.D > 128 || d.D < 8 || d.JQ > kTcJQP || d.K > 8) return false;
+  const bool bounded = (d.simi == 4) || d.add_tanh;
+  if (!bounded || d.time_warp_att) return false;
+  p.KC = (d.D + 63) / 64;
+  p.ksteps = (d.D + 15) / 16;
+  for (int TB = 128 / d.K; TB >= 4; --TB) {
+    p.TB = TB;
+    p.rows = d.K * TB;
+    p.stage_bytes = round_up(p.rows * d.D * 4, 128);
+    p.smem = tc_smem_bytes(p.KC, p.stage_bytes, round_up(d.D, 4));
+    if (p.smem <= 227 * 1024) break;
+    p.TB = 0;
+  }
+  if (p.TB == 0) return false;
+  p.tiles = (d.T + p.TB - 1) / p.TB;
+  int want = (148 + d.N - 1) / d.N;  // one CTA per SM
+  p.slabs = want < 1 ? 1 : (want > p.tiles ? p.tiles : want);
+  return true;
+}
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+      "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzled operand: 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16, A/B = fp16 K-major, D = fp32, M = 128
+__device__ __forceinline__ uint32_t umma_idesc_f16(int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24); }
+
+// tanh(x) = 1 - 2 / (1 + e^{2x}); |error| < 1e-6, never exceeds 1 in magnitude
+__device__ __forceinline__ float tanh_bounded(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+// ---- B operand: [B_hi ; B_lo * 2^11] as fp16, pre-swizzled, one image per sample -------------
+__global__ void attn_prep_qb(FvtaAttnDesc d, const float* __restrict__ qeffT, __half* __restrict__ qB, int Dp,
+                             int JQP, int KC) {
+  const int n = blockIdx.x;
+  const float* q = qeffT + (size_t)n * Dp * JQP;
+  uint8_t* out = reinterpret_cast<uint8_t*>(qB) + (size_t)n * KC * 8192;
+  for (int i = threadIdx.x; i < KC * 64 * 8; i += blockDim.x) {
+    const int c = i & 7, row = (i >> 3) & 63, kc = i >> 9;
+    const int j = row & 31;
+    const bool lo = row >= 32;
+    __half v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int dd = kc * 64 + c * 8 + e;
+      const float x = (dd < d.D && j < d.JQ) ? q[(size_t)dd * JQP + j] : 0.f;
+      const __half hi = __float2half_rn(x);
+      v[e] = lo ? __float2half_rn((x - __half2float(hi)) * kLoScale) : hi;
+    }
+    *reinterpret_cast<uint4*>(out + kc * 8192 + row * 128 + ((c ^ (row & 7)) << 4)) = *reinterpret_cast<uint4*>(v);
+  }
+}
+
+// ---- the fused kernel: grid (slabs, N) ----------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
+    const __grid_constant__ CUtensorMap tmap, FvtaAttnDesc d, TcPlan pl, const uint8_t* __restrict__ hall_mask,
+    const uint8_t* __restrict__ hq_mask, const float* __restrict__ coef, const __half* __restrict__ qB,
+    const float* __restrict__ col, const float* __restrict__ zconst, float* __restrict__ a_logits,
+    float* __restrict__ c_col, float* __restrict__ part_stat, float* __restrict__ part_o, int Dp, int JQPg) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = a_hi + pl.KC * 16384;
+  uint8_t* b_s = a_lo + pl.KC * 16384;
+  uint8_t* ring = b_s + pl.KC * 8192;
+  float* coef_s = reinterpret_cast<float*>(ring + kTcStages * pl.stage_bytes);  // [3][Dp]
+  float* col_s = coef_s + 3 * Dp;      // [32]
+  float* qm_s = col_s + kTcJQP;        // [32]
+  float* zd_s = qm_s + kTcJQP;         // [128]
+  float* wg_s = zd_s + 128;            // [128]
+  float* red_s = wg_s + 128;           // [5][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red_s + 5 * 128);
+  uint64_t* full = bars;               // [3]
+  uint64_t* empty = bars + 3;          // [3]
+  uint64_t* a_ready = bars + 6;        // [1]
+  uint64_t* acc_full = bars + 7;       // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slab = blockIdx.x, n = blockIdx.y;
+  const int tile_begin = (int)(((long long)slab * pl.tiles) / pl.slabs);
+  const int tile_end = (int)(((long long)(slab + 1) * pl.tiles) / pl.slabs);
+  const int ntile = tile_end - tile_begin;
+  const int D = d.D, TB = pl.TB, rows = pl.rows;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 128); }
+    mbar_init(a_ready, 128);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(kTcTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // per-sample constants
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(qB) + (size_t)n * pl.KC * 8192);
+    uint4* dst = reinterpret_cast<uint4*>(b_s);
+    for (int i = threadIdx.x; i < pl.KC * 512; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < 3 * Dp; i += blockDim.x) coef_s[i] = coef[i];
+    for (int j = threadIdx.x; j < kTcJQP; j += blockDim.x) {
+      col_s[j] = j < JQPg ? col[(size_t)n * JQPg + j] : 0.f;
+      qm_s[j] = (j < d.JQ && (!d.has_mask || hq_mask[(size_t)n * d.JQ + j])) ? 1.f : 0.f;
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < ntile; ++i) {
+        const int s = i % kTcStages;
+        mbar_wait(&empty[s], ((i / kTcStages) & 1) ^ 1);
+        mbar_expect_tx(&full[s], (uint32_t)(rows * D * 4));
+        tma_load_3d(ring + s * pl.stage_bytes, &tmap, &full[s], 0, (tile_begin + i) * TB, n * d.K);
+      }
+    }
+  } else if (warp == 5) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc64 = umma_idesc_f16(64), idesc32 = umma_idesc_f16(32);
+      const uint32_t a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo), b_u = smem_u32(b_s);
+      for (int i = 0; i < ntile; ++i) {
+        mbar_wait(a_ready, i & 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)((i & 1) * 128);
+        for (int ks = 0; ks < pl.ksteps; ++ks) {
+          const uint32_t off = (uint32_t)((ks >> 2) * 16384 + (ks & 3) * 32);
+          const uint32_t boff = (uint32_t)((ks >> 2) * 8192 + (ks & 3) * 32);
+          umma_f16(acc, umma_desc_sw128(a_hi_u + off), umma_desc_sw128(b_u + boff), idesc64, ks > 0);
+          umma_f16(acc + 64, umma_desc_sw128(a_lo_u + off), umma_desc_sw128(b_u + boff), idesc32, ks > 0);
+        }
+        umma_commit(&acc_full[i & 1]);
+      }
+    }
+  } else {
+    // ===== math warps: thread r owns context row r = k*TB + tt of every tile =====
+    const int r = threadIdx.x;
+    const bool active = r < rows;
+    const int k = active ? r / TB : 0, tt = active ? r - k * TB : 0;
+    const bool tanh_on = d.add_tanh && d.simi != 4;
+    const int D4 = D >> 2;
+    const int npair = d.K * D4;
+    float4 o_acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o_acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l_acc = 0.f, smax = -INFINITY, ties = 0.f, am_t = 0.f, am_j = 0.f;
+    // state of the tile whose epilogue is pending
+    float p_c1 = 0.f, p_c0 = 0.f, p_g = 0.f;
+    int p_t = 0;
+
+    auto epilogue = [&](int i) {
+      const int s = i % kTcStages;
+      const float* tile = reinterpret_cast<const float*>(ring + s * pl.stage_bytes);
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((i & 1) * 128);
+      float P[32];
+      {
+        float x[32], y[32];
+        tmem_ld32(taddr + 32, x);
+        tmem_ld32(taddr + 64, y);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = (x[j] + y[j]) * (1.f / kLoScale);
+        tmem_ld32(taddr, P);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) P[j] += x[j];
+      }
+      const int t = p_t;
+      const bool in_range = active && t < d.T;
+      const bool mh = in_range && (!d.has_mask || hall_mask[((size_t)n * d.K + k) * d.T + t]);
+      float m = -INFINITY;
+      int rowcnt = 0, jm = 0;
+      float* arow = (a_logits != nullptr && in_range) ? a_logits + (((size_t)n * d.K + k) * d.T + t) * d.JQ : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < d.JQ) {
+          const float S = fmaf(p_c1, P[j], p_c0) + col_s[j];
+          const float th = tanh_on ? tanh_bounded(S) : S;
+          float a = th;
+          if (d.has_mask) a = a + ((mh && qm_s[j] != 0.f) ? 0.f : 1.f) * FVTA_VERY_NEGATIVE;
+          if (arow) arow[j] = a;
+          if (a > m) { m = a; rowcnt = 1; jm = j; }
+          else if (a == m) { rowcnt++; }
+        }
+      }
+      float w = 0.f;
+      if (in_range) {
+        if (m > smax) { smax = m; ties = (float)rowcnt; am_t = (float)t; am_j = (float)jm; }
+        else if (m == smax) { ties += (float)rowcnt; }
+        w = (m <= -1e29f) ? kMaskedWeight : expf(m - 1.f);
+        l_acc += w;
+      }
+      wg_s[r] = w * p_g;
+      tc_fence_before();
+      named_bar_sync(2, 128);
+      // pass 2: o[k2][d4] += sum_tt w*g*h
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int p = r + q * 128;
+        if (p < npair) {
+          const int k2 = p / D4, d4 = p - k2 * D4;
+          const float* hp = tile + (size_t)k2 * TB * D + d4 * 4;
+          const float* wp = wg_s + k2 * TB;
+          float4 o = o_acc[q];
+          for (int t2 = 0; t2 < TB; ++t2) {
+            const float4 hv = *reinterpret_cast<const float4*>(hp + (size_t)t2 * D);
+            const float ww = wp[t2];
+            o.x = fmaf(ww, hv.x, o.x); o.y = fmaf(ww, hv.y, o.y);
+            o.z = fmaf(ww, hv.z, o.z); o.w = fmaf(ww, hv.w, o.w);
+          }
+          o_acc[q] = o;
+        }
+      }
+      mbar_arrive(&empty[s]);
+    };
+
+    for (int i = 0; i < ntile; ++i) {
+      const int s = i % kTcStages;
+      mbar_wait(&full[s], (i / kTcStages) & 1);
+      if (i >= 1) {
+        mbar_wait(&acc_full[(i - 1) & 1], ((i - 1) >> 1) & 1);  // MMA(i-1) done: A is free, acc(i-1) ready
+        tc_fence_after();
+      }
+      // ---- pass 1: row statistics + fp16 hi/lo split into the swizzled A tiles ----
+      float zdot = 0.f, lin = 0.f, quad = 0.f;
+      if (active) {
+        const float* hrow = reinterpret_cast<const float*>(ring + s * pl.stage_bytes) + (size_t)r * D;
+        const int nch = pl.ksteps * 2;  // 16-byte (8 x fp16) chunks the MMA will read
+        for (int c = 0; c < nch; ++c) {
+          float x[8];
+          const int d0 = c * 8;
+          if (d0 < D) {
+            const float4 v = *reinterpret_cast<const float4*>(hrow + d0);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+          } else { x[0] = x[1] = x[2] = x[3] = 0.f; }
+          if (d0 + 4 < D) {
+            const float4 v = *reinterpret_cast<const float4*>(hrow + d0 + 4);
+            x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+          } else { x[4] = x[5] = x[6] = x[7] = 0.f; }
+          __half hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float xv = x[e];
+            if (d0 + e < D) {
+              const float x2 = xv * xv;
+              zdot = fmaf(coef_s[d0 + e], x2, zdot);
+              lin = fmaf(coef_s[Dp + d0 + e], xv, lin);
+              quad = fmaf(coef_s[2 * Dp + d0 + e], x2, quad);
+            }
+            hi[e] = __float2half_rn(xv);
+            lo[e] = __float2half_rn((xv - __half2float(hi[e])) * kLoScale);
+          }
+          const uint32_t off = (uint32_t)((c >> 3) * 16384 + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(a_hi + off) = *reinterpret_cast<uint4*>(hi);
+          *reinterpret_cast<uint4*>(a_lo + off) = *reinterpret_cast<uint4*>(lo);
+        }
+      }
+      zd_s[r] = zdot;
+      named_bar_sync(1, 128);
+      const int t = (tile_begin + i) * TB + tt;
+      float g = 1.f;
+      if (d.use_time_warp && active) {
+        float z = zconst[n];
+        for (int kk = 0; kk < d.K; ++kk) z += zd_s[kk * TB + tt];
+        float tz, cnt;
+        g = gate_from_z(d, z, t < d.T ? t : d.T - 1, tz, cnt);
+        if (c_col != nullptr && k == 0 && t < d.T) c_col[(size_t)n * d.T + t] = tz;
+      }
+      float c1, c0v;
+      row_coefs(d, g, lin, quad, c1, c0v);
+      fence_async_smem();   // A tiles were written through the generic proxy; UMMA reads via the async proxy
+      tc_fence_before();
+      mbar_arrive(a_ready);
+      if (i >= 1) epilogue(i - 1);
+      p_c1 = c1; p_c0 = c0v; p_g = g; p_t = t;
+    }
+    if (ntile > 0) {
+      mbar_wait(&acc_full[(ntile - 1) & 1], ((ntile - 1) >> 1) & 1);
+      tc_fence_after();
+      epilogue(ntile - 1);
+    }
+    // ---- slab partials: per-modality reductions over the TB row-owning threads ----
+    red_s[r] = l_acc; red_s[128 + r] = smax; red_s[256 + r] = ties; red_s[384 + r] = am_t; red_s[512 + r] = am_j;
+    named_bar_sync(1, 128);
+    if (r < d.K) {
+      float l = 0.f, sm = -INFINITY, ti = 0.f, at = 0.f, aj = 0.f;
+      for (int t2 = 0; t2 < TB; ++t2) {
+        const int rr = r * TB + t2;
+        l += red_s[rr];
+        const float v = red_s[128 + rr];
+        if (v > sm) { sm = v; ti = red_s[256 + rr]; at = red_s[384 + rr]; aj = red_s[512 + rr]; }
+        else if (v == sm) {
+          ti += red_s[256 + rr];
+          if (red_s[384 + rr] < at) { at = red_s[384 + rr]; aj = red_s[512 + rr]; }
+        }
+      }
+      float* ps = part_stat + (((size_t)n * pl.slabs + slab) * d.K + r) * kPartW;
+      ps[0] = 1.f; ps[1] = l; ps[2] = sm; ps[3] = ti; ps[4] = at; ps[5] = aj; ps[6] = 0.f; ps[7] = 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int p = r + q * 128;
+      if (p < npair) {
+        const int k2 = p / D4, d4 = p - k2 * D4;
+        *reinterpret_cast<float4*>(part_o + (((size_t)n * pl.slabs + slab) * d.K + k2) * Dp + d4 * 4) = o_acc[q];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// Returns FVTA_OK if it ran, 1 if this shape/flag combination is not covered (caller uses the
+// FFMA kernel), or a negative error.
+int attn_fwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hall, const uint8_t* hall_mask,
+                    const uint8_t* hq_mask, float* ws, float* g1_all, float* a_logits, float* c_col, float* stats,
+                    cudaStream_t st) {
+  TcPlan pl;
+  if (!tc_make_plan(d, pl)) return 1;
+  if (pl.slabs > L.nt) return 1;  // partial buffers are sized for ceil(T/32) tiles per sample
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) return 1;
+  CUtensorMap tmap;
+  cuuint64_t gdim[3] = {(cuuint64_t)d.D, (cuuint64_t)d.T, (cuuint64_t)d.N * d.K};
+  cuuint64_t gstr[2] = {(cuuint64_t)d.D * 4, (cuuint64_t)d.T * d.D * 4};
+  cuuint32_t box[3] = {(cuuint32_t)d.D, (cuuint32_t)pl.TB, (cuuint32_t)d.K};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(hall), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return 1;
+  __half* qB = reinterpret_cast<__half*>(ws + L.qB);
+  attn_prep_qb<<<d.N, 256, 0, st>>>(d, ws + L.qeffT, qB, L.Dp, L.JQP, pl.KC);
+  int rc = check_launch("attn_prep_qb");
+  if (rc) return rc;
+  cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  if (e != cudaSuccess) { set_last_error("attn_fwd_tc smem attr", e); return FVTA_E_LAUNCH; }
+  dim3 grid(pl.slabs, d.N);
+  attn_fwd_tc<<<grid, kTcThreads, pl.smem, st>>>(tmap, d, pl, hall_mask, hq_mask, ws + L.coef, qB, ws + L.col,
+                                                 ws + L.zconst, a_logits, c_col, ws + L.part_stat, ws + L.part_o,
+                                                 L.Dp, L.JQP);
+  rc = check_launch("attn_fwd_tc");
+  if (rc) return rc;
+  return attn_combine_launch(d, ws + L.part_stat, ws + L.part_o, g1_all, stats, pl.slabs, L.Dp, st);
+}
+
+}  // namespace fvta

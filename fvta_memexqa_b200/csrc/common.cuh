@@ -72,7 +72,8 @@ __host__ __device__ inline float window_count(int t, int T, int warp_type, int w
 // ---------------------------------------------------------------------------------------
 constexpr int kAttnTT = 32;      // context positions per CTA tile (one warp lane per position)
 constexpr int kAttnMaxDC = 128;  // D is streamed through shared memory in chunks of <= 128
-constexpr int kStatW = 8;        // floats per (n,k) in stats: M, L, s, ties, beta, pad
+constexpr int kStatW = 8;        // floats per (n,k) in stats: M, L, s, ties, beta, argmax t, argmax j, pad
+constexpr int kPartW = 8;        // floats per tile partial: M, l, s, ties, argmax t, argmax j, pad
 
 struct AttnLayout {
   int nt;    // tiles per sample = ceil(T / kAttnTT)
@@ -83,7 +84,7 @@ struct AttnLayout {
   size_t qeffT;      // [N][Dp][JQP] effective question operand, transposed (d-major)
   size_t col;        // [N][JQP]     per-question-word term + bias
   size_t zconst;     // [N]          K*((b_WH+lq).W_WC + b_WC)
-  size_t part_stat;  // [N][nt][K][4] tile partials: M, l, smax, ties
+  size_t part_stat;  // [N][nt][K][kPartW] tile partials: M, l, smax, ties, argmax (t, j)
   size_t part_o;     // [N][nt][K][Dp] tile partial weighted sums
   // backward scratch
   size_t dqeffT;     // [N][Dp][JQP]
@@ -93,6 +94,7 @@ struct AttnLayout {
   size_t drow;       // [N][K][4]    per-(n,k) scalars the backward needs (ds, rdotdr, ...)
   size_t du;         // [Dp]         d u summed over samples
   size_t scal;       // [4]          sum_n dzc, d att_b
+  size_t qB;         // [N][ceil(D/64)][64][64] fp16: tensor-core B operand image (8 KB per chunk)
   size_t total;      // floats
 };
 
@@ -118,7 +120,7 @@ __host__ __device__ inline AttnLayout attn_layout(const FvtaAttnDesc& d) {
   L.qeffT = take((size_t)d.N * L.Dp * L.JQP);
   L.col = take((size_t)d.N * L.JQP);
   L.zconst = take((size_t)d.N);
-  L.part_stat = take((size_t)d.N * L.nt * d.K * 4);
+  L.part_stat = take((size_t)d.N * L.nt * d.K * kPartW);
   L.part_o = take((size_t)d.N * L.nt * d.K * L.Dp);
   L.dqeffT = take((size_t)d.N * L.Dp * L.JQP);
   L.dcol = take((size_t)d.N * L.JQP);
@@ -127,6 +129,7 @@ __host__ __device__ inline AttnLayout attn_layout(const FvtaAttnDesc& d) {
   L.drow = take((size_t)d.N * d.K * 4);
   L.du = take((size_t)L.Dp);
   L.scal = take(4);
+  L.qB = take((size_t)d.N * ((d.D + 63) / 64) * 2048);
   L.total = o;
   return L;
 }
