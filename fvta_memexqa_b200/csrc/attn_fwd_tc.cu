@@ -171,8 +171,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     const uint8_t* __restrict__ hq_mask, const float* __restrict__ coef, const __half* __restrict__ qB,
     const float* __restrict__ col, const float* __restrict__ zconst, float* __restrict__ a_logits,
     float* __restrict__ c_col, float* __restrict__ part_stat, float* __restrict__ part_o, int Dp, int JQPg) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment is what the 128B swizzle pattern is defined against; keeping the pointers
+  // derived from the __shared__ symbol (no integer round-trip) lets ptxas emit LDS/STS, not LD/ST
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* a_hi = smem;
   uint8_t* a_lo = a_hi + pl.KC * 16384;
   uint8_t* b_s = a_lo + pl.KC * 16384;
@@ -260,6 +262,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     const bool active = r < rows;
     const int k = active ? r / TB : 0, tt = active ? r - k * TB : 0;
     const bool tanh_on = d.add_tanh && d.simi != 4;
+    uint32_t qbits = 0u;   // question mask as a bit per position
+    for (int j = 0; j < kTcJQP; ++j) qbits |= (qm_s[j] != 0.f ? 1u : 0u) << j;
     const int D4 = D >> 2;
     const int npair = d.K * D4;
     float4 o_acc[4];
@@ -288,19 +292,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       const int t = p_t;
       const bool in_range = active && t < d.T;
       const bool mh = in_range && (!d.has_mask || hall_mask[((size_t)n * d.K + k) * d.T + t]);
+      // branch-free logits: P[] is overwritten by the masked logits a[]
+      const uint32_t valid_bits = mh ? qbits : 0u;
       float m = -INFINITY;
-      int rowcnt = 0, jm = 0;
-      float* arow = (a_logits != nullptr && in_range) ? a_logits + (((size_t)n * d.K + k) * d.T + t) * d.JQ : nullptr;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < d.JQ) {
-          const float S = fmaf(p_c1, P[j], p_c0) + col_s[j];
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 cj = *reinterpret_cast<const float4*>(col_s + j4 * 4);
+        const float cc[4] = {cj.x, cj.y, cj.z, cj.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = j4 * 4 + e;
+          const float S = fmaf(p_c1, P[j], p_c0) + cc[e];
           const float th = tanh_on ? tanh_bounded(S) : S;
           float a = th;
-          if (d.has_mask) a = a + ((mh && qm_s[j] != 0.f) ? 0.f : 1.f) * FVTA_VERY_NEGATIVE;
-          if (arow) arow[j] = a;
-          if (a > m) { m = a; rowcnt = 1; jm = j; }
-          else if (a == m) { rowcnt++; }
+          if (d.has_mask) a = ((valid_bits >> j) & 1u) ? th : th + FVTA_VERY_NEGATIVE;  // exp_mask in fp32
+          a = (j < d.JQ) ? a : -INFINITY;                                              // padding columns
+          P[j] = a;
+          m = fmaxf(m, a);
+        }
+      }
+      int rowcnt = 0, jm = 31;
+#pragma unroll
+      for (int j = 31; j >= 0; --j) {
+        const bool hit = P[j] == m;
+        rowcnt += hit ? 1 : 0;
+        jm = hit ? j : jm;
+      }
+      if (a_logits != nullptr && in_range) {
+        float* arow = a_logits + (((size_t)n * d.K + k) * d.T + t) * d.JQ;
+        if ((d.JQ & 3) == 0) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            if (j4 * 4 < d.JQ)
+              *reinterpret_cast<float4*>(arow + j4 * 4) = make_float4(P[j4 * 4], P[j4 * 4 + 1], P[j4 * 4 + 2], P[j4 * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < d.JQ) arow[j] = P[j];
         }
       }
       float w = 0.f;
@@ -345,34 +373,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       float zdot = 0.f, lin = 0.f, quad = 0.f;
       if (active) {
         const float* hrow = reinterpret_cast<const float*>(ring + s * pl.stage_bytes) + (size_t)r * D;
-        const int nch = pl.ksteps * 2;  // 16-byte (8 x fp16) chunks the MMA will read
-        for (int c = 0; c < nch; ++c) {
-          float x[8];
-          const int d0 = c * 8;
-          if (d0 < D) {
-            const float4 v = *reinterpret_cast<const float4*>(hrow + d0);
-            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-          } else { x[0] = x[1] = x[2] = x[3] = 0.f; }
-          if (d0 + 4 < D) {
-            const float4 v = *reinterpret_cast<const float4*>(hrow + d0 + 4);
-            x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
-          } else { x[4] = x[5] = x[6] = x[7] = 0.f; }
-          __half hi[8], lo[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float xv = x[e];
-            if (d0 + e < D) {
-              const float x2 = xv * xv;
-              zdot = fmaf(coef_s[d0 + e], x2, zdot);
-              lin = fmaf(coef_s[Dp + d0 + e], xv, lin);
-              quad = fmaf(coef_s[2 * Dp + d0 + e], x2, quad);
-            }
-            hi[e] = __float2half_rn(xv);
-            lo[e] = __float2half_rn((xv - __half2float(hi[e])) * kLoScale);
-          }
-          const uint32_t off = (uint32_t)((c >> 3) * 16384 + r * 128 + (((c & 7) ^ (r & 7)) << 4));
-          *reinterpret_cast<uint4*>(a_hi + off) = *reinterpret_cast<uint4*>(hi);
-          *reinterpret_cast<uint4*>(a_lo + off) = *reinterpret_cast<uint4*>(lo);
+        uint8_t* ahi_row = a_hi + r * 128;
+        uint8_t* alo_row = a_lo + r * 128;
+        const int nch = pl.ksteps * 2;   // 16-byte (8 x fp16) chunks the MMA will read
+        const int nfull = D >> 3;        // chunks with 8 real features
+        auto split_store = [&](int c, const float4& v0, const float4& v1) {
+          const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
+          const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+          const __half2 l0 = __floats2half2_rn((v0.x - f0.x) * kLoScale, (v0.y - f0.y) * kLoScale);
+          const __half2 l1 = __floats2half2_rn((v0.z - f1.x) * kLoScale, (v0.w - f1.y) * kLoScale);
+          const __half2 l2 = __floats2half2_rn((v1.x - f2.x) * kLoScale, (v1.y - f2.y) * kLoScale);
+          const __half2 l3 = __floats2half2_rn((v1.z - f3.x) * kLoScale, (v1.w - f3.y) * kLoScale);
+          const uint32_t off = (uint32_t)((c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4));
+          uint4 ph, plo;
+          ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+          ph.z = *reinterpret_cast<const uint32_t*>(&h2); ph.w = *reinterpret_cast<const uint32_t*>(&h3);
+          plo.x = *reinterpret_cast<const uint32_t*>(&l0); plo.y = *reinterpret_cast<const uint32_t*>(&l1);
+          plo.z = *reinterpret_cast<const uint32_t*>(&l2); plo.w = *reinterpret_cast<const uint32_t*>(&l3);
+          *reinterpret_cast<uint4*>(ahi_row + off) = ph;
+          *reinterpret_cast<uint4*>(alo_row + off) = plo;
+        };
+        auto stats4 = [&](int d0, const float4& v) {
+          const float4 cu = *reinterpret_cast<const float4*>(coef_s + d0);
+          const float4 cl = *reinterpret_cast<const float4*>(coef_s + Dp + d0);
+          const float4 cq = *reinterpret_cast<const float4*>(coef_s + 2 * Dp + d0);
+          const float x2 = v.x * v.x, y2 = v.y * v.y, z2 = v.z * v.z, w2 = v.w * v.w;
+          zdot = fmaf(cu.x, x2, zdot); zdot = fmaf(cu.y, y2, zdot); zdot = fmaf(cu.z, z2, zdot); zdot = fmaf(cu.w, w2, zdot);
+          lin = fmaf(cl.x, v.x, lin); lin = fmaf(cl.y, v.y, lin); lin = fmaf(cl.z, v.z, lin); lin = fmaf(cl.w, v.w, lin);
+          quad = fmaf(cq.x, x2, quad); quad = fmaf(cq.y, y2, quad); quad = fmaf(cq.z, z2, quad); quad = fmaf(cq.w, w2, quad);
+        };
+#pragma unroll 2
+        for (int c = 0; c < nfull; ++c) {
+          const float4 v0 = *reinterpret_cast<const float4*>(hrow + c * 8);
+          const float4 v1 = *reinterpret_cast<const float4*>(hrow + c * 8 + 4);
+          stats4(c * 8, v0);
+          stats4(c * 8 + 4, v1);
+          split_store(c, v0, v1);
+        }
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = nfull; c < nch; ++c) {  // D % 8 == 4 leaves a half chunk; the rest is zero padding
+          float4 v0 = zero4;
+          if (c * 8 < D) { v0 = *reinterpret_cast<const float4*>(hrow + c * 8); stats4(c * 8, v0); }
+          split_store(c, v0, zero4);
         }
       }
       zd_s[r] = zdot;
