@@ -31,7 +31,7 @@ namespace fvta {
 int attn_combine_launch(const FvtaAttnDesc& d, const float* part_stat, const float* part_o, float* g1_all,
                         float* stats, int nt, int Dp, cudaStream_t st);
 
-constexpr int kTcThreads = 192;  // warps 0-3 math, warp 4 TMA, warp 5 MMA
+constexpr int kTcThreads = 320;  // warps 0-3 split, 4-7 softmax, warp 8 TMA, warp 9 MMA
 constexpr int kTcStages = 3;
 constexpr int kTcJQP = 32;       // question positions per tile (N of the MMA = 64 + 32)
 constexpr int kTcTmemCols = 256; // 2 accumulator buffers x 128 columns (96 used)
@@ -54,7 +54,7 @@ __host__ __device__ inline size_t tc_smem_bytes(int KC, int stage_bytes, int Dp)
   b += (size_t)2 * KC * 16384;                      // A_hi, A_lo
   b += (size_t)KC * 8192;                           // [B_hi ; B_lo]
   b += (size_t)kTcStages * stage_bytes;             // fp32 ring
-  b += (size_t)(3 * Dp + 2 * kTcJQP + 2 * 128 + 5 * 128) * sizeof(float);
+  b += (size_t)(3 * Dp + 2 * kTcJQP + 128 + 256 + 4 * 256 + 5 * 128) * sizeof(float);
   b += 256;                                         // barriers, tmem pointer
   return b;
 }
@@ -166,6 +166,10 @@ __global__ void attn_prep_qb(FvtaAttnDesc d, const float* __restrict__ qeffT, __
 }
 
 // ---- the fused kernel: grid (slabs, N) ----------------------------------------------------------
+// warps 0-3  "split"   : pass 1 of tile i+1 (row statistics, gate, fp16 hi/lo operands)
+// warps 4-7  "softmax" : epilogue + pass 2 of tile i (TMEM lanes 32*(warp%4)..)
+// warp  8    TMA producer,  warp 9  MMA issuer (+ TMEM allocation)
+template <bool HAS_LIN>
 __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     const __grid_constant__ CUtensorMap tmap, FvtaAttnDesc d, TcPlan pl, const uint8_t* __restrict__ hall_mask,
     const uint8_t* __restrict__ hq_mask, const float* __restrict__ coef, const __half* __restrict__ qB,
@@ -182,15 +186,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   float* coef_s = reinterpret_cast<float*>(ring + kTcStages * pl.stage_bytes);  // [3][Dp]
   float* col_s = coef_s + 3 * Dp;      // [32]
   float* qm_s = col_s + kTcJQP;        // [32]
-  float* zd_s = qm_s + kTcJQP;         // [128]
-  float* wg_s = zd_s + 128;            // [128]
-  float* red_s = wg_s + 128;           // [5][128]
+  float* zd_s = qm_s + kTcJQP;         // [128]   gate dots of the tile being split
+  float* wg_s = zd_s + 128;            // [2][128] softmax weight * gate
+  float4* st_s = reinterpret_cast<float4*>(wg_s + 256);  // [2][128] (c1, c0, g, -) per row
+  float* red_s = reinterpret_cast<float*>(st_s + 256);   // [5][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(red_s + 5 * 128);
-  uint64_t* full = bars;               // [3]
-  uint64_t* empty = bars + 3;          // [3]
-  uint64_t* a_ready = bars + 6;        // [1]
-  uint64_t* acc_full = bars + 7;       // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* full = bars;               // [3]  TMA -> split, softmax
+  uint64_t* empty = bars + 3;          // [3]  softmax -> TMA
+  uint64_t* a_ready = bars + 6;        // [1]  split -> MMA
+  uint64_t* acc_full = bars + 7;       // [2]  MMA -> split (A free), softmax (accumulator ready)
+  uint64_t* st_ready = bars + 9;       // [2]  split -> softmax (row coefficients)
+  uint64_t* ep_done = bars + 11;       // [2]  softmax -> split (accumulator + coefficient buffer free)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab = blockIdx.x, n = blockIdx.y;
@@ -202,11 +209,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 128); }
     mbar_init(a_ready, 128);
-    mbar_init(&acc_full[0], 1);
-    mbar_init(&acc_full[1], 1);
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(&acc_full[b2], 1); mbar_init(&st_ready[b2], 128); mbar_init(&ep_done[b2], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                  "r"(kTcTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===== TMA producer =====
     if (lane == 0) {
       for (int i = 0; i < ntile; ++i) {
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         tma_load_3d(ring + s * pl.stage_bytes, &tmap, &full[s], 0, (tile_begin + i) * TB, n * d.K);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc64 = umma_idesc_f16(64), idesc32 = umma_idesc_f16(32);
@@ -256,9 +262,89 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         umma_commit(&acc_full[i & 1]);
       }
     }
-  } else {
-    // ===== math warps: thread r owns context row r = k*TB + tt of every tile =====
+  } else if (warp < 4) {
+    // ===== split warps: thread r owns context row r = k*TB + tt =====
     const int r = threadIdx.x;
+    const bool active = r < rows;
+    const int k = active ? r / TB : 0, tt = active ? r - k * TB : 0;
+    for (int i = 0; i < ntile; ++i) {
+      const int s = i % kTcStages;
+      mbar_wait(&full[s], (i / kTcStages) & 1);
+      if (i >= 1) mbar_wait(&acc_full[(i - 1) & 1], ((i - 1) >> 1) & 1);   // MMA(i-1) has read A
+      if (i >= 2) mbar_wait(&ep_done[i & 1], ((i - 2) >> 1) & 1);          // softmax(i-2) released buffer i&1
+      float zdot = 0.f, lin = 0.f, quad = 0.f;
+      if (active) {
+        const float* hrow = reinterpret_cast<const float*>(ring + s * pl.stage_bytes) + (size_t)r * D;
+        uint8_t* ahi_row = a_hi + r * 128;
+        uint8_t* alo_row = a_lo + r * 128;
+        const int nch = pl.ksteps * 2;   // 16-byte (8 x fp16) chunks the MMA will read
+        const int nfull = D >> 3;        // chunks with 8 real features
+        auto split_store = [&](int c, const float4& v0, const float4& v1) {
+          const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
+          const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+          const __half2 l0 = __floats2half2_rn((v0.x - f0.x) * kLoScale, (v0.y - f0.y) * kLoScale);
+          const __half2 l1 = __floats2half2_rn((v0.z - f1.x) * kLoScale, (v0.w - f1.y) * kLoScale);
+          const __half2 l2 = __floats2half2_rn((v1.x - f2.x) * kLoScale, (v1.y - f2.y) * kLoScale);
+          const __half2 l3 = __floats2half2_rn((v1.z - f3.x) * kLoScale, (v1.w - f3.y) * kLoScale);
+          const uint32_t off = (uint32_t)((c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4));
+          uint4 ph, plo;
+          ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+          ph.z = *reinterpret_cast<const uint32_t*>(&h2); ph.w = *reinterpret_cast<const uint32_t*>(&h3);
+          plo.x = *reinterpret_cast<const uint32_t*>(&l0); plo.y = *reinterpret_cast<const uint32_t*>(&l1);
+          plo.z = *reinterpret_cast<const uint32_t*>(&l2); plo.w = *reinterpret_cast<const uint32_t*>(&l3);
+          *reinterpret_cast<uint4*>(ahi_row + off) = ph;
+          *reinterpret_cast<uint4*>(alo_row + off) = plo;
+        };
+        auto stats4 = [&](int d0, const float4& v) {
+          const float4 cu = *reinterpret_cast<const float4*>(coef_s + d0);
+          const float4 cq = *reinterpret_cast<const float4*>(coef_s + 2 * Dp + d0);
+          const float x2 = v.x * v.x, y2 = v.y * v.y, z2 = v.z * v.z, w2 = v.w * v.w;
+          zdot = fmaf(cu.x, x2, zdot); zdot = fmaf(cu.y, y2, zdot); zdot = fmaf(cu.z, z2, zdot); zdot = fmaf(cu.w, w2, zdot);
+          quad = fmaf(cq.x, x2, quad); quad = fmaf(cq.y, y2, quad); quad = fmaf(cq.z, z2, quad); quad = fmaf(cq.w, w2, quad);
+          if (HAS_LIN) {
+            const float4 cl = *reinterpret_cast<const float4*>(coef_s + Dp + d0);
+            lin = fmaf(cl.x, v.x, lin); lin = fmaf(cl.y, v.y, lin); lin = fmaf(cl.z, v.z, lin); lin = fmaf(cl.w, v.w, lin);
+          }
+        };
+#pragma unroll 2
+        for (int c = 0; c < nfull; ++c) {
+          const float4 v0 = *reinterpret_cast<const float4*>(hrow + c * 8);
+          const float4 v1 = *reinterpret_cast<const float4*>(hrow + c * 8 + 4);
+          stats4(c * 8, v0);
+          stats4(c * 8 + 4, v1);
+          split_store(c, v0, v1);
+        }
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = nfull; c < nch; ++c) {  // D % 8 == 4 leaves a half chunk; the rest is zero padding
+          float4 v0 = zero4;
+          if (c * 8 < D) { v0 = *reinterpret_cast<const float4*>(hrow + c * 8); stats4(c * 8, v0); }
+          split_store(c, v0, zero4);
+        }
+      }
+      zd_s[r] = zdot;
+      named_bar_sync(1, 128);
+      const int t = (tile_begin + i) * TB + tt;
+      float g = 1.f;
+      if (d.use_time_warp && active) {
+        float z = zconst[n];
+        for (int kk = 0; kk < d.K; ++kk) z += zd_s[kk * TB + tt];
+        float tz, cnt;
+        g = gate_from_z(d, z, t < d.T ? t : d.T - 1, tz, cnt);
+        if (c_col != nullptr && k == 0 && t < d.T) c_col[(size_t)n * d.T + t] = tz;
+      }
+      float c1, c0v;
+      row_coefs(d, g, lin, quad, c1, c0v);
+      st_s[(i & 1) * 128 + r] = make_float4(c1, c0v, g, 0.f);
+      fence_async_smem();   // A tiles were written through the generic proxy; UMMA reads via the async proxy
+      mbar_arrive(a_ready);
+      mbar_arrive(&st_ready[i & 1]);
+      named_bar_sync(1, 128);   // zd_s is rewritten by the next tile
+    }
+  } else {
+    // ===== softmax warps: thread r owns TMEM lane r = accumulator row r =====
+    const int r = threadIdx.x - 128;
+    const int wq = warp & 3;
     const bool active = r < rows;
     const int k = active ? r / TB : 0, tt = active ? r - k * TB : 0;
     const bool tanh_on = d.add_tanh && d.simi != 4;
@@ -270,14 +356,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
 #pragma unroll
     for (int q = 0; q < 4; ++q) o_acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     float l_acc = 0.f, smax = -INFINITY, ties = 0.f, am_t = 0.f, am_j = 0.f;
-    // state of the tile whose epilogue is pending
-    float p_c1 = 0.f, p_c0 = 0.f, p_g = 0.f;
-    int p_t = 0;
 
-    auto epilogue = [&](int i) {
-      const int s = i % kTcStages;
+    for (int i = 0; i < ntile; ++i) {
+      const int s = i % kTcStages, b2 = i & 1;
+      mbar_wait(&st_ready[b2], (i >> 1) & 1);
+      mbar_wait(&acc_full[b2], (i >> 1) & 1);
+      tc_fence_after();
+      const float4 st = st_s[b2 * 128 + r];
+      const float p_c1 = st.x, p_c0 = st.y, p_g = st.z;
       const float* tile = reinterpret_cast<const float*>(ring + s * pl.stage_bytes);
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((i & 1) * 128);
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b2 * 128);
       float P[32];
       {
         float x[32], y[32];
@@ -289,7 +377,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
 #pragma unroll
         for (int j = 0; j < 32; ++j) P[j] += x[j];
       }
-      const int t = p_t;
+      tc_fence_before();
+      const int t = (tile_begin + i) * TB + tt;
       const bool in_range = active && t < d.T;
       const bool mh = in_range && (!d.has_mask || hall_mask[((size_t)n * d.K + k) * d.T + t]);
       // branch-free logits: P[] is overwritten by the masked logits a[]
@@ -338,8 +427,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         w = (m <= -1e29f) ? kMaskedWeight : expf(m - 1.f);
         l_acc += w;
       }
-      wg_s[r] = w * p_g;
-      tc_fence_before();
+      float* wg = wg_s + b2 * 128;
+      wg[r] = w * p_g;
       named_bar_sync(2, 128);
       // pass 2: o[k2][d4] += sum_tt w*g*h
 #pragma unroll
@@ -348,8 +437,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         if (p < npair) {
           const int k2 = p / D4, d4 = p - k2 * D4;
           const float* hp = tile + (size_t)k2 * TB * D + d4 * 4;
-          const float* wp = wg_s + k2 * TB;
+          const float* wp = wg + k2 * TB;
           float4 o = o_acc[q];
+#pragma unroll 4
           for (int t2 = 0; t2 < TB; ++t2) {
             const float4 hv = *reinterpret_cast<const float4*>(hp + (size_t)t2 * D);
             const float ww = wp[t2];
@@ -360,91 +450,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         }
       }
       mbar_arrive(&empty[s]);
-    };
-
-    for (int i = 0; i < ntile; ++i) {
-      const int s = i % kTcStages;
-      mbar_wait(&full[s], (i / kTcStages) & 1);
-      if (i >= 1) {
-        mbar_wait(&acc_full[(i - 1) & 1], ((i - 1) >> 1) & 1);  // MMA(i-1) done: A is free, acc(i-1) ready
-        tc_fence_after();
-      }
-      // ---- pass 1: row statistics + fp16 hi/lo split into the swizzled A tiles ----
-      float zdot = 0.f, lin = 0.f, quad = 0.f;
-      if (active) {
-        const float* hrow = reinterpret_cast<const float*>(ring + s * pl.stage_bytes) + (size_t)r * D;
-        uint8_t* ahi_row = a_hi + r * 128;
-        uint8_t* alo_row = a_lo + r * 128;
-        const int nch = pl.ksteps * 2;   // 16-byte (8 x fp16) chunks the MMA will read
-        const int nfull = D >> 3;        // chunks with 8 real features
-        auto split_store = [&](int c, const float4& v0, const float4& v1) {
-          const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
-          const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
-          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
-          const __half2 l0 = __floats2half2_rn((v0.x - f0.x) * kLoScale, (v0.y - f0.y) * kLoScale);
-          const __half2 l1 = __floats2half2_rn((v0.z - f1.x) * kLoScale, (v0.w - f1.y) * kLoScale);
-          const __half2 l2 = __floats2half2_rn((v1.x - f2.x) * kLoScale, (v1.y - f2.y) * kLoScale);
-          const __half2 l3 = __floats2half2_rn((v1.z - f3.x) * kLoScale, (v1.w - f3.y) * kLoScale);
-          const uint32_t off = (uint32_t)((c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4));
-          uint4 ph, plo;
-          ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
-          ph.z = *reinterpret_cast<const uint32_t*>(&h2); ph.w = *reinterpret_cast<const uint32_t*>(&h3);
-          plo.x = *reinterpret_cast<const uint32_t*>(&l0); plo.y = *reinterpret_cast<const uint32_t*>(&l1);
-          plo.z = *reinterpret_cast<const uint32_t*>(&l2); plo.w = *reinterpret_cast<const uint32_t*>(&l3);
-          *reinterpret_cast<uint4*>(ahi_row + off) = ph;
-          *reinterpret_cast<uint4*>(alo_row + off) = plo;
-        };
-        auto stats4 = [&](int d0, const float4& v) {
-          const float4 cu = *reinterpret_cast<const float4*>(coef_s + d0);
-          const float4 cl = *reinterpret_cast<const float4*>(coef_s + Dp + d0);
-          const float4 cq = *reinterpret_cast<const float4*>(coef_s + 2 * Dp + d0);
-          const float x2 = v.x * v.x, y2 = v.y * v.y, z2 = v.z * v.z, w2 = v.w * v.w;
-          zdot = fmaf(cu.x, x2, zdot); zdot = fmaf(cu.y, y2, zdot); zdot = fmaf(cu.z, z2, zdot); zdot = fmaf(cu.w, w2, zdot);
-          lin = fmaf(cl.x, v.x, lin); lin = fmaf(cl.y, v.y, lin); lin = fmaf(cl.z, v.z, lin); lin = fmaf(cl.w, v.w, lin);
-          quad = fmaf(cq.x, x2, quad); quad = fmaf(cq.y, y2, quad); quad = fmaf(cq.z, z2, quad); quad = fmaf(cq.w, w2, quad);
-        };
-#pragma unroll 2
-        for (int c = 0; c < nfull; ++c) {
-          const float4 v0 = *reinterpret_cast<const float4*>(hrow + c * 8);
-          const float4 v1 = *reinterpret_cast<const float4*>(hrow + c * 8 + 4);
-          stats4(c * 8, v0);
-          stats4(c * 8 + 4, v1);
-          split_store(c, v0, v1);
-        }
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = nfull; c < nch; ++c) {  // D % 8 == 4 leaves a half chunk; the rest is zero padding
-          float4 v0 = zero4;
-          if (c * 8 < D) { v0 = *reinterpret_cast<const float4*>(hrow + c * 8); stats4(c * 8, v0); }
-          split_store(c, v0, zero4);
-        }
-      }
-      zd_s[r] = zdot;
-      named_bar_sync(1, 128);
-      const int t = (tile_begin + i) * TB + tt;
-      float g = 1.f;
-      if (d.use_time_warp && active) {
-        float z = zconst[n];
-        for (int kk = 0; kk < d.K; ++kk) z += zd_s[kk * TB + tt];
-        float tz, cnt;
-        g = gate_from_z(d, z, t < d.T ? t : d.T - 1, tz, cnt);
-        if (c_col != nullptr && k == 0 && t < d.T) c_col[(size_t)n * d.T + t] = tz;
-      }
-      float c1, c0v;
-      row_coefs(d, g, lin, quad, c1, c0v);
-      fence_async_smem();   // A tiles were written through the generic proxy; UMMA reads via the async proxy
-      tc_fence_before();
-      mbar_arrive(a_ready);
-      if (i >= 1) epilogue(i - 1);
-      p_c1 = c1; p_c0 = c0v; p_g = g; p_t = t;
-    }
-    if (ntile > 0) {
-      mbar_wait(&acc_full[(ntile - 1) & 1], ((ntile - 1) >> 1) & 1);
-      tc_fence_after();
-      epilogue(ntile - 1);
+      mbar_arrive(&ep_done[b2]);
     }
     // ---- slab partials: per-modality reductions over the TB row-owning threads ----
     red_s[r] = l_acc; red_s[128 + r] = smax; red_s[256 + r] = ties; red_s[384 + r] = am_t; red_s[512 + r] = am_j;
-    named_bar_sync(1, 128);
+    named_bar_sync(2, 128);
     if (r < d.K) {
       float l = 0.f, sm = -INFINITY, ti = 0.f, at = 0.f, aj = 0.f;
       for (int t2 = 0; t2 < TB; ++t2) {
@@ -471,7 +481,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
   }
 }
@@ -514,12 +524,14 @@ int attn_fwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hal
   attn_prep_qb<<<d.N, 256, 0, st>>>(d, ws + L.qeffT, qB, L.Dp, L.JQP, pl.KC);
   int rc = check_launch("attn_prep_qb");
   if (rc) return rc;
-  cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  const bool has_lin = (d.simi == 1 || d.simi == 3);   // w_lin is identically zero otherwise
+  auto kern = has_lin ? attn_fwd_tc<true> : attn_fwd_tc<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) { set_last_error("attn_fwd_tc smem attr", e); return FVTA_E_LAUNCH; }
   dim3 grid(pl.slabs, d.N);
-  attn_fwd_tc<<<grid, kTcThreads, pl.smem, st>>>(tmap, d, pl, hall_mask, hq_mask, ws + L.coef, qB, ws + L.col,
-                                                 ws + L.zconst, a_logits, c_col, ws + L.part_stat, ws + L.part_o,
-                                                 L.Dp, L.JQP);
+  kern<<<grid, kTcThreads, pl.smem, st>>>(tmap, d, pl, hall_mask, hq_mask, ws + L.coef, qB, ws + L.col,
+                                          ws + L.zconst, a_logits, c_col, ws + L.part_stat, ws + L.part_o, L.Dp,
+                                          L.JQP);
   rc = check_launch("attn_fwd_tc");
   if (rc) return rc;
   return attn_combine_launch(d, ws + L.part_stat, ws + L.part_o, g1_all, stats, pl.slabs, L.Dp, st);
