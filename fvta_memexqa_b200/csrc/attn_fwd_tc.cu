@@ -31,11 +31,10 @@ namespace fvta {
 int attn_combine_launch(const FvtaAttnDesc& d, const float* part_stat, const float* part_o, float* g1_all,
                         float* stats, int nt, int Dp, cudaStream_t st);
 
-constexpr int kTcThreads = 320;  // warps 0-3 split, 4-7 softmax, warp 8 TMA, warp 9 MMA
+constexpr int kTcThreads = 576;  // warps 0-7 split, 8-15 softmax, warp 16 TMA, warp 17 MMA
 constexpr int kTcStages = 3;
 constexpr int kTcJQP = 32;       // question positions per tile (N of the MMA = 64 + 32)
 constexpr int kTcTmemCols = 256; // 2 accumulator buffers x 128 columns (96 used)
-constexpr float kLoScale = 2048.f;
 constexpr float kMaskedWeight = 7.888609052210118e-31f;  // 2^-100
 
 struct TcPlan {
@@ -50,11 +49,11 @@ struct TcPlan {
 };
 
 __host__ __device__ inline size_t tc_smem_bytes(int KC, int stage_bytes, int Dp) {
-  size_t b = 1024;                                  // alignment slack
+  size_t b = 0;
   b += (size_t)2 * KC * 16384;                      // A_hi, A_lo
   b += (size_t)KC * 8192;                           // [B_hi ; B_lo]
   b += (size_t)kTcStages * stage_bytes;             // fp32 ring
-  b += (size_t)(3 * Dp + 2 * kTcJQP + 128 + 256 + 4 * 256 + 5 * 128) * sizeof(float);
+  b += (size_t)(3 * Dp + 2 * kTcJQP + 256 + 512 + 2 * 256 + 4 * 512) * sizeof(float);  // coef, col, cap, wg, mx, st, zq/red
   b += 256;                                         // barriers, tmem pointer
   return b;
 }
@@ -133,6 +132,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // K-major, 128B-swizzled operand: 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -143,7 +155,7 @@ __device__ __forceinline__ uint32_t umma_idesc_f16(int N) { return (1u << 4) | (
 // tanh(x) = 1 - 2 / (1 + e^{2x}); |error| < 1e-6, never exceeds 1 in magnitude
 __device__ __forceinline__ float tanh_bounded(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
-// ---- B operand: [B_hi ; B_lo * 2^11] as fp16, pre-swizzled, one image per sample -------------
+// ---- B operand: [B_hi ; B_lo] as fp16, pre-swizzled, one image per sample ----------------------
 __global__ void attn_prep_qb(FvtaAttnDesc d, const float* __restrict__ qeffT, __half* __restrict__ qB, int Dp,
                              int JQP, int KC) {
   const int n = blockIdx.x;
@@ -159,16 +171,20 @@ __global__ void attn_prep_qb(FvtaAttnDesc d, const float* __restrict__ qeffT, __
       const int dd = kc * 64 + c * 8 + e;
       const float x = (dd < d.D && j < d.JQ) ? q[(size_t)dd * JQP + j] : 0.f;
       const __half hi = __float2half_rn(x);
-      v[e] = lo ? __float2half_rn((x - __half2float(hi)) * kLoScale) : hi;
+      v[e] = lo ? __float2half_rn(x - __half2float(hi)) : hi;
     }
     *reinterpret_cast<uint4*>(out + kc * 8192 + row * 128 + ((c ^ (row & 7)) << 4)) = *reinterpret_cast<uint4*>(v);
   }
 }
 
 // ---- the fused kernel: grid (slabs, N) ----------------------------------------------------------
-// warps 0-3  "split"   : pass 1 of tile i+1 (row statistics, gate, fp16 hi/lo operands)
-// warps 4-7  "softmax" : epilogue + pass 2 of tile i (TMEM lanes 32*(warp%4)..)
-// warp  8    TMA producer,  warp 9  MMA issuer (+ TMEM allocation)
+// 18 warps.  Two threads share one context row so that each scheduler has four math warps to
+// interleave (the per-tile work is ~2.5k dependent-ish instructions per row):
+//   warps 0-7   "split"   : pass 1 of tile i+1 -- thread (r, h) converts the 16-byte chunks c = h, h+2, ...
+//                           of row r into the fp16 hi/lo operands and accumulates the row statistics
+//   warps 8-15  "softmax" : epilogue + pass 2 of tile i -- thread (r, h) owns accumulator columns
+//                           [16h, 16h+16) of TMEM lane r (warp & 3 selects the lane quadrant)
+//   warp 16 TMA producer,  warp 17 MMA issuer (+ TMEM allocation)
 template <bool HAS_LIN>
 __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     const __grid_constant__ CUtensorMap tmap, FvtaAttnDesc d, TcPlan pl, const uint8_t* __restrict__ hall_mask,
@@ -184,13 +200,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   uint8_t* b_s = a_lo + pl.KC * 16384;
   uint8_t* ring = b_s + pl.KC * 8192;
   float* coef_s = reinterpret_cast<float*>(ring + kTcStages * pl.stage_bytes);  // [3][Dp]
-  float* col_s = coef_s + 3 * Dp;      // [32]
-  float* qm_s = col_s + kTcJQP;        // [32]
-  float* zd_s = qm_s + kTcJQP;         // [128]   gate dots of the tile being split
-  float* wg_s = zd_s + 128;            // [2][128] softmax weight * gate
-  float4* st_s = reinterpret_cast<float4*>(wg_s + 256);  // [2][128] (c1, c0, g, -) per row
-  float* red_s = reinterpret_cast<float*>(st_s + 256);   // [5][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red_s + 5 * 128);
+  float* col_s = coef_s + 3 * Dp;      // [32]   per-question-word term + bias
+  float* cap_s = col_s + kTcJQP;       // [32]   +inf for a valid question word, -1e30 masked, -inf padding
+  float* wg_s = cap_s + kTcJQP;        // [2][128]     softmax weight * gate
+  float* mx_s = wg_s + 256;            // [2][2][128]  half-row maxima
+  float2* st_s = reinterpret_cast<float2*>(mx_s + 512);  // [2][128]  (c1, second coefficient) per row
+  float4* zq_s = reinterpret_cast<float4*>(st_s + 256);  // [2][2][128] half-row (zdot, quad, lin, -)
+  float* red_s = reinterpret_cast<float*>(zq_s);         // [5][256], aliases zq_s after the last tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(zq_s + 512);
   uint64_t* full = bars;               // [3]  TMA -> split, softmax
   uint64_t* empty = bars + 3;          // [3]  softmax -> TMA
   uint64_t* a_ready = bars + 6;        // [1]  split -> MMA
@@ -207,12 +224,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   const int D = d.D, TB = pl.TB, rows = pl.rows;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 128); }
-    mbar_init(a_ready, 128);
-    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(&acc_full[b2], 1); mbar_init(&st_ready[b2], 128); mbar_init(&ep_done[b2], 128); }
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 256); }
+    mbar_init(a_ready, 256);
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(&acc_full[b2], 1); mbar_init(&st_ready[b2], 256); mbar_init(&ep_done[b2], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == 17) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                  "r"(kTcTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -225,7 +242,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     for (int i = threadIdx.x; i < 3 * Dp; i += blockDim.x) coef_s[i] = coef[i];
     for (int j = threadIdx.x; j < kTcJQP; j += blockDim.x) {
       col_s[j] = j < JQPg ? col[(size_t)n * JQPg + j] : 0.f;
-      qm_s[j] = (j < d.JQ && (!d.has_mask || hq_mask[(size_t)n * d.JQ + j])) ? 1.f : 0.f;
+      const bool qv = !d.has_mask || (j < d.JQ && hq_mask[(size_t)n * d.JQ + j]);
+      cap_s[j] = j >= d.JQ ? -INFINITY : (qv ? INFINITY : FVTA_VERY_NEGATIVE);
     }
   }
   fence_async_smem();
@@ -234,7 +252,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ===== TMA producer =====
     if (lane == 0) {
       for (int i = 0; i < ntile; ++i) {
@@ -244,8 +262,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         tma_load_3d(ring + s * pl.stage_bytes, &tmap, &full[s], 0, (tile_begin + i) * TB, n * d.K);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ===== MMA issuer =====
+    // per k-step:  D[:, 0:64] += A_hi . [B_hi ; B_lo]^T   and   D[:, 32:64] += A_lo . B_hi^T
+    // so the epilogue adds two 32-column groups: P = D[:, 0:32] + D[:, 32:64]
     if (lane == 0) {
       const uint32_t idesc64 = umma_idesc_f16(64), idesc32 = umma_idesc_f16(32);
       const uint32_t a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo), b_u = smem_u32(b_s);
@@ -257,36 +277,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
           const uint32_t off = (uint32_t)((ks >> 2) * 16384 + (ks & 3) * 32);
           const uint32_t boff = (uint32_t)((ks >> 2) * 8192 + (ks & 3) * 32);
           umma_f16(acc, umma_desc_sw128(a_hi_u + off), umma_desc_sw128(b_u + boff), idesc64, ks > 0);
-          umma_f16(acc + 64, umma_desc_sw128(a_lo_u + off), umma_desc_sw128(b_u + boff), idesc32, ks > 0);
+          umma_f16(acc + 32, umma_desc_sw128(a_lo_u + off), umma_desc_sw128(b_u + boff), idesc32, 1u);
         }
         umma_commit(&acc_full[i & 1]);
       }
     }
-  } else if (warp < 4) {
-    // ===== split warps: thread r owns context row r = k*TB + tt =====
-    const int r = threadIdx.x;
+  } else if (warp < 8) {
+    // ===== split warps: threads (r, 0) and (r, 1) share context row r = k*TB + tt =====
+    const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
     const bool active = r < rows;
     const int k = active ? r / TB : 0, tt = active ? r - k * TB : 0;
+    const int nch = pl.ksteps * 2;   // 16-byte (8 x fp16) chunks the MMA reads
+    const int nfull = D >> 3;        // chunks holding 8 real features
+    uint8_t* ahi_row = a_hi + r * 128;
+    uint8_t* alo_row = a_lo + r * 128;
     for (int i = 0; i < ntile; ++i) {
-      const int s = i % kTcStages;
+      const int s = i % kTcStages, b2 = i & 1;
       mbar_wait(&full[s], (i / kTcStages) & 1);
       if (i >= 1) mbar_wait(&acc_full[(i - 1) & 1], ((i - 1) >> 1) & 1);   // MMA(i-1) has read A
-      if (i >= 2) mbar_wait(&ep_done[i & 1], ((i - 2) >> 1) & 1);          // softmax(i-2) released buffer i&1
+      if (i >= 2) mbar_wait(&ep_done[b2], ((i - 2) >> 1) & 1);             // softmax(i-2) released buffers b2
       float zdot = 0.f, lin = 0.f, quad = 0.f;
       if (active) {
         const float* hrow = reinterpret_cast<const float*>(ring + s * pl.stage_bytes) + (size_t)r * D;
-        uint8_t* ahi_row = a_hi + r * 128;
-        uint8_t* alo_row = a_lo + r * 128;
-        const int nch = pl.ksteps * 2;   // 16-byte (8 x fp16) chunks the MMA will read
-        const int nfull = D >> 3;        // chunks with 8 real features
         auto split_store = [&](int c, const float4& v0, const float4& v1) {
           const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
           const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
           const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
-          const __half2 l0 = __floats2half2_rn((v0.x - f0.x) * kLoScale, (v0.y - f0.y) * kLoScale);
-          const __half2 l1 = __floats2half2_rn((v0.z - f1.x) * kLoScale, (v0.w - f1.y) * kLoScale);
-          const __half2 l2 = __floats2half2_rn((v1.x - f2.x) * kLoScale, (v1.y - f2.y) * kLoScale);
-          const __half2 l3 = __floats2half2_rn((v1.z - f3.x) * kLoScale, (v1.w - f3.y) * kLoScale);
+          // residual x - fp16(x) is exact in fp32; below 2^-14 it lands on fp16 subnormals whose
+          // 2^-25 absolute rounding is under the fp32 rounding of the operand itself
+          const __half2 l0 = __floats2half2_rn(v0.x - f0.x, v0.y - f0.y), l1 = __floats2half2_rn(v0.z - f1.x, v0.w - f1.y);
+          const __half2 l2 = __floats2half2_rn(v1.x - f2.x, v1.y - f2.y), l3 = __floats2half2_rn(v1.z - f3.x, v1.w - f3.y);
           const uint32_t off = (uint32_t)((c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4));
           uint4 ph, plo;
           ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
@@ -307,144 +327,150 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
             lin = fmaf(cl.x, v.x, lin); lin = fmaf(cl.y, v.y, lin); lin = fmaf(cl.z, v.z, lin); lin = fmaf(cl.w, v.w, lin);
           }
         };
-#pragma unroll 2
-        for (int c = 0; c < nfull; ++c) {
-          const float4 v0 = *reinterpret_cast<const float4*>(hrow + c * 8);
-          const float4 v1 = *reinterpret_cast<const float4*>(hrow + c * 8 + 4);
-          stats4(c * 8, v0);
-          stats4(c * 8 + 4, v1);
-          split_store(c, v0, v1);
-        }
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = nfull; c < nch; ++c) {  // D % 8 == 4 leaves a half chunk; the rest is zero padding
-          float4 v0 = zero4;
-          if (c * 8 < D) { v0 = *reinterpret_cast<const float4*>(hrow + c * 8); stats4(c * 8, v0); }
-          split_store(c, v0, zero4);
+#pragma unroll 2
+        for (int c = h; c < nch; c += 2) {
+          if (c < nfull) {
+            const float4 v0 = *reinterpret_cast<const float4*>(hrow + c * 8);
+            const float4 v1 = *reinterpret_cast<const float4*>(hrow + c * 8 + 4);
+            stats4(c * 8, v0);
+            stats4(c * 8 + 4, v1);
+            split_store(c, v0, v1);
+          } else {  // D % 8 == 4 leaves a half chunk; the rest is zero padding up to the k-step
+            float4 v0 = zero4;
+            if (c * 8 < D) { v0 = *reinterpret_cast<const float4*>(hrow + c * 8); stats4(c * 8, v0); }
+            split_store(c, v0, zero4);
+          }
         }
       }
-      zd_s[r] = zdot;
-      named_bar_sync(1, 128);
-      const int t = (tile_begin + i) * TB + tt;
-      float g = 1.f;
-      if (d.use_time_warp && active) {
-        float z = zconst[n];
-        for (int kk = 0; kk < d.K; ++kk) z += zd_s[kk * TB + tt];
-        float tz, cnt;
-        g = gate_from_z(d, z, t < d.T ? t : d.T - 1, tz, cnt);
-        if (c_col != nullptr && k == 0 && t < d.T) c_col[(size_t)n * d.T + t] = tz;
-      }
-      float c1, c0v;
-      row_coefs(d, g, lin, quad, c1, c0v);
-      st_s[(i & 1) * 128 + r] = make_float4(c1, c0v, g, 0.f);
+      zq_s[(b2 * 2 + h) * 128 + r] = make_float4(zdot, quad, lin, 0.f);
       fence_async_smem();   // A tiles were written through the generic proxy; UMMA reads via the async proxy
       mbar_arrive(a_ready);
-      mbar_arrive(&st_ready[i & 1]);
-      named_bar_sync(1, 128);   // zd_s is rewritten by the next tile
+      named_bar_sync(1, 256);
+      if (h == 0 && active) {
+        const float4* zq0 = zq_s + (b2 * 2) * 128;
+        const float4* zq1 = zq0 + 128;
+        const float4 p0 = zq0[r], p1 = zq1[r];
+        const int t = (tile_begin + i) * TB + tt;
+        float g = 1.f;
+        if (d.use_time_warp) {
+          float z = zconst[n];
+          for (int kk = 0; kk < d.K; ++kk) z += zq0[kk * TB + tt].x + zq1[kk * TB + tt].x;
+          float tz, cnt;
+          g = gate_from_z(d, z, t < d.T ? t : d.T - 1, tz, cnt);
+          if (c_col != nullptr && k == 0 && t < d.T) c_col[(size_t)n * d.T + t] = tz;
+        }
+        float c1, c0v;
+        row_coefs(d, g, p0.z + p1.z, p0.y + p1.y, c1, c0v);
+        // simi 1-3: c1 == g, second slot carries c0;  cosine: c0 == 0, second slot carries g
+        st_s[b2 * 128 + r] = make_float2(c1, d.simi == 4 ? g : c0v);
+      }
+      mbar_arrive(&st_ready[b2]);
     }
   } else {
-    // ===== softmax warps: thread r owns TMEM lane r = accumulator row r =====
-    const int r = threadIdx.x - 128;
+    // ===== softmax warps: thread (r, h) owns columns [16h, 16h+16) of accumulator row r =====
+    const int tid = threadIdx.x - 256;
+    const int r = tid & 127, h = tid >> 7;
     const int wq = warp & 3;
     const bool active = r < rows;
     const int k = active ? r / TB : 0, tt = active ? r - k * TB : 0;
     const bool tanh_on = d.add_tanh && d.simi != 4;
-    uint32_t qbits = 0u;   // question mask as a bit per position
-    for (int j = 0; j < kTcJQP; ++j) qbits |= (qm_s[j] != 0.f ? 1u : 0u) << j;
-    const int D4 = D >> 2;
-    const int npair = d.K * D4;
-    float4 o_acc[4];
+    const bool cosine = d.simi == 4;
+    const int D2 = D >> 1;
+    const int nitem = d.K * D2;      // float2 items of the weighted sum
+    float2 o_acc[3];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) o_acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float l_acc = 0.f, smax = -INFINITY, ties = 0.f, am_t = 0.f, am_j = 0.f;
+    for (int q = 0; q < 3; ++q) o_acc[q] = make_float2(0.f, 0.f);
+    float l_acc = 0.f, smax = -INFINITY, ties = 0.f, am_t = 3.0e38f, am_j = 0.f;
+    float colr[16], capr[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { colr[j] = col_s[16 * h + j]; capr[j] = cap_s[16 * h + j]; }
 
     for (int i = 0; i < ntile; ++i) {
       const int s = i % kTcStages, b2 = i & 1;
+      const int t = (tile_begin + i) * TB + tt;
+      const bool in_range = active && t < d.T;
+      // issue the mask load before blocking on the barriers
+      uint8_t mh_u = 1;
+      if (in_range && d.has_mask) mh_u = hall_mask[((size_t)n * d.K + k) * d.T + t];
       mbar_wait(&st_ready[b2], (i >> 1) & 1);
       mbar_wait(&acc_full[b2], (i >> 1) & 1);
       tc_fence_after();
-      const float4 st = st_s[b2 * 128 + r];
-      const float p_c1 = st.x, p_c0 = st.y, p_g = st.z;
+      const float2 st = st_s[b2 * 128 + r];
+      const float p_c1 = st.x, p_c0 = cosine ? 0.f : st.y, p_g = cosine ? st.y : st.x;
       const float* tile = reinterpret_cast<const float*>(ring + s * pl.stage_bytes);
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b2 * 128);
-      float P[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b2 * 128 + 16 * h);
+      float P[16];
       {
-        float x[32], y[32];
-        tmem_ld32(taddr + 32, x);
-        tmem_ld32(taddr + 64, y);
+        float x[16];
+        tmem_ld16(taddr, P);
+        tmem_ld16(taddr + 32, x);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = (x[j] + y[j]) * (1.f / kLoScale);
-        tmem_ld32(taddr, P);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) P[j] += x[j];
+        for (int j = 0; j < 16; ++j) P[j] += x[j];
       }
       tc_fence_before();
-      const int t = (tile_begin + i) * TB + tt;
-      const bool in_range = active && t < d.T;
-      const bool mh = in_range && (!d.has_mask || hall_mask[((size_t)n * d.K + k) * d.T + t]);
-      // branch-free logits: P[] is overwritten by the masked logits a[]
-      const uint32_t valid_bits = mh ? qbits : 0u;
+      const bool mh = in_range && mh_u != 0;
+      // branch-free logits: P[] is overwritten by the masked logits a[].  |th| <= 1 here, so
+      // th + (-1e30) == -1e30 exactly: exp_mask is a min with the per-column cap
       float m = -INFINITY;
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 cj = *reinterpret_cast<const float4*>(col_s + j4 * 4);
-        const float cc[4] = {cj.x, cj.y, cj.z, cj.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = j4 * 4 + e;
-          const float S = fmaf(p_c1, P[j], p_c0) + cc[e];
-          const float th = tanh_on ? tanh_bounded(S) : S;
-          float a = th;
-          if (d.has_mask) a = ((valid_bits >> j) & 1u) ? th : th + FVTA_VERY_NEGATIVE;  // exp_mask in fp32
-          a = (j < d.JQ) ? a : -INFINITY;                                              // padding columns
-          P[j] = a;
-          m = fmaxf(m, a);
-        }
+      for (int j = 0; j < 16; ++j) {
+        const float S = fmaf(p_c1, P[j], p_c0) + colr[j];
+        const float th = tanh_on ? tanh_bounded(S) : S;
+        const float a = fminf(th, mh ? capr[j] : fminf(capr[j], FVTA_VERY_NEGATIVE));
+        P[j] = a;
+        m = fmaxf(m, a);
       }
-      int rowcnt = 0, jm = 31;
-#pragma unroll
-      for (int j = 31; j >= 0; --j) {
-        const bool hit = P[j] == m;
-        rowcnt += hit ? 1 : 0;
-        jm = hit ? j : jm;
-      }
+      mx_s[(b2 * 2 + h) * 128 + r] = m;
       if (a_logits != nullptr && in_range) {
-        float* arow = a_logits + (((size_t)n * d.K + k) * d.T + t) * d.JQ;
+        float* arow = a_logits + (((size_t)n * d.K + k) * d.T + t) * d.JQ + 16 * h;
         if ((d.JQ & 3) == 0) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            if (j4 * 4 < d.JQ)
+          for (int j4 = 0; j4 < 4; ++j4)
+            if (16 * h + j4 * 4 < d.JQ)
               *reinterpret_cast<float4*>(arow + j4 * 4) = make_float4(P[j4 * 4], P[j4 * 4 + 1], P[j4 * 4 + 2], P[j4 * 4 + 3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < d.JQ) arow[j] = P[j];
+          for (int j = 0; j < 16; ++j)
+            if (16 * h + j < d.JQ) arow[j] = P[j];
         }
       }
+      named_bar_sync(2, 256);
+      m = fmaxf(m, mx_s[(b2 * 2 + (h ^ 1)) * 128 + r]);   // full-row maximum
       float w = 0.f;
       if (in_range) {
-        if (m > smax) { smax = m; ties = (float)rowcnt; am_t = (float)t; am_j = (float)jm; }
-        else if (m == smax) { ties += (float)rowcnt; }
+        if (m >= smax) {   // rare after the first tiles: count ties / record the position lazily
+          if (m > smax) { smax = m; ties = 0.f; am_t = 3.0e38f; }
+          int cnt = 0, jm = -1;
+#pragma unroll
+          for (int j = 15; j >= 0; --j) {
+            const bool hit = P[j] == m;
+            cnt += hit ? 1 : 0;
+            jm = hit ? j : jm;
+          }
+          ties += (float)cnt;
+          if (jm >= 0 && (float)t < am_t) { am_t = (float)t; am_j = (float)(16 * h + jm); }
+        }
         w = (m <= -1e29f) ? kMaskedWeight : expf(m - 1.f);
-        l_acc += w;
+        if (h == 0) l_acc += w;
       }
       float* wg = wg_s + b2 * 128;
-      wg[r] = w * p_g;
-      named_bar_sync(2, 128);
-      // pass 2: o[k2][d4] += sum_tt w*g*h
+      if (h == 0) wg[r] = w * p_g;
+      named_bar_sync(3, 256);
+      // pass 2: o[k2][d2] += sum_tt w*g*h   (float2 items over the 256 softmax threads)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int p = r + q * 128;
-        if (p < npair) {
-          const int k2 = p / D4, d4 = p - k2 * D4;
-          const float* hp = tile + (size_t)k2 * TB * D + d4 * 4;
+      for (int q = 0; q < 3; ++q) {
+        const int p = tid + q * 256;
+        if (p < nitem) {
+          const int k2 = p / D2, d2 = p - k2 * D2;
+          const float* hp = tile + (size_t)k2 * TB * D + d2 * 2;
           const float* wp = wg + k2 * TB;
-          float4 o = o_acc[q];
+          float2 o = o_acc[q];
 #pragma unroll 4
           for (int t2 = 0; t2 < TB; ++t2) {
-            const float4 hv = *reinterpret_cast<const float4*>(hp + (size_t)t2 * D);
+            const float2 hv = *reinterpret_cast<const float2*>(hp + (size_t)t2 * D);
             const float ww = wp[t2];
             o.x = fmaf(ww, hv.x, o.x); o.y = fmaf(ww, hv.y, o.y);
-            o.z = fmaf(ww, hv.z, o.z); o.w = fmaf(ww, hv.w, o.w);
           }
           o_acc[q] = o;
         }
@@ -452,36 +478,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       mbar_arrive(&empty[s]);
       mbar_arrive(&ep_done[b2]);
     }
-    // ---- slab partials: per-modality reductions over the TB row-owning threads ----
-    red_s[r] = l_acc; red_s[128 + r] = smax; red_s[256 + r] = ties; red_s[384 + r] = am_t; red_s[512 + r] = am_j;
-    named_bar_sync(2, 128);
-    if (r < d.K) {
-      float l = 0.f, sm = -INFINITY, ti = 0.f, at = 0.f, aj = 0.f;
-      for (int t2 = 0; t2 < TB; ++t2) {
-        const int rr = r * TB + t2;
-        l += red_s[rr];
-        const float v = red_s[128 + rr];
-        if (v > sm) { sm = v; ti = red_s[256 + rr]; at = red_s[384 + rr]; aj = red_s[512 + rr]; }
-        else if (v == sm) {
-          ti += red_s[256 + rr];
-          if (red_s[384 + rr] < at) { at = red_s[384 + rr]; aj = red_s[512 + rr]; }
+    // ---- slab partials: per-modality reductions over the 2*TB threads owning its rows ----
+    // (red_s aliases zq_s: the split warps finished their last tile before st_ready of that tile)
+    red_s[tid] = l_acc; red_s[256 + tid] = smax; red_s[512 + tid] = ties; red_s[768 + tid] = am_t; red_s[1024 + tid] = am_j;
+    named_bar_sync(2, 256);
+    if (tid < d.K) {
+      float l = 0.f, sm = -INFINITY, ti = 0.f, at = 3.0e38f, aj = 0.f;
+      for (int hh = 0; hh < 2; ++hh)
+        for (int t2 = 0; t2 < TB; ++t2) {
+          const int rr = hh * 128 + tid * TB + t2;
+          l += red_s[rr];
+          const float v = red_s[256 + rr];
+          if (v > sm) { sm = v; ti = 0.f; at = 3.0e38f; }
+          if (v == sm) {
+            ti += red_s[512 + rr];
+            if (red_s[768 + rr] < at) { at = red_s[768 + rr]; aj = red_s[1024 + rr]; }
+          }
         }
-      }
-      float* ps = part_stat + (((size_t)n * pl.slabs + slab) * d.K + r) * kPartW;
+      float* ps = part_stat + (((size_t)n * pl.slabs + slab) * d.K + tid) * kPartW;
       ps[0] = 1.f; ps[1] = l; ps[2] = sm; ps[3] = ti; ps[4] = at; ps[5] = aj; ps[6] = 0.f; ps[7] = 0.f;
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int p = r + q * 128;
-      if (p < npair) {
-        const int k2 = p / D4, d4 = p - k2 * D4;
-        *reinterpret_cast<float4*>(part_o + (((size_t)n * pl.slabs + slab) * d.K + k2) * Dp + d4 * 4) = o_acc[q];
+    for (int q = 0; q < 3; ++q) {
+      const int p = tid + q * 256;
+      if (p < nitem) {
+        const int k2 = p / D2, d2 = p - k2 * D2;
+        *reinterpret_cast<float2*>(part_o + (((size_t)n * pl.slabs + slab) * d.K + k2) * Dp + d2 * 2) = o_acc[q];
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 17) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
   }
 }
