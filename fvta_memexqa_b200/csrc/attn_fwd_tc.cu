@@ -152,8 +152,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // kind::f16, A/B = fp16 K-major, D = fp32, M = 128
 __device__ __forceinline__ uint32_t umma_idesc_f16(int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24); }
 
-// tanh(x) = 1 - 2 / (1 + e^{2x}); |error| < 1e-6, never exceeds 1 in magnitude
-__device__ __forceinline__ float tanh_bounded(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+// MUFU.EX2 / MUFU.RCP; tanh(x) = 1 - 2 / (1 + 2^{2 log2(e) x}) built from them has |error| < 1e-6
+// and never exceeds 1 in magnitude
+__device__ __forceinline__ float exp2f_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // ---- B operand: [B_hi ; B_lo] as fp16, pre-swizzled, one image per sample ----------------------
 __global__ void attn_prep_qb(FvtaAttnDesc d, const float* __restrict__ qeffT, __half* __restrict__ qB, int Dp,
@@ -210,11 +212,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   uint64_t* bars = reinterpret_cast<uint64_t*>(zq_s + 512);
   uint64_t* full = bars;               // [3]  TMA -> split, softmax
   uint64_t* empty = bars + 3;          // [3]  softmax -> TMA
-  uint64_t* a_ready = bars + 6;        // [1]  split -> MMA
-  uint64_t* acc_full = bars + 7;       // [2]  MMA -> split (A free), softmax (accumulator ready)
-  uint64_t* st_ready = bars + 9;       // [2]  split -> softmax (row coefficients)
-  uint64_t* ep_done = bars + 11;       // [2]  softmax -> split (accumulator + coefficient buffer free)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* a_ready = bars + 6;        // [2]  split -> MMA, one per 64-feature operand chunk
+  uint64_t* a_free = bars + 8;         // [2]  MMA -> split: the chunk's MMAs have read the operand
+  uint64_t* acc_full = bars + 10;      // [2]  MMA -> softmax (accumulator ready)
+  uint64_t* st_ready = bars + 12;      // [2]  split -> softmax (row coefficients)
+  uint64_t* ep_done = bars + 14;       // [2]  softmax -> split (accumulator + coefficient buffer free)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab = blockIdx.x, n = blockIdx.y;
@@ -225,8 +228,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 256); }
-    mbar_init(a_ready, 256);
-    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(&acc_full[b2], 1); mbar_init(&st_ready[b2], 256); mbar_init(&ep_done[b2], 256); }
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(&a_ready[b2], 256); mbar_init(&a_free[b2], 1); mbar_init(&acc_full[b2], 1); mbar_init(&st_ready[b2], 256); mbar_init(&ep_done[b2], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 17) {
@@ -270,14 +272,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       const uint32_t idesc64 = umma_idesc_f16(64), idesc32 = umma_idesc_f16(32);
       const uint32_t a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo), b_u = smem_u32(b_s);
       for (int i = 0; i < ntile; ++i) {
-        mbar_wait(a_ready, i & 1);
-        tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)((i & 1) * 128);
-        for (int ks = 0; ks < pl.ksteps; ++ks) {
-          const uint32_t off = (uint32_t)((ks >> 2) * 16384 + (ks & 3) * 32);
-          const uint32_t boff = (uint32_t)((ks >> 2) * 8192 + (ks & 3) * 32);
-          umma_f16(acc, umma_desc_sw128(a_hi_u + off), umma_desc_sw128(b_u + boff), idesc64, ks > 0);
-          umma_f16(acc + 32, umma_desc_sw128(a_lo_u + off), umma_desc_sw128(b_u + boff), idesc32, 1u);
+        for (int kc = 0; kc < pl.KC; ++kc) {
+          mbar_wait(&a_ready[kc], i & 1);
+          tc_fence_after();
+          const int ks_end = min(pl.ksteps, kc * 4 + 4);
+          for (int ks = kc * 4; ks < ks_end; ++ks) {
+            const uint32_t off = (uint32_t)(kc * 16384 + (ks & 3) * 32);
+            const uint32_t boff = (uint32_t)(kc * 8192 + (ks & 3) * 32);
+            umma_f16(acc, umma_desc_sw128(a_hi_u + off), umma_desc_sw128(b_u + boff), idesc64, ks > 0);
+            umma_f16(acc + 32, umma_desc_sw128(a_lo_u + off), umma_desc_sw128(b_u + boff), idesc32, 1u);
+          }
+          umma_commit(&a_free[kc]);   // the split warps may overwrite this chunk for the next tile
         }
         umma_commit(&acc_full[i & 1]);
       }
@@ -294,58 +300,71 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     for (int i = 0; i < ntile; ++i) {
       const int s = i % kTcStages, b2 = i & 1;
       mbar_wait(&full[s], (i / kTcStages) & 1);
-      if (i >= 1) mbar_wait(&acc_full[(i - 1) & 1], ((i - 1) >> 1) & 1);   // MMA(i-1) has read A
       if (i >= 2) mbar_wait(&ep_done[b2], ((i - 2) >> 1) & 1);             // softmax(i-2) released buffers b2
-      float zdot = 0.f, lin = 0.f, quad = 0.f;
-      if (active) {
-        const float* hrow = reinterpret_cast<const float*>(ring + s * pl.stage_bytes) + (size_t)r * D;
-        auto split_store = [&](int c, const float4& v0, const float4& v1) {
-          const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
-          const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
-          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
-          // residual x - fp16(x) is exact in fp32; below 2^-14 it lands on fp16 subnormals whose
-          // 2^-25 absolute rounding is under the fp32 rounding of the operand itself
-          const __half2 l0 = __floats2half2_rn(v0.x - f0.x, v0.y - f0.y), l1 = __floats2half2_rn(v0.z - f1.x, v0.w - f1.y);
-          const __half2 l2 = __floats2half2_rn(v1.x - f2.x, v1.y - f2.y), l3 = __floats2half2_rn(v1.z - f3.x, v1.w - f3.y);
-          const uint32_t off = (uint32_t)((c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4));
-          uint4 ph, plo;
-          ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
-          ph.z = *reinterpret_cast<const uint32_t*>(&h2); ph.w = *reinterpret_cast<const uint32_t*>(&h3);
-          plo.x = *reinterpret_cast<const uint32_t*>(&l0); plo.y = *reinterpret_cast<const uint32_t*>(&l1);
-          plo.z = *reinterpret_cast<const uint32_t*>(&l2); plo.w = *reinterpret_cast<const uint32_t*>(&l3);
-          *reinterpret_cast<uint4*>(ahi_row + off) = ph;
-          *reinterpret_cast<uint4*>(alo_row + off) = plo;
-        };
-        auto stats4 = [&](int d0, const float4& v) {
-          const float4 cu = *reinterpret_cast<const float4*>(coef_s + d0);
-          const float4 cq = *reinterpret_cast<const float4*>(coef_s + 2 * Dp + d0);
-          const float x2 = v.x * v.x, y2 = v.y * v.y, z2 = v.z * v.z, w2 = v.w * v.w;
-          zdot = fmaf(cu.x, x2, zdot); zdot = fmaf(cu.y, y2, zdot); zdot = fmaf(cu.z, z2, zdot); zdot = fmaf(cu.w, w2, zdot);
-          quad = fmaf(cq.x, x2, quad); quad = fmaf(cq.y, y2, quad); quad = fmaf(cq.z, z2, quad); quad = fmaf(cq.w, w2, quad);
-          if (HAS_LIN) {
-            const float4 cl = *reinterpret_cast<const float4*>(coef_s + Dp + d0);
-            lin = fmaf(cl.x, v.x, lin); lin = fmaf(cl.y, v.y, lin); lin = fmaf(cl.z, v.z, lin); lin = fmaf(cl.w, v.w, lin);
-          }
-        };
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      // packed fp32x2 arithmetic (FFMA2/FMUL2): this loop is issue-bound, not FMA-pipe-bound
+      float2 zd2 = make_float2(0.f, 0.f), qd2 = make_float2(0.f, 0.f), ln2 = make_float2(0.f, 0.f);
+      const float* hrow = reinterpret_cast<const float*>(ring + s * pl.stage_bytes) + (size_t)r * D;
+      const float2 neg1 = make_float2(-1.f, -1.f);
+      auto split_store = [&](int c, const float4& v0, const float4& v1) {
+        const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
+        const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
+        // residual x - fp16(x) is exact in fp32; below 2^-14 it lands on fp16 subnormals whose
+        // 2^-25 absolute rounding is under the fp32 rounding of the operand itself
+        const float2 r0 = __ffma2_rn(__half22float2(h0), neg1, make_float2(v0.x, v0.y));
+        const float2 r1 = __ffma2_rn(__half22float2(h1), neg1, make_float2(v0.z, v0.w));
+        const float2 r2 = __ffma2_rn(__half22float2(h2), neg1, make_float2(v1.x, v1.y));
+        const float2 r3 = __ffma2_rn(__half22float2(h3), neg1, make_float2(v1.z, v1.w));
+        const __half2 l0 = __floats2half2_rn(r0.x, r0.y), l1 = __floats2half2_rn(r1.x, r1.y);
+        const __half2 l2 = __floats2half2_rn(r2.x, r2.y), l3 = __floats2half2_rn(r3.x, r3.y);
+        const uint32_t off = (uint32_t)((c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4));
+        uint4 ph, plo;
+        ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
+        ph.z = *reinterpret_cast<const uint32_t*>(&h2); ph.w = *reinterpret_cast<const uint32_t*>(&h3);
+        plo.x = *reinterpret_cast<const uint32_t*>(&l0); plo.y = *reinterpret_cast<const uint32_t*>(&l1);
+        plo.z = *reinterpret_cast<const uint32_t*>(&l2); plo.w = *reinterpret_cast<const uint32_t*>(&l3);
+        *reinterpret_cast<uint4*>(ahi_row + off) = ph;
+        *reinterpret_cast<uint4*>(alo_row + off) = plo;
+      };
+      auto stats4 = [&](int d0, const float4& v) {
+        const float4 cu = *reinterpret_cast<const float4*>(coef_s + d0);
+        const float4 cq = *reinterpret_cast<const float4*>(coef_s + 2 * Dp + d0);
+        const float2 a01 = make_float2(v.x, v.y), a23 = make_float2(v.z, v.w);
+        const float2 s01 = __fmul2_rn(a01, a01), s23 = __fmul2_rn(a23, a23);
+        zd2 = __ffma2_rn(make_float2(cu.x, cu.y), s01, zd2);
+        zd2 = __ffma2_rn(make_float2(cu.z, cu.w), s23, zd2);
+        qd2 = __ffma2_rn(make_float2(cq.x, cq.y), s01, qd2);
+        qd2 = __ffma2_rn(make_float2(cq.z, cq.w), s23, qd2);
+        if (HAS_LIN) {
+          const float4 cl = *reinterpret_cast<const float4*>(coef_s + Dp + d0);
+          ln2 = __ffma2_rn(make_float2(cl.x, cl.y), a01, ln2);
+          ln2 = __ffma2_rn(make_float2(cl.z, cl.w), a23, ln2);
+        }
+      };
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kc = 0; kc < pl.KC; ++kc) {
+        if (i >= 1) mbar_wait(&a_free[kc], (i - 1) & 1);   // MMA(i-1) has read this operand chunk
+        if (active) {
+          const int c_end = min(nch, kc * 8 + 8);
 #pragma unroll 2
-        for (int c = h; c < nch; c += 2) {
-          if (c < nfull) {
-            const float4 v0 = *reinterpret_cast<const float4*>(hrow + c * 8);
-            const float4 v1 = *reinterpret_cast<const float4*>(hrow + c * 8 + 4);
-            stats4(c * 8, v0);
-            stats4(c * 8 + 4, v1);
-            split_store(c, v0, v1);
-          } else {  // D % 8 == 4 leaves a half chunk; the rest is zero padding up to the k-step
-            float4 v0 = zero4;
-            if (c * 8 < D) { v0 = *reinterpret_cast<const float4*>(hrow + c * 8); stats4(c * 8, v0); }
-            split_store(c, v0, zero4);
+          for (int c = kc * 8 + h; c < c_end; c += 2) {
+            if (c < nfull) {
+              const float4 v0 = *reinterpret_cast<const float4*>(hrow + c * 8);
+              const float4 v1 = *reinterpret_cast<const float4*>(hrow + c * 8 + 4);
+              stats4(c * 8, v0);
+              stats4(c * 8 + 4, v1);
+              split_store(c, v0, v1);
+            } else {  // D % 8 == 4 leaves a half chunk; the rest is zero padding up to the k-step
+              float4 v0 = zero4;
+              if (c * 8 < D) { v0 = *reinterpret_cast<const float4*>(hrow + c * 8); stats4(c * 8, v0); }
+              split_store(c, v0, zero4);
+            }
           }
         }
+        fence_async_smem();   // written through the generic proxy; UMMA reads via the async proxy
+        mbar_arrive(&a_ready[kc]);
       }
+      const float zdot = zd2.x + zd2.y, quad = qd2.x + qd2.y, lin = ln2.x + ln2.y;
       zq_s[(b2 * 2 + h) * 128 + r] = make_float4(zdot, quad, lin, 0.f);
-      fence_async_smem();   // A tiles were written through the generic proxy; UMMA reads via the async proxy
-      mbar_arrive(a_ready);
       named_bar_sync(1, 256);
       if (h == 0 && active) {
         const float4* zq0 = zq_s + (b2 * 2) * 128;
@@ -413,13 +432,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       // branch-free logits: P[] is overwritten by the masked logits a[].  |th| <= 1 here, so
       // th + (-1e30) == -1e30 exactly: exp_mask is a min with the per-column cap
       float m = -INFINITY;
+      const float2 c1c1 = make_float2(p_c1, p_c1), c0c0 = make_float2(p_c0, p_c0);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float S = fmaf(p_c1, P[j], p_c0) + colr[j];
-        const float th = tanh_on ? tanh_bounded(S) : S;
-        const float a = fminf(th, mh ? capr[j] : fminf(capr[j], FVTA_VERY_NEGATIVE));
-        P[j] = a;
-        m = fmaxf(m, a);
+      for (int j = 0; j < 16; j += 2) {
+        float2 S = __fadd2_rn(__ffma2_rn(c1c1, make_float2(P[j], P[j + 1]), c0c0), make_float2(colr[j], colr[j + 1]));
+        if (tanh_on) {  // tanh(x) = 1 - 2 / (1 + e^{2x}), packed
+          const float2 e2 = __fmul2_rn(S, make_float2(2.885390081777927f, 2.885390081777927f));  // 2*log2(e)
+          const float2 den = __fadd2_rn(make_float2(exp2f_approx(e2.x), exp2f_approx(e2.y)), make_float2(1.f, 1.f));
+          S = __ffma2_rn(make_float2(rcp_approx(den.x), rcp_approx(den.y)), make_float2(-2.f, -2.f), make_float2(1.f, 1.f));
+        }
+        const float a0 = fminf(S.x, mh ? capr[j] : fminf(capr[j], FVTA_VERY_NEGATIVE));
+        const float a1 = fminf(S.y, mh ? capr[j + 1] : fminf(capr[j + 1], FVTA_VERY_NEGATIVE));
+        P[j] = a0; P[j + 1] = a1;
+        m = fmaxf(m, fmaxf(a0, a1));
       }
       mx_s[(b2 * 2 + h) * 128 + r] = m;
       if (a_logits != nullptr && in_range) {
@@ -470,7 +495,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
           for (int t2 = 0; t2 < TB; ++t2) {
             const float2 hv = *reinterpret_cast<const float2*>(hp + (size_t)t2 * D);
             const float ww = wp[t2];
-            o.x = fmaf(ww, hv.x, o.x); o.y = fmaf(ww, hv.y, o.y);
+            o = __ffma2_rn(make_float2(ww, ww), hv, o);
           }
           o_acc[q] = o;
         }
