@@ -34,7 +34,7 @@ def build_library(force=False, verbose=False):
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "nvcc")
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("NVCC_EXTRA", "").split()
     objs = []
     procs = []
     for src in sources():

@@ -28,6 +28,18 @@
 
 namespace fvta {
 
+// Optional per-role timeline (build with -DFVTA_TC_TRACE, run tools/tc_trace.py): CTA (0,0) stores
+// the SM clock at each pipeline event of its first kTraceTiles tiles into g_tc_trace.
+#ifdef FVTA_TC_TRACE
+constexpr int kTraceTiles = 24;
+__device__ long long g_tc_trace[4][kTraceTiles][8];
+#define TC_TRACE(role, i, ev)                                                                     \
+  do { if (blockIdx.x == 0 && blockIdx.y == 0 && (i) < kTraceTiles && (threadIdx.x == 0 || threadIdx.x == 256 || threadIdx.x == 512 || threadIdx.x == 544)) \
+         g_tc_trace[role][i][ev] = clock64(); } while (0)
+#else
+#define TC_TRACE(role, i, ev) do {} while (0)
+#endif
+
 int attn_combine_launch(const FvtaAttnDesc& d, const float* part_stat, const float* part_o, float* g1_all,
                         float* stats, int nt, int Dp, cudaStream_t st);
 
@@ -60,6 +72,7 @@ __host__ __device__ inline size_t tc_smem_bytes(int KC, int stage_bytes, int Dp)
 
 static bool tc_make_plan(const FvtaAttnDesc& d, TcPlan& p) {
   if ((d.D & 3) != 0 || d.D > 128 || d.D < 8 || d.JQ > kTcJQP || d.K > 8) return false;
+  if (2 * d.K * (d.D / 4) > 512) return false;   // weighted-sum work units over 256 threads x 2
   const bool bounded = (d.simi == 4) || d.add_tanh;
   if (!bounded || d.time_warp_att) return false;
   p.KC = (d.D + 63) / 64;
@@ -260,6 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       for (int i = 0; i < ntile; ++i) {
         const int s = i % kTcStages;
         mbar_wait(&empty[s], ((i / kTcStages) & 1) ^ 1);
+        TC_TRACE(0, i, 0);
         mbar_expect_tx(&full[s], (uint32_t)(rows * D * 4));
         tma_load_3d(ring + s * pl.stage_bytes, &tmap, &full[s], 0, (tile_begin + i) * TB, n * d.K);
       }
@@ -275,6 +289,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         const uint32_t acc = tmem_base + (uint32_t)((i & 1) * 128);
         for (int kc = 0; kc < pl.KC; ++kc) {
           mbar_wait(&a_ready[kc], i & 1);
+          TC_TRACE(1, i, kc);
           tc_fence_after();
           const int ks_end = min(pl.ksteps, kc * 4 + 4);
           for (int ks = kc * 4; ks < ks_end; ++ks) {
@@ -286,6 +301,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
           umma_commit(&a_free[kc]);   // the split warps may overwrite this chunk for the next tile
         }
         umma_commit(&acc_full[i & 1]);
+        TC_TRACE(1, i, 2);
       }
     }
   } else if (warp < 8) {
@@ -297,10 +313,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     const int nfull = D >> 3;        // chunks holding 8 real features
     uint8_t* ahi_row = a_hi + r * 128;
     uint8_t* alo_row = a_lo + r * 128;
+    const float zc = d.use_time_warp ? zconst[n] : 0.f;
     for (int i = 0; i < ntile; ++i) {
       const int s = i % kTcStages, b2 = i & 1;
+      TC_TRACE(2, i, 0);
       mbar_wait(&full[s], (i / kTcStages) & 1);
+      TC_TRACE(2, i, 1);
       if (i >= 2) mbar_wait(&ep_done[b2], ((i - 2) >> 1) & 1);             // softmax(i-2) released buffers b2
+      TC_TRACE(2, i, 2);
       // packed fp32x2 arithmetic (FFMA2/FMUL2): this loop is issue-bound, not FMA-pipe-bound
       float2 zd2 = make_float2(0.f, 0.f), qd2 = make_float2(0.f, 0.f), ln2 = make_float2(0.f, 0.f);
       const float* hrow = reinterpret_cast<const float*>(ring + s * pl.stage_bytes) + (size_t)r * D;
@@ -343,6 +363,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int kc = 0; kc < pl.KC; ++kc) {
         if (i >= 1) mbar_wait(&a_free[kc], (i - 1) & 1);   // MMA(i-1) has read this operand chunk
+        TC_TRACE(2, i, 3 + kc);
         if (active) {
           const int c_end = min(nch, kc * 8 + 8);
 #pragma unroll 2
@@ -365,7 +386,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       }
       const float zdot = zd2.x + zd2.y, quad = qd2.x + qd2.y, lin = ln2.x + ln2.y;
       zq_s[(b2 * 2 + h) * 128 + r] = make_float4(zdot, quad, lin, 0.f);
+      TC_TRACE(2, i, 5);
       named_bar_sync(1, 256);
+      TC_TRACE(2, i, 6);
       if (h == 0 && active) {
         const float4* zq0 = zq_s + (b2 * 2) * 128;
         const float4* zq1 = zq0 + 128;
@@ -373,7 +396,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         const int t = (tile_begin + i) * TB + tt;
         float g = 1.f;
         if (d.use_time_warp) {
-          float z = zconst[n];
+          float z = zc;
           for (int kk = 0; kk < d.K; ++kk) z += zq0[kk * TB + tt].x + zq1[kk * TB + tt].x;
           float tz, cnt;
           g = gate_from_z(d, z, t < d.T ? t : d.T - 1, tz, cnt);
@@ -385,6 +408,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         st_s[b2 * 128 + r] = make_float2(c1, d.simi == 4 ? g : c0v);
       }
       mbar_arrive(&st_ready[b2]);
+      TC_TRACE(2, i, 7);
     }
   } else {
     // ===== softmax warps: thread (r, h) owns columns [16h, 16h+16) of accumulator row r =====
@@ -395,11 +419,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     const int k = active ? r / TB : 0, tt = active ? r - k * TB : 0;
     const bool tanh_on = d.add_tanh && d.simi != 4;
     const bool cosine = d.simi == 4;
-    const int D2 = D >> 1;
-    const int nitem = d.K * D2;      // float2 items of the weighted sum
-    float2 o_acc[3];
+    const int D4 = D >> 2;
+    const int npair = d.K * D4;      // float4 feature groups of the weighted sum
+    const int nunit = 2 * npair;     // x two halves of the tile's positions
+    const int TBh = (TB + 1) >> 1;
+    float4 o_acc[2];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) o_acc[q] = make_float2(0.f, 0.f);
+    for (int q = 0; q < 2; ++q) o_acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     float l_acc = 0.f, smax = -INFINITY, ties = 0.f, am_t = 3.0e38f, am_j = 0.f;
     float colr[16], capr[16];
 #pragma unroll
@@ -412,8 +438,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       // issue the mask load before blocking on the barriers
       uint8_t mh_u = 1;
       if (in_range && d.has_mask) mh_u = hall_mask[((size_t)n * d.K + k) * d.T + t];
+      TC_TRACE(3, i, 0);
       mbar_wait(&st_ready[b2], (i >> 1) & 1);
+      TC_TRACE(3, i, 1);
       mbar_wait(&acc_full[b2], (i >> 1) & 1);
+      TC_TRACE(3, i, 2);
       tc_fence_after();
       const float2 st = st_s[b2 * 128 + r];
       const float p_c1 = st.x, p_c0 = cosine ? 0.f : st.y, p_g = cosine ? st.y : st.x;
@@ -428,6 +457,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         for (int j = 0; j < 16; ++j) P[j] += x[j];
       }
       tc_fence_before();
+      TC_TRACE(3, i, 3);
       const bool mh = in_range && mh_u != 0;
       // branch-free logits: P[] is overwritten by the masked logits a[].  |th| <= 1 here, so
       // th + (-1e30) == -1e30 exactly: exp_mask is a min with the per-column cap
@@ -441,10 +471,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
           const float2 den = __fadd2_rn(make_float2(exp2f_approx(e2.x), exp2f_approx(e2.y)), make_float2(1.f, 1.f));
           S = __ffma2_rn(make_float2(rcp_approx(den.x), rcp_approx(den.y)), make_float2(-2.f, -2.f), make_float2(1.f, 1.f));
         }
-        const float a0 = fminf(S.x, mh ? capr[j] : fminf(capr[j], FVTA_VERY_NEGATIVE));
-        const float a1 = fminf(S.y, mh ? capr[j + 1] : fminf(capr[j + 1], FVTA_VERY_NEGATIVE));
+        const float a0 = fminf(S.x, capr[j]);
+        const float a1 = fminf(S.y, capr[j + 1]);
         P[j] = a0; P[j + 1] = a1;
         m = fmaxf(m, fmaxf(a0, a1));
+      }
+      if (!mh) {   // masked context row: every logit is -1e30 (padding columns stay -inf)
+        m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { P[j] = fminf(capr[j], FVTA_VERY_NEGATIVE); m = fmaxf(m, P[j]); }
       }
       mx_s[(b2 * 2 + h) * 128 + r] = m;
       if (a_logits != nullptr && in_range) {
@@ -460,6 +495,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
             if (16 * h + j < d.JQ) arow[j] = P[j];
         }
       }
+      TC_TRACE(3, i, 4);
       named_bar_sync(2, 256);
       m = fmaxf(m, mx_s[(b2 * 2 + (h ^ 1)) * 128 + r]);   // full-row maximum
       float w = 0.f;
@@ -481,27 +517,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       }
       float* wg = wg_s + b2 * 128;
       if (h == 0) wg[r] = w * p_g;
+      TC_TRACE(3, i, 5);
       named_bar_sync(3, 256);
-      // pass 2: o[k2][d2] += sum_tt w*g*h   (float2 items over the 256 softmax threads)
+      TC_TRACE(3, i, 6);
+      // pass 2: o[k2][d4] += sum_tt w*g*h.  Work unit = (float4 feature group, half of the tile's
+      // positions): 2*K*D/4 units over the 256 softmax threads, short independent FFMA2 chains.
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const int p = tid + q * 256;
-        if (p < nitem) {
-          const int k2 = p / D2, d2 = p - k2 * D2;
-          const float* hp = tile + (size_t)k2 * TB * D + d2 * 2;
-          const float* wp = wg + k2 * TB;
-          float2 o = o_acc[q];
-#pragma unroll 4
-          for (int t2 = 0; t2 < TB; ++t2) {
-            const float2 hv = *reinterpret_cast<const float2*>(hp + (size_t)t2 * D);
+      for (int q = 0; q < 2; ++q) {
+        const int u = tid + q * 256;
+        if (u < nunit) {
+          const int half = u >= npair ? 1 : 0;
+          const int p = u - half * npair;
+          const int k2 = p / D4, d4 = p - k2 * D4;
+          const int t_lo = half ? TBh : 0, t_hi = half ? TB : TBh;
+          const float* hp = tile + ((size_t)k2 * TB + t_lo) * D + d4 * 4;
+          const float* wp = wg + k2 * TB + t_lo;
+          float2 oa = make_float2(o_acc[q].x, o_acc[q].y), ob = make_float2(o_acc[q].z, o_acc[q].w);
+#pragma unroll 5
+          for (int t2 = 0; t2 < t_hi - t_lo; ++t2) {
+            const float4 hv = *reinterpret_cast<const float4*>(hp + (size_t)t2 * D);
             const float ww = wp[t2];
-            o = __ffma2_rn(make_float2(ww, ww), hv, o);
+            const float2 w2 = make_float2(ww, ww);
+            oa = __ffma2_rn(w2, make_float2(hv.x, hv.y), oa);
+            ob = __ffma2_rn(w2, make_float2(hv.z, hv.w), ob);
           }
-          o_acc[q] = o;
+          o_acc[q] = make_float4(oa.x, oa.y, ob.x, ob.y);
         }
       }
       mbar_arrive(&empty[s]);
       mbar_arrive(&ep_done[b2]);
+      TC_TRACE(3, i, 7);
     }
     // ---- slab partials: per-modality reductions over the 2*TB threads owning its rows ----
     // (red_s aliases zq_s: the split warps finished their last tile before st_ready of that tile)
@@ -523,13 +568,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       float* ps = part_stat + (((size_t)n * pl.slabs + slab) * d.K + tid) * kPartW;
       ps[0] = 1.f; ps[1] = l; ps[2] = sm; ps[3] = ti; ps[4] = at; ps[5] = aj; ps[6] = 0.f; ps[7] = 0.f;
     }
+    // the two position-halves of a feature group live on different threads: the first stores its
+    // partial sum, the second adds to it after a barrier (this CTA owns the part_o slab exclusively)
+    for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int p = tid + q * 256;
-      if (p < nitem) {
-        const int k2 = p / D2, d2 = p - k2 * D2;
-        *reinterpret_cast<float2*>(part_o + (((size_t)n * pl.slabs + slab) * d.K + k2) * Dp + d2 * 2) = o_acc[q];
+      for (int q = 0; q < 2; ++q) {
+        const int u = tid + q * 256;
+        if (u < nunit && (u >= npair ? 1 : 0) == pass) {
+          const int p = u - pass * npair;
+          const int k2 = p / D4, d4 = p - k2 * D4;
+          float4* dst = reinterpret_cast<float4*>(part_o + (((size_t)n * pl.slabs + slab) * d.K + k2) * Dp + d4 * 4);
+          float4 v = o_acc[q];
+          if (pass == 1) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+          *dst = v;
+        }
       }
+      __threadfence_block();
+      named_bar_sync(2, 256);
     }
   }
   tc_fence_before();
@@ -538,6 +593,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
   }
 }
+
+#ifdef FVTA_TC_TRACE
+extern "C" int fvta_tc_trace_read(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 4 * kTraceTiles * 8);
+}
+#endif
 
 // ---- host side --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
