@@ -60,16 +60,18 @@ __global__ void attn_prep_q(FvtaAttnDesc d, FvtaAttnParams p, const float* __res
                             float* __restrict__ col, float* __restrict__ zconst, int Dp, int JQP) {
   extern __shared__ float sm[];
   float* scale = sm;  // [JQP] cosine scale per question word
+  // grid (N, kPrepSplit): block (n, y) owns question words j = y, y + kPrepSplit, ...
   const int n = blockIdx.x;
   const int D = d.D, JQ = d.JQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int jy = blockIdx.y, jstep = gridDim.y;
   const float* q = hq + (size_t)n * JQ * D;
   const float* wq_lin = nullptr;
   const float* wq_quad = nullptr;
   if (d.simi == 1) wq_lin = p.att_W + D;
   else if (d.simi == 2) wq_quad = p.att_W + D;
   else if (d.simi == 3) { wq_lin = p.att_W + D; wq_quad = p.att_W + 2 * D; }
-  for (int j = warp; j < JQP; j += nwarp) {
+  for (int j = jy + warp * jstep; j < JQP; j += nwarp * jstep) {
     float qq = 0.f, c = 0.f;
     if (j < JQ) {
       for (int e = lane; e < D; e += 32) {
@@ -87,7 +89,7 @@ __global__ void attn_prep_q(FvtaAttnDesc d, FvtaAttnParams p, const float* __res
       col[(size_t)n * JQP + j] = (j < JQ && d.simi != 4) ? c + bias : 0.f;
     }
   }
-  if (warp == 0) {
+  if (warp == 0 && jy == 0) {
     float acc = 0.f;
     if (d.use_time_warp)
       for (int e = lane; e < D; e += 32) acc += (p.WH_b[e] + lq[(size_t)n * D + e]) * p.WC_W[e];
@@ -96,8 +98,9 @@ __global__ void attn_prep_q(FvtaAttnDesc d, FvtaAttnParams p, const float* __res
   }
   __syncthreads();
   float* out = qeffT + (size_t)n * Dp * JQP;
-  for (int i = threadIdx.x; i < Dp * JQP; i += blockDim.x) {
-    int dd = i / JQP, j = i - dd * JQP;
+  const int nj = (JQP - jy + jstep - 1) / jstep;   // question words owned by this block
+  for (int i = threadIdx.x; i < Dp * nj; i += blockDim.x) {
+    int dd = i / nj, j = jy + (i - dd * nj) * jstep;
     float v = 0.f;
     if (dd < D && j < JQ) {
       float qv = q[(size_t)j * D + dd];
@@ -106,7 +109,7 @@ __global__ void attn_prep_q(FvtaAttnDesc d, FvtaAttnParams p, const float* __res
       else if (d.simi == 3) v = qv * (p.att_W[3 * D + dd] - 2.f * p.att_W[2 * D + dd]);
       else v = qv * scale[j];
     }
-    out[i] = v;
+    out[(size_t)dd * JQP + j] = v;
   }
 }
 
@@ -287,39 +290,34 @@ __global__ void attn_combine_stats(FvtaAttnDesc d, const float* __restrict__ par
   }
 }
 
-// combine, stage 2: grid (ceil(D/32), N), block 32 x 8.  r_k[:] = sum_tiles o * exp(M_tile - M) / L
-// (lane = feature, the 8 warps stride over the tiles), then g1_all = sum_k beta_k r_k.
+// combine, stage 2: grid (ceil(D/32), N, K), block 32 x 8.  r_k[:] = sum_tiles o * exp(M_tile - M) / L
+// (lane = feature, the 8 warps stride over the tiles), then g1_all += beta_k r_k (g1_all zeroed first).
 __global__ void attn_combine_o(FvtaAttnDesc d, const float* __restrict__ part_stat,
                                const float* __restrict__ part_o, float* __restrict__ g1_all,
                                float* __restrict__ stats, int nt, int Dp) {
   __shared__ float red[8][33];
-  const int n = blockIdx.y;
+  const int n = blockIdx.y, k = blockIdx.z;
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* ps = part_stat + (size_t)n * nt * d.K * kPartW;
-  float g1 = 0.f;
-  for (int k = 0; k < d.K; ++k) {
-    const float* st = stats + ((size_t)n * d.K + k) * kStatW;
-    const float M = st[0], invL = 1.f / st[1], beta = st[4];
-    float o = 0.f;
-    if (c < d.D)
-      for (int i = w; i < nt; i += 8) {
-        const float sc = expf(ps[((size_t)i * d.K + k) * kPartW] - M);
-        o = fmaf(part_o[(((size_t)n * nt + i) * d.K + k) * Dp + c], sc, o);
-      }
-    red[w][lane] = o;
-    __syncthreads();
-    if (w == 0 && c < d.D) {
-      float r = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) r += red[i][lane];
-      r *= invL;
-      stats[attn_stats_r_offset(d) + ((size_t)n * d.K + k) * d.D + c] = r;
-      g1 = fmaf(beta, r, g1);
+  const float* st = stats + ((size_t)n * d.K + k) * kStatW;
+  const float M = st[0], invL = 1.f / st[1], beta = st[4];
+  float o = 0.f;
+  if (c < d.D)
+    for (int i = w; i < nt; i += 8) {
+      const float sc = expf(ps[((size_t)i * d.K + k) * kPartW] - M);
+      o = fmaf(part_o[(((size_t)n * nt + i) * d.K + k) * Dp + c], sc, o);
     }
-    __syncthreads();
+  red[w][lane] = o;
+  __syncthreads();
+  if (w == 0 && c < d.D) {
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += red[i][lane];
+    r *= invL;
+    stats[attn_stats_r_offset(d) + ((size_t)n * d.K + k) * d.D + c] = r;
+    atomicAdd(g1_all + (size_t)n * d.D + c, beta * r);
   }
-  if (w == 0 && c < d.D) g1_all[(size_t)n * d.D + c] = g1;
 }
 
 int attn_combine_launch(const FvtaAttnDesc& d, const float* part_stat, const float* part_o, float* g1_all,
@@ -327,7 +325,9 @@ int attn_combine_launch(const FvtaAttnDesc& d, const float* part_stat, const flo
   attn_combine_stats<<<d.N, d.K * 32, 0, st>>>(d, part_stat, stats, nt);
   int rc = check_launch("attn_combine_stats");
   if (rc) return rc;
-  dim3 grid((d.D + 31) / 32, d.N);
+  cudaError_t e = cudaMemsetAsync(g1_all, 0, (size_t)d.N * d.D * sizeof(float), st);
+  if (e != cudaSuccess) { set_last_error("attn_combine memset", e); return FVTA_E_LAUNCH; }
+  dim3 grid((d.D + 31) / 32, d.N, d.K);
   attn_combine_o<<<grid, 256, 0, st>>>(d, part_stat, part_o, g1_all, stats, nt, Dp);
   return check_launch("attn_combine_o");
 }
@@ -362,7 +362,7 @@ int attn_prep_launch(const FvtaAttnDesc& d, const AttnLayout& L, const FvtaAttnP
     int rc = check_launch("attn_prep_coef");
     if (rc) return rc;
   }
-  attn_prep_q<<<d.N, 256, L.JQP * sizeof(float), st>>>(d, p, hq, lq, ws + L.qeffT, ws + L.col,
+  attn_prep_q<<<dim3(d.N, L.JQP < 8 ? L.JQP : 8), 128, L.JQP * sizeof(float), st>>>(d, p, hq, lq, ws + L.qeffT, ws + L.col,
                                                          ws + L.zconst, L.Dp, L.JQP);
   return check_launch("attn_prep_q");
 }
