@@ -251,13 +251,12 @@ def run_own(args):
     batches = list(data.get_batches(PER_GPU_BATCH, num_steps=4, shuffle=False))
     dfeeds = [model.to_device(model.get_feed_dict(b[1], is_train=True)) for b in batches]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    h2d = batches[0][1].h2d_bytes()
+    h2d = max(model.h2d_bytes(df) for df in dfeeds)
     if not args.no_graph:
-        # the whole device step replays as ONE CUDA graph (static shapes; see Trainer.enable_graph)
-        snap = [t.clone() for t in (model.params.flat, model.params.accum, model.params.accum_update)]
-        trainer.enable_graph(batches[0][1].feed)
-        for t, s0 in zip((model.params.flat, model.params.accum, model.params.accum_update), snap):
-            t.copy_(s0)
+        # the whole device step replays as ONE CUDA graph per packed-token bucket (Trainer.enable_graph)
+        trainer.enable_graph()
+        for df in dfeeds:
+            trainer.graph_step(df)          # captures each bucket this data touches, outside the timed region
         device_step = trainer.graph_step
     else:
         device_step = trainer._device_step

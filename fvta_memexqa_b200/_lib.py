@@ -31,6 +31,10 @@ class FvtaLstmDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("B", "J", "In", "d")]
 
 
+class FvtaReaderDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "ntok", "In", "d", "Jmax")]
+
+
 ERRORS = {0: "FVTA_OK", -1: "FVTA_E_BADARG", -2: "FVTA_E_UNSUPPORTED", -3: "FVTA_E_WORKSPACE",
           -4: "FVTA_E_LAUNCH", -5: "FVTA_E_SHAPE"}
 
@@ -58,6 +62,14 @@ SYMBOLS = {
                                        c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                        c_float_p, c_float_p, c_float_p, c_float_p,
                                        ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "fvta_reader_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(FvtaReaderDesc)]),
+    "fvta_reader_reserve_floats": (ctypes.c_size_t, [ctypes.POINTER(FvtaReaderDesc)]),
+    "fvta_reader_fwd": (ctypes.c_int, [ctypes.POINTER(FvtaReaderDesc), c_float_p, c_i32_p, c_i32_p, ctypes.c_void_p,
+                                       c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                       ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "fvta_reader_bwd": (ctypes.c_int, [ctypes.POINTER(FvtaReaderDesc), c_float_p, c_i32_p, c_i32_p, ctypes.c_void_p,
+                                       c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                       c_float_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "fvta_gemm": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_float_p, ctypes.c_int32,
                                  ctypes.c_int32, c_float_p, ctypes.c_int32, ctypes.c_int32, c_float_p,
                                  ctypes.c_int32, c_float_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),

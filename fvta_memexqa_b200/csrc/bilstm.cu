@@ -36,11 +36,22 @@ __host__ __device__ inline LstmSmemPlan lstm_smem_plan(int d) {
   return p;
 }
 
+// Addressing of one sequence b: its tokens are rows tok0 .. tok0+len-1 of the packed arrays
+// (projected inputs, reserve, d gates); its outputs go to rows out0 .. of the output arena
+// (out0 < 0: outputs are not stored).  Dense [B,J] layout = (b*J, b*J).
+struct SeqAddr {
+  const int32_t* tok_off;   // [B] or null (dense)
+  const int64_t* out_row;   // [B] or null (dense)
+  int ntok;                 // rows of the packed arrays
+  __device__ __forceinline__ int tok0(int b, int J) const { return tok_off ? tok_off[b] : b * J; }
+  __device__ __forceinline__ long long out0(int b, int J) const { return out_row ? out_row[b] : (long long)b * J; }
+};
+
 // grid (ceil(B/kSG), 2); block: multiple of 32
-__global__ void bilstm_rec_fwd(FvtaLstmDesc L, const int32_t* __restrict__ lens, const float* __restrict__ xp_fw,
-                               const float* __restrict__ xp_bw, const float* __restrict__ wh_fw,
-                               const float* __restrict__ wh_bw, float* __restrict__ out,
-                               float* __restrict__ last, float* __restrict__ reserve) {
+__global__ void bilstm_rec_fwd(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
+                               const float* __restrict__ xp_fw, const float* __restrict__ xp_bw,
+                               const float* __restrict__ wh_fw, const float* __restrict__ wh_bw,
+                               float* __restrict__ out, float* __restrict__ last, float* __restrict__ reserve) {
   extern __shared__ __align__(16) float sm[];
   const int d = L.d, G = 4 * d;
   const LstmSmemPlan plan = lstm_smem_plan(d);
@@ -52,11 +63,18 @@ __global__ void bilstm_rec_fwd(FvtaLstmDesc L, const int32_t* __restrict__ lens,
   float* c_s = h_s + kSG * d;                                         // [kSG][d]
   float* g_s = c_s + kSG * d;                                         // [kSG][4d]
   __shared__ int len_s[kSG];
+  __shared__ int tok_s[kSG];
+  __shared__ long long orow_s[kSG];
   const int b0 = blockIdx.x * kSG;
   if (plan.w_in_smem)
     for (int i = threadIdx.x; i < d * G; i += blockDim.x) w_s[(i / G) * plan.wstride + (i % G)] = wh_g[i];
   for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) { h_s[i] = 0.f; c_s[i] = 0.f; }
-  if (threadIdx.x < kSG) len_s[threadIdx.x] = (b0 + threadIdx.x < L.B) ? min(lens[b0 + threadIdx.x], L.J) : 0;
+  if (threadIdx.x < kSG) {
+    const int b = b0 + threadIdx.x;
+    len_s[threadIdx.x] = (b < L.B) ? min(lens[b], L.J) : 0;
+    tok_s[threadIdx.x] = (b < L.B) ? A.tok0(b, L.J) : 0;
+    orow_s[threadIdx.x] = (b < L.B) ? A.out0(b, L.J) : -1;
+  }
   __syncthreads();
   int maxlen = 0;
 #pragma unroll
@@ -65,14 +83,14 @@ __global__ void bilstm_rec_fwd(FvtaLstmDesc L, const int32_t* __restrict__ lens,
   const int ws = plan.wstride;
 
   for (int step = 0; step < maxlen; ++step) {
-    // gate pre-activations: g_s[s][g] = xp[b][t][g] + sum_e h[s][e] * Wh[e][g]
+    // gate pre-activations: g_s[s][g] = xp[tok][g] + sum_e h[s][e] * Wh[e][g]
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
       float acc[kSG];
 #pragma unroll
       for (int s = 0; s < kSG; ++s) {
         const int len = len_s[s];
         const int t = dir == 0 ? step : len - 1 - step;
-        acc[s] = (step < len) ? xp[((size_t)(b0 + s) * L.J + t) * G + g] : 0.f;
+        acc[s] = (step < len) ? xp[((size_t)tok_s[s] + t) * G + g] : 0.f;
       }
       for (int e = 0; e < d; ++e) {
         const float w = W[(size_t)e * ws + g];
@@ -87,7 +105,6 @@ __global__ void bilstm_rec_fwd(FvtaLstmDesc L, const int32_t* __restrict__ lens,
       const int s = i / d, e = i - s * d;
       const int len = len_s[s];
       if (step < len) {
-        const int b = b0 + s;
         const int t = dir == 0 ? step : len - 1 - step;
         const float* gs = g_s + s * G;
         const float ig = sigmoidf_(gs[e]);
@@ -99,8 +116,8 @@ __global__ void bilstm_rec_fwd(FvtaLstmDesc L, const int32_t* __restrict__ lens,
         const float h = tanhf(c) * og;
         c_s[i] = c;
         h_s[i] = h;
-        out[((size_t)b * L.J + t) * 2 * d + dir * d + e] = h;
-        float* r = reserve + (((size_t)dir * L.B + b) * L.J + t) * kResW * d;
+        if (orow_s[s] >= 0) out[((size_t)orow_s[s] + t) * 2 * d + dir * d + e] = h;
+        float* r = reserve + ((size_t)dir * A.ntok + tok_s[s] + t) * kResW * d;
         r[e] = ig; r[d + e] = jg; r[2 * d + e] = fg; r[3 * d + e] = og; r[4 * d + e] = c; r[5 * d + e] = hp;
       }
     }
@@ -113,10 +130,10 @@ __global__ void bilstm_rec_fwd(FvtaLstmDesc L, const int32_t* __restrict__ lens,
 }
 
 // BPTT.  dgates [2][B*J][4d] must be zero-initialised (padded steps stay zero).
-__global__ void bilstm_rec_bwd(FvtaLstmDesc L, const int32_t* __restrict__ lens, const float* __restrict__ wh_fw,
-                               const float* __restrict__ wh_bw, const float* __restrict__ reserve,
-                               const float* __restrict__ d_out, const float* __restrict__ d_last,
-                               float* __restrict__ dgates) {
+__global__ void bilstm_rec_bwd(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
+                               const float* __restrict__ wh_fw, const float* __restrict__ wh_bw,
+                               const float* __restrict__ reserve, const float* __restrict__ d_out,
+                               const float* __restrict__ d_last, float* __restrict__ dgates) {
   extern __shared__ __align__(16) float sm[];
   const int d = L.d, G = 4 * d;
   const LstmSmemPlan plan = lstm_smem_plan(d);
@@ -127,18 +144,25 @@ __global__ void bilstm_rec_bwd(FvtaLstmDesc L, const int32_t* __restrict__ lens,
   float* dc_s = dh_s + kSG * d;                                        // [kSG][d]
   float* dg_s = dc_s + kSG * d;                                        // [kSG][4d]
   __shared__ int len_s[kSG];
+  __shared__ int tok_s[kSG];
+  __shared__ long long orow_s[kSG];
   const int b0 = blockIdx.x * kSG;
   if (plan.w_in_smem)
     for (int i = threadIdx.x; i < d * G; i += blockDim.x) w_s[(i / G) * plan.wstride + (i % G)] = wh_g[i];
   for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) { dh_s[i] = 0.f; dc_s[i] = 0.f; }
-  if (threadIdx.x < kSG) len_s[threadIdx.x] = (b0 + threadIdx.x < L.B) ? min(lens[b0 + threadIdx.x], L.J) : 0;
+  if (threadIdx.x < kSG) {
+    const int b = b0 + threadIdx.x;
+    len_s[threadIdx.x] = (b < L.B) ? min(lens[b], L.J) : 0;
+    tok_s[threadIdx.x] = (b < L.B) ? A.tok0(b, L.J) : 0;
+    orow_s[threadIdx.x] = (b < L.B) ? A.out0(b, L.J) : -1;
+  }
   __syncthreads();
   int maxlen = 0;
 #pragma unroll
   for (int s = 0; s < kSG; ++s) maxlen = max(maxlen, len_s[s]);
   const float* W = plan.w_in_smem ? w_s : wh_g;
   const int ws = plan.wstride;
-  float* dgd = dgates + (size_t)dir * L.B * L.J * G;
+  float* dgd = dgates + (size_t)dir * A.ntok * G;
 
   for (int step = maxlen - 1; step >= 0; --step) {
     for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) {
@@ -148,15 +172,15 @@ __global__ void bilstm_rec_bwd(FvtaLstmDesc L, const int32_t* __restrict__ lens,
       if (step < len) {
         const int b = b0 + s;
         const int t = dir == 0 ? step : len - 1 - step;
-        const float* r = reserve + (((size_t)dir * L.B + b) * L.J + t) * kResW * d;
+        const float* r = reserve + ((size_t)dir * A.ntok + tok_s[s] + t) * kResW * d;
         const float ig = r[e], jg = r[d + e], fg = r[2 * d + e], og = r[3 * d + e], c = r[4 * d + e];
         float c_prev = 0.f;
         if (step > 0) {
           const int tp = dir == 0 ? t - 1 : t + 1;
-          c_prev = reserve[(((size_t)dir * L.B + b) * L.J + tp) * kResW * d + 4 * d + e];
+          c_prev = reserve[((size_t)dir * A.ntok + tok_s[s] + tp) * kResW * d + 4 * d + e];
         }
         float dh = dh_s[i];
-        if (d_out) dh += d_out[((size_t)b * L.J + t) * 2 * d + dir * d + e];
+        if (d_out && orow_s[s] >= 0) dh += d_out[((size_t)orow_s[s] + t) * 2 * d + dir * d + e];
         if (d_last && step == len - 1) dh += d_last[(size_t)b * 2 * d + dir * d + e];
         const float tc = tanhf(c);
         const float dc = fmaf(dh * og, 1.f - tc * tc, dc_s[i]);
@@ -165,7 +189,7 @@ __global__ void bilstm_rec_bwd(FvtaLstmDesc L, const int32_t* __restrict__ lens,
         dgj = dc * ig * (1.f - jg * jg);
         dgf = dc * c_prev * fg * (1.f - fg);
         dc_s[i] = dc * fg;
-        float* o = dgd + ((size_t)b * L.J + t) * G;
+        float* o = dgd + ((size_t)tok_s[s] + t) * G;
         o[e] = dgi; o[d + e] = dgj; o[2 * d + e] = dgf; o[3 * d + e] = dgo;
       }
       float* gs = dg_s + s * G;
@@ -214,6 +238,82 @@ static int lstm_validate(const FvtaLstmDesc* L) {
   return FVTA_OK;
 }
 
+// Forward over `ntok` packed token rows (dense layout: ntok = B*J).
+//   workspace: xp_fw [ntok*4d], xp_bw [ntok*4d];   reserve: [2][ntok][6d]
+static int lstm_fwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x, const int32_t* lens,
+                         const float* kernel_fw, const float* bias_fw, const float* kernel_bw,
+                         const float* bias_bw, float* out, float* last, float* reserve, float* workspace,
+                         void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = 4 * L.d;
+  float* xp_fw = workspace;
+  float* xp_bw = xp_fw + (size_t)A.ntok * G;
+  // input projection for every token at once: xp = x @ kernel[:In] + bias
+  int rc = fvta_gemm(A.ntok, G, L.In, x, L.In, 0, kernel_fw, G, 0, bias_fw, 0, xp_fw, G, 0, stream);
+  if (rc) return rc;
+  const bool shared = (kernel_bw == kernel_fw && bias_bw == bias_fw);
+  if (!shared) {
+    rc = fvta_gemm(A.ntok, G, L.In, x, L.In, 0, kernel_bw, G, 0, bias_bw, 0, xp_bw, G, 0, stream);
+    if (rc) return rc;
+  } else {
+    xp_bw = xp_fw;
+  }
+  // padded steps of `reserve` feed 0 * h_prev products in the backward GEMMs: keep them finite
+  cudaError_t e = cudaMemsetAsync(reserve, 0, (size_t)2 * A.ntok * kResW * L.d * sizeof(float), st);
+  if (e != cudaSuccess) { set_last_error("bilstm memset", e); return FVTA_E_LAUNCH; }
+  const LstmSmemPlan plan = lstm_smem_plan(L.d);
+  e = cudaFuncSetAttribute(bilstm_rec_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.bytes);
+  if (e != cudaSuccess) { set_last_error("bilstm_rec_fwd smem attr", e); return FVTA_E_LAUNCH; }
+  int threads = round_up(G < 1024 ? G : 1024, 32);
+  dim3 grid((L.B + kSG - 1) / kSG, 2);
+  bilstm_rec_fwd<<<grid, threads, plan.bytes, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+                                                   kernel_bw + (size_t)L.In * G, out, last, reserve);
+  return check_launch("bilstm_rec_fwd");
+}
+
+//   workspace: d gates [2][ntok][4d]
+static int lstm_bwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x, const int32_t* lens,
+                         const float* kernel_fw, const float* kernel_bw, const float* reserve, const float* d_out,
+                         const float* d_last, float* d_x, float* d_kernel_fw, float* d_bias_fw,
+                         float* d_kernel_bw, float* d_bias_bw, float* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = 4 * L.d, NT = A.ntok;
+  float* dg = workspace;
+  cudaError_t e = cudaMemsetAsync(dg, 0, (size_t)2 * NT * G * sizeof(float), st);
+  if (e != cudaSuccess) { set_last_error("bilstm bwd memset", e); return FVTA_E_LAUNCH; }
+  const LstmSmemPlan plan = lstm_smem_plan(L.d);
+  e = cudaFuncSetAttribute(bilstm_rec_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.bytes);
+  if (e != cudaSuccess) { set_last_error("bilstm_rec_bwd smem attr", e); return FVTA_E_LAUNCH; }
+  int threads = round_up((kSG * L.d) < 1024 ? (kSG * L.d) : 1024, 32);
+  dim3 grid((L.B + kSG - 1) / kSG, 2);
+  bilstm_rec_bwd<<<grid, threads, plan.bytes, st>>>(L, A, lens, kernel_fw + (size_t)L.In * G,
+                                                   kernel_bw + (size_t)L.In * G, reserve, d_out, d_last, dg);
+  int rc = check_launch("bilstm_rec_bwd");
+  if (rc) return rc;
+  const float* dgs[2] = {dg, dg + (size_t)NT * G};
+  const float* ress[2] = {reserve, reserve + (size_t)NT * kResW * L.d};
+  // d_x = dg_fw @ Wx_fw^T + dg_bw @ Wx_bw^T
+  rc = fvta_gemm(NT, L.In, G, dgs[0], G, 0, kernel_fw, G, 1, nullptr, 0, d_x, L.In, 0, stream);
+  if (rc) return rc;
+  rc = fvta_gemm(NT, L.In, G, dgs[1], G, 0, kernel_bw, G, 1, nullptr, 0, d_x, L.In, 1, stream);
+  if (rc) return rc;
+  float* dks[2] = {d_kernel_fw, d_kernel_bw};
+  float* dbs[2] = {d_bias_fw, d_bias_bw};
+  for (int dir = 0; dir < 2; ++dir) {
+    // d kernel[:In] += x^T @ dg ;  d kernel[In:] += h_prev^T @ dg ;  d bias += colsum(dg)
+    rc = fvta_gemm(L.In, G, NT, x, L.In, 1, dgs[dir], G, 0, nullptr, 0, dks[dir], G, 1, stream);
+    if (rc) return rc;
+    rc = fvta_gemm(L.d, G, NT, ress[dir] + 5 * L.d, kResW * L.d, 1, dgs[dir], G, 0, nullptr, 0,
+                   dks[dir] + (size_t)L.In * G, G, 1, stream);
+    if (rc) return rc;
+    dim3 cg((G + 31) / 32, 64);
+    colsum_accumulate<<<cg, 256, 0, st>>>(NT, G, dgs[dir], G, dbs[dir]);
+    rc = check_launch("colsum_accumulate");
+    if (rc) return rc;
+  }
+  return FVTA_OK;
+}
+
 // workspace: xp_fw [B*J*4d], xp_bw [B*J*4d] (forward) or dgates [2][B*J*4d] (backward)
 extern "C" size_t fvta_bilstm_workspace_bytes(const FvtaLstmDesc* L) {
   if (lstm_validate(L)) return 0;
@@ -234,33 +334,11 @@ extern "C" int fvta_bilstm_fwd(const FvtaLstmDesc* desc, const float* x, const i
   if (!x || !lens || !kernel_fw || !bias_fw || !kernel_bw || !bias_bw || !out || !last || !reserve || !workspace)
     return FVTA_E_BADARG;
   if (workspace_bytes < fvta_bilstm_workspace_bytes(desc)) return FVTA_E_WORKSPACE;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int G = 4 * L.d, BJ = L.B * L.J;
-  float* xp_fw = (float*)workspace;
-  float* xp_bw = xp_fw + (size_t)BJ * G;
-  // input projection for every timestep at once: xp = x @ kernel[:In] + bias
-  rc = fvta_gemm(BJ, G, L.In, x, L.In, 0, kernel_fw, G, 0, bias_fw, 0, xp_fw, G, 0, stream);
-  if (rc) return rc;
-  const bool shared = (kernel_bw == kernel_fw && bias_bw == bias_fw);
-  if (!shared) {
-    rc = fvta_gemm(BJ, G, L.In, x, L.In, 0, kernel_bw, G, 0, bias_bw, 0, xp_bw, G, 0, stream);
-    if (rc) return rc;
-  } else {
-    xp_bw = xp_fw;
-  }
-  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)BJ * 2 * L.d * sizeof(float), st);
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)L.B * L.J * 2 * L.d * sizeof(float), (cudaStream_t)stream);
   if (e != cudaSuccess) { set_last_error("bilstm memset", e); return FVTA_E_LAUNCH; }
-  // padded steps of `reserve` feed 0 * h_prev products in the backward GEMMs: keep them finite
-  e = cudaMemsetAsync(reserve, 0, fvta_bilstm_reserve_floats(desc) * sizeof(float), st);
-  if (e != cudaSuccess) { set_last_error("bilstm memset", e); return FVTA_E_LAUNCH; }
-  const LstmSmemPlan plan = lstm_smem_plan(L.d);
-  e = cudaFuncSetAttribute(bilstm_rec_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.bytes);
-  if (e != cudaSuccess) { set_last_error("bilstm_rec_fwd smem attr", e); return FVTA_E_LAUNCH; }
-  int threads = round_up(G < 1024 ? G : 1024, 32);
-  dim3 grid((L.B + kSG - 1) / kSG, 2);
-  bilstm_rec_fwd<<<grid, threads, plan.bytes, st>>>(L, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
-                                                   kernel_bw + (size_t)L.In * G, out, last, reserve);
-  return check_launch("bilstm_rec_fwd");
+  SeqAddr A{nullptr, nullptr, L.B * L.J};
+  return lstm_fwd_impl(L, A, x, lens, kernel_fw, bias_fw, kernel_bw, bias_bw, out, last, reserve,
+                       (float*)workspace, stream);
 }
 
 extern "C" int fvta_bilstm_bwd(const FvtaLstmDesc* desc, const float* x, const int32_t* lens,
@@ -276,44 +354,55 @@ extern "C" int fvta_bilstm_bwd(const FvtaLstmDesc* desc, const float* x, const i
       !d_kernel_bw || !d_bias_bw || !workspace)
     return FVTA_E_BADARG;
   if (workspace_bytes < fvta_bilstm_workspace_bytes(desc)) return FVTA_E_WORKSPACE;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int G = 4 * L.d, BJ = L.B * L.J;
-  float* dg = (float*)workspace;  // [2][BJ][G]
-  cudaError_t e = cudaMemsetAsync(dg, 0, (size_t)2 * BJ * G * sizeof(float), st);
-  if (e != cudaSuccess) { set_last_error("bilstm bwd memset", e); return FVTA_E_LAUNCH; }
-  const LstmSmemPlan plan = lstm_smem_plan(L.d);
-  e = cudaFuncSetAttribute(bilstm_rec_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.bytes);
-  if (e != cudaSuccess) { set_last_error("bilstm_rec_bwd smem attr", e); return FVTA_E_LAUNCH; }
-  int threads = round_up((kSG * L.d) < 1024 ? (kSG * L.d) : 1024, 32);
-  dim3 grid((L.B + kSG - 1) / kSG, 2);
-  bilstm_rec_bwd<<<grid, threads, plan.bytes, st>>>(L, lens, kernel_fw + (size_t)L.In * G,
-                                                   kernel_bw + (size_t)L.In * G, reserve, d_out, d_last, dg);
-  rc = check_launch("bilstm_rec_bwd");
-  if (rc) return rc;
-  const float* dg_fw = dg;
-  const float* dg_bw = dg + (size_t)BJ * G;
-  // d_x = dg_fw @ Wx_fw^T + dg_bw @ Wx_bw^T
-  rc = fvta_gemm(BJ, L.In, G, dg_fw, G, 0, kernel_fw, G, 1, nullptr, 0, d_x, L.In, 0, stream);
-  if (rc) return rc;
-  rc = fvta_gemm(BJ, L.In, G, dg_bw, G, 0, kernel_bw, G, 1, nullptr, 0, d_x, L.In, 1, stream);
-  if (rc) return rc;
-  const float* res_fw = reserve;
-  const float* res_bw = reserve + (size_t)BJ * kResW * L.d;
-  const float* dgs[2] = {dg_fw, dg_bw};
-  const float* ress[2] = {res_fw, res_bw};
-  float* dks[2] = {d_kernel_fw, d_kernel_bw};
-  float* dbs[2] = {d_bias_fw, d_bias_bw};
-  for (int dir = 0; dir < 2; ++dir) {
-    // d kernel[:In] += x^T @ dg ;  d kernel[In:] += h_prev^T @ dg ;  d bias += colsum(dg)
-    rc = fvta_gemm(L.In, G, BJ, x, L.In, 1, dgs[dir], G, 0, nullptr, 0, dks[dir], G, 1, stream);
-    if (rc) return rc;
-    rc = fvta_gemm(L.d, G, BJ, ress[dir] + 5 * L.d, kResW * L.d, 1, dgs[dir], G, 0, nullptr, 0,
-                   dks[dir] + (size_t)L.In * G, G, 1, stream);
-    if (rc) return rc;
-    dim3 cg((G + 31) / 32, 64);
-    colsum_accumulate<<<cg, 256, 0, st>>>(BJ, G, dgs[dir], G, dbs[dir]);
-    rc = check_launch("colsum_accumulate");
-    if (rc) return rc;
-  }
+  SeqAddr A{nullptr, nullptr, L.B * L.J};
+  return lstm_bwd_impl(L, A, x, lens, kernel_fw, kernel_bw, reserve, d_out, d_last, d_x, d_kernel_fw, d_bias_fw,
+                       d_kernel_bw, d_bias_bw, (float*)workspace, stream);
+}
+
+// ---- packed reader ------------------------------------------------------------------------------
+static int reader_validate(const FvtaReaderDesc* R) {
+  if (!R) return FVTA_E_BADARG;
+  if (R->B <= 0 || R->ntok <= 0 || R->In <= 0 || R->d <= 0 || R->Jmax <= 0) return FVTA_E_BADARG;
   return FVTA_OK;
+}
+extern "C" size_t fvta_reader_workspace_bytes(const FvtaReaderDesc* R) {
+  if (reader_validate(R)) return 0;
+  return (size_t)2 * R->ntok * 4 * R->d * sizeof(float);
+}
+extern "C" size_t fvta_reader_reserve_floats(const FvtaReaderDesc* R) {
+  if (reader_validate(R)) return 0;
+  return (size_t)2 * R->ntok * kResW * R->d;
+}
+
+extern "C" int fvta_reader_fwd(const FvtaReaderDesc* desc, const float* x_tok, const int32_t* seq_tok_off,
+                               const int32_t* seq_len, const int64_t* seq_out_row, const float* kernel,
+                               const float* bias, float* out_arena, float* last, float* reserve, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  int rc = reader_validate(desc);
+  if (rc) return rc;
+  if (!x_tok || !seq_tok_off || !seq_len || !seq_out_row || !kernel || !bias || !out_arena || !last || !reserve ||
+      !workspace)
+    return FVTA_E_BADARG;
+  if (workspace_bytes < fvta_reader_workspace_bytes(desc)) return FVTA_E_WORKSPACE;
+  FvtaLstmDesc L{desc->B, desc->Jmax, desc->In, desc->d};
+  SeqAddr A{seq_tok_off, seq_out_row, desc->ntok};
+  return lstm_fwd_impl(L, A, x_tok, seq_len, kernel, bias, kernel, bias, out_arena, last, reserve,
+                       (float*)workspace, stream);
+}
+
+extern "C" int fvta_reader_bwd(const FvtaReaderDesc* desc, const float* x_tok, const int32_t* seq_tok_off,
+                               const int32_t* seq_len, const int64_t* seq_out_row, const float* kernel,
+                               const float* reserve, const float* d_out_arena, const float* d_last, float* d_x_tok,
+                               float* d_kernel, float* d_bias, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  int rc = reader_validate(desc);
+  if (rc) return rc;
+  if (!x_tok || !seq_tok_off || !seq_len || !seq_out_row || !kernel || !reserve || !d_x_tok || !d_kernel ||
+      !d_bias || !workspace)
+    return FVTA_E_BADARG;
+  if (workspace_bytes < fvta_reader_workspace_bytes(desc)) return FVTA_E_WORKSPACE;
+  FvtaLstmDesc L{desc->B, desc->Jmax, desc->In, desc->d};
+  SeqAddr A{seq_tok_off, seq_out_row, desc->ntok};
+  return lstm_bwd_impl(L, A, x_tok, seq_len, kernel, kernel, reserve, d_out_arena, d_last, d_x_tok, d_kernel,
+                       d_bias, d_kernel, d_bias, (float*)workspace, stream);
 }

@@ -224,25 +224,41 @@ class Model:
         feed["is_train"] = is_train
         return feed
 
-    def to_device(self, feed):
-        """Host->device copy of a feed dict (non-blocking when the host tensors are pinned)."""
-        out = {}
-        for k, v in feed.items():
-            if isinstance(v, torch.Tensor):
-                out[k] = v.to(self.device, non_blocking=True)
-            elif hasattr(v, "dtype") and hasattr(v, "shape"):   # numpy
-                out[k] = torch.as_tensor(v).to(self.device, non_blocking=True)
-            else:
-                out[k] = v
+    # tensors the device step consumes besides the packed reader inputs
+    _DEVICE_KEYS = ("q_mask", "y", "existing_emb_mat", "image_emb_mat")
+
+    def to_device(self, feed, pack=None):
+        """Host feed -> device step inputs.  The host packs the valid tokens and the per-sequence
+        arena rows (packing.build_pack); only those, the question mask, the labels and the two
+        embedding tables are copied (non-blocking when the host tensors are pinned)."""
+        if "_meta" in feed:
+            return feed                      # already a device step input
+        from .packing import build_pack
+        host = {k: (torch.as_tensor(v) if not isinstance(v, torch.Tensor) and hasattr(v, "shape") else v)
+                for k, v in feed.items()}
+        if pack is None:
+            pack = build_pack(host, self.config)
+        tensors, meta = pack
+        out = {"_meta": meta, "_host": host, "is_train": feed.get("is_train", False)}
+        for k in self._DEVICE_KEYS:
+            if k in host and host[k] is not None:
+                out[k] = host[k].to(self.device, non_blocking=True)
+        for k, v in tensors.items():
+            out[k] = v.to(self.device, non_blocking=True)
         return out
 
+    @staticmethod
+    def h2d_bytes(dfeed):
+        return sum(v.numel() * v.element_size() for k, v in dfeed.items()
+                   if isinstance(v, torch.Tensor) and not k.startswith("_"))
+
     # ------------------------------------------------------------------ forward
-    def _embed_words(self, ids, ids_c, glove, is_train):
+    def _embed_tokens(self, ids, ids_c, glove, is_train):
+        """model_v2.py:524-620 for the packed valid tokens: word vector (trainable table for ids <
+        VW, fed GloVe table otherwise, :596) and the char-CNN (:52-70) concatenated [char, word]."""
         cfg, v = self.config, self.vars
         VW = self.VW
-        ids = ids.long()
         table = v["emb/word/var/word_emb_mat"]
-        # word table = concat(trainable [VW], fed GloVe) (model_v2.py:596) without the concat
         # F.embedding, not advanced indexing: its backward is the sorted segmented reduction
         # (plain index backward serialises on the heavily repeated ids)
         emb = torch.nn.functional.embedding
@@ -251,79 +267,52 @@ class Model:
                         emb((ids - VW).clamp(min=0), glove))
         if not cfg.use_char:
             return A
-        Ac = emb(ids_c.long(), v["emb/var/char_emb"])                  # [..., J, W, cdim]
-        if is_train and cfg.keep_prob < 1.0:                           # conv1d input dropout (:60-61)
+        Ac = emb(ids_c, v["emb/var/char_emb"])                          # [cap, W, cdim]
+        if is_train and cfg.keep_prob < 1.0:                            # conv1d input dropout (:60-61)
             Ac = torch.nn.functional.dropout(Ac, 1.0 - cfg.keep_prob, True)
-        filt = v["emb/conv/conv1d/filter"]                             # [1,5,cdim,cwdim]
+        filt = v["emb/conv/conv1d/filter"]                              # [1,5,cdim,cwdim]
         height, cdim, cw = filt.shape[1], filt.shape[2], filt.shape[3]
-        win = Ac.unfold(-2, height, 1)                                 # [..., J, W-4, cdim, 5]
-        lead = win.shape[:-2]
+        win = Ac.unfold(1, height, 1)                                   # [cap, W-4, cdim, 5]
+        npos = win.shape[1]
         flat = win.reshape(-1, cdim * height)
         Wm = filt[0].permute(1, 0, 2).reshape(cdim * height, cw)
         xc = torch.relu(torch.matmul(flat, Wm) + v["emb/conv/conv1d/bias"])
-        xc = xc.reshape(*lead, cw).amax(dim=-2)                        # max over positions (:65)
+        xc = xc.reshape(-1, npos, cw).amax(dim=1)                       # max over positions (:65)
         return torch.cat([xc, A], dim=-1)
 
-    def _read(self, x, mask, which):
-        v = self.vars
-        pre = "reader/text/utext" if which == "text" else "reader/image/uimage"
-        kernel, bias = v[pre + "/fw/basic_lstm_cell/kernel"], v[pre + "/fw/basic_lstm_cell/bias"]
-        cfg = self.config
-        if self._is_train and cfg.keep_prob < 1.0:                     # DropoutWrapper input keep_prob
-            x = torch.nn.functional.dropout(x, 1.0 - cfg.keep_prob, True)
-        lens = mask.sum(-1).to(torch.int32).reshape(-1).contiguous()
-        flat = x.reshape(-1, x.shape[-2], x.shape[-1])
-        out, last = ops.bilstm(flat, lens, kernel, bias)
-        d2 = out.shape[-1]
-        return out.reshape(*x.shape[:-1], d2), last.reshape(*x.shape[:-2], d2)
-
     def forward(self, feed, is_train=False, want_vis=False):
-        """model_v2.py:493-1096 on device tensors.  Sets and returns loss/logits/yp."""
+        """model_v2.py:493-1096 on a device step input (see to_device).  Sets and returns
+        loss/logits/yp."""
         cfg, v = self.config, self.vars
-        f = feed
+        f = feed if "_meta" in feed else self.to_device(feed)
+        meta = f["_meta"]
         self._is_train = is_train
-        N = f["q"].shape[0]
+        N, K, T, M, JMAX, JQ = meta["N"], meta["K"], meta["T"], meta["M"], meta["JMAX"], meta["JQ"]
         d = cfg.hidden_size
         D = 2 * d
-        glove = f["existing_emb_mat"]
-        x = {}
-        for nme in ("at", "ad", "when", "where", "pts", "q", "choices"):
-            x[nme] = self._embed_words(f[nme], f.get(nme + "_c"), glove, is_train)
-        # image: transform the batch's unique photos once, then gather (== lookup then linear, :634-645)
-        feats = f["image_emb_mat"]
-        if cfg.use_image_trans:
-            feats = ops.linear(feats, v["emb/image/image_transform/image_trans_linear/W"],
+        drop = (lambda t: torch.nn.functional.dropout(t, 1.0 - cfg.keep_prob, True)) \
+            if (is_train and cfg.keep_prob < 1.0) else (lambda t: t)
+        # embeddings of the valid tokens only (padding never reaches a consumer: dynamic_rnn ignores it)
+        x_text = self._embed_tokens(f["text_tok_ids"], f.get("text_tok_cids"), f["existing_emb_mat"], is_train)
+        x_img = torch.nn.functional.embedding(f["img_tok_pidx"], f["image_emb_mat"])
+        if cfg.use_image_trans:                                        # model_v2.py:634-645
+            x_img = ops.linear(x_img, v["emb/image/image_transform/image_trans_linear/W"],
                                v["emb/image/image_transform/image_trans_linear/b"], cfg.add_tanh)
-        xpis = torch.nn.functional.embedding(f["pis"].long(), feats)
-
-        hq, lq = self._read(x["q"], f["q_mask"], "text")
-        hat, _ = self._read(x["at"], f["at_mask"], "text")
-        had, _ = self._read(x["ad"], f["ad_mask"], "text")
-        hwhen, _ = self._read(x["when"], f["when_mask"], "text")
-        hwhere, _ = self._read(x["where"], f["where_mask"], "text")
-        hpts, _ = self._read(x["pts"], f["pts_mask"], "text")
-        _, lchoices = self._read(x["choices"], f["choices_mask"], "text")
-        hpis, _ = self._read(xpis, f["pis_mask"], "image")
-
-        # context tensor (model_v2.py:862-914)
-        M, JXA = hat.shape[1], hat.shape[2]
-        JD, JT, JG = had.shape[2], hwhen.shape[2], hwhere.shape[2]
-        JI, JXP = hpts.shape[2], hpts.shape[3]
-        JMAX = max(JXA, JD, JT, JG, JI * JXP, JI)
-        pad = torch.nn.functional.pad
-        hs = [pad(hat, (0, 0, 0, JMAX - JXA)), pad(had, (0, 0, 0, JMAX - JD)),
-              pad(hwhen, (0, 0, 0, JMAX - JT)), pad(hwhere, (0, 0, 0, JMAX - JG)),
-              pad(hpts.reshape(N, M, JI * JXP, D), (0, 0, 0, JMAX - JI * JXP))]
-        ms = [pad(f["at_mask"], (0, JMAX - JXA)), pad(f["ad_mask"], (0, JMAX - JD)),
-              pad(f["when_mask"], (0, JMAX - JT)), pad(f["where_mask"], (0, JMAX - JG)),
-              pad(f["pts_mask"].reshape(N, M, JI * JXP), (0, JMAX - JI * JXP))]
-        if not cfg.no_photo:
-            hs.append(pad(hpis, (0, 0, 0, JMAX - JI)))
-            ms.append(pad(f["pis_mask"], (0, JMAX - JI)))
-        K = len(hs)
-        hall = torch.stack(hs, dim=1)                  # [N,K,M,JMAX,D]
-        hall_mask = torch.stack(ms, dim=1)             # [N,K,M,JMAX]
-        T = M * JMAX
+        # the eight reader call sites (model_v2.py:694-823) + the context tensor (:862-914)
+        arena, last_t, last_i = ops.ReaderFn.apply(
+            drop(x_text), drop(x_img), f["text_seq_off"], f["text_seq_len"], f["text_seq_out"],
+            f["img_seq_off"], f["img_seq_len"], f["img_seq_out"],
+            v["reader/text/utext/fw/basic_lstm_cell/kernel"], v["reader/text/utext/fw/basic_lstm_cell/bias"],
+            v["reader/image/uimage/fw/basic_lstm_cell/kernel"], v["reader/image/uimage/fw/basic_lstm_cell/bias"],
+            meta["arena_rows"], meta["text_Jmax"], meta["img_Jmax"])
+        hall = arena[:meta["hall_rows"]].view(N, K, M, JMAX, D)
+        hall_mask = f["hall_mask"].view(N, K, M, JMAX)
+        hq = arena[meta["hq_row0"]:].view(N, JQ, D)
+        q0, q1 = meta["q_range"]
+        c0, c1 = meta["choices_range"]
+        lq = last_t[q0:q1]
+        lchoices = last_t[c0:c1].view(N, meta["C"], D)
+        JXP = meta["JXP"]
 
         # time warp + attention_3d, fused (model_v2.py:953-1024)
         acfg = ops.AttnConfig(cfg.simiMatrix, cfg.add_tanh, cfg.use_time_warp, cfg.warp_type,
@@ -331,7 +320,7 @@ class Model:
         tw = cfg.use_time_warp
         g1_all, a_logits, c_col, warp_h = ops.FvtaAttentionFn.apply(
             acfg, (want_vis, want_vis and tw, want_vis and tw),
-            hall.reshape(N, K, T, D), hall_mask.reshape(N, K, T), hq, f["q_mask"], lq if tw else None,
+            hall.reshape(N, K, T, D), f["hall_mask"], hq, f["q_mask"], lq if tw else None,
             v.get("attention/all/att_logits/W"), v.get("attention/all/att_logits/b"),
             v.get("time_warp/WH/W") if tw else None, v.get("time_warp/WH/b") if tw else None,
             v.get("time_warp/WC/W") if tw else None, v.get("time_warp/WC/b") if tw else None)

@@ -300,3 +300,67 @@ class FvtaAttentionFn(torch.autograd.Function):
         ctx.fwd = None
         return (None, None, g["d_hall"], None, g["d_hq"], None, g["d_lq"] if ctx.has_lq else None,
                 g["d_att_W"], g["d_att_b"], g["d_WH_W"], g["d_WH_b"], g["d_WC_W"], g["d_WC_b"])
+
+
+# ---------------------------------------------------------------------------------------------
+# packed reader: every text call site in one launch, outputs written in place into the arena
+# ---------------------------------------------------------------------------------------------
+def _reader_call(lib, x_tok, off, lens, outrow, kernel, bias, arena, Jmax):
+    from ._lib import FvtaReaderDesc
+    f32 = torch.float32
+    d = kernel.shape[1] // 4
+    desc = FvtaReaderDesc(B=lens.numel(), ntok=x_tok.shape[0], In=x_tok.shape[1], d=d, Jmax=Jmax)
+    dev = x_tok.device
+    last = torch.empty(lens.numel(), 2 * d, dtype=f32, device=dev)
+    reserve = torch.empty(lib.fvta_reader_reserve_floats(ctypes.byref(desc)), dtype=f32, device=dev)
+    ws_bytes = lib.fvta_reader_workspace_bytes(ctypes.byref(desc))
+    ws = torch.empty(ws_bytes // 4, dtype=f32, device=dev)
+    rc = lib.fvta_reader_fwd(ctypes.byref(desc), _ptr(x_tok), _ptr(off), _ptr(lens), _ptr(outrow), _ptr(kernel),
+                             _ptr(bias), _ptr(arena), _ptr(last), _ptr(reserve), _ptr(ws), ws_bytes, _stream())
+    check(rc, "fvta_reader_fwd")
+    return last, reserve, desc
+
+
+class ReaderFn(torch.autograd.Function):
+    """The eight bidirectional_dynamic_rnn call sites of model_v2.py:694-823 as two launches
+    (text cell, image cell) over packed tokens, writing into one zeroed arena
+    [hall rows | hq rows] x 2d.  Returns (arena, last_text [Bt,2d], last_img [Bi,2d])."""
+
+    @staticmethod
+    def forward(ctx, x_text, x_img, t_off, t_len, t_out, i_off, i_len, i_out, kt, bt, ki, bi, arena_rows,
+                Jmax_t, Jmax_i):
+        lib = _lib.load()
+        f32 = torch.float32
+        x_text, x_img = _req(x_text, f32, "x_text"), _req(x_img, f32, "x_img")
+        kt, bt, ki, bi = (_req(v, f32, "reader weights") for v in (kt, bt, ki, bi))
+        d = kt.shape[1] // 4
+        arena = torch.zeros(arena_rows, 2 * d, dtype=f32, device=x_text.device)
+        last_t, res_t, desc_t = _reader_call(lib, x_text, t_off, t_len, t_out, kt, bt, arena, Jmax_t)
+        last_i, res_i, desc_i = _reader_call(lib, x_img, i_off, i_len, i_out, ki, bi, arena, Jmax_i)
+        ctx.save_for_backward(x_text, x_img, t_off, t_len, t_out, i_off, i_len, i_out, kt, ki, res_t, res_i)
+        ctx.descs = (desc_t, desc_i)
+        return arena, last_t, last_i
+
+    @staticmethod
+    def backward(ctx, d_arena, d_last_t, d_last_i):
+        lib = _lib.load()
+        f32 = torch.float32
+        x_text, x_img, t_off, t_len, t_out, i_off, i_len, i_out, kt, ki, res_t, res_i = ctx.saved_tensors
+        desc_t, desc_i = ctx.descs
+        d_arena = _req(d_arena, f32, "d_arena") if d_arena is not None else None
+        outs = []
+        for (x, off, ln, orow, k, res, desc, dl) in ((x_text, t_off, t_len, t_out, kt, res_t, desc_t, d_last_t),
+                                                     (x_img, i_off, i_len, i_out, ki, res_i, desc_i, d_last_i)):
+            dx = torch.empty_like(x)
+            dk = torch.zeros_like(k)
+            db = torch.zeros(k.shape[1], dtype=f32, device=x.device)
+            dl = _req(dl, f32, "d_last") if dl is not None else None
+            ws_bytes = lib.fvta_reader_workspace_bytes(ctypes.byref(desc))
+            ws = torch.empty(ws_bytes // 4, dtype=f32, device=x.device)
+            rc = lib.fvta_reader_bwd(ctypes.byref(desc), _ptr(x), _ptr(off), _ptr(ln), _ptr(orow), _ptr(k), _ptr(res),
+                                     _ptr(d_arena), _ptr(dl), _ptr(dx), _ptr(dk), _ptr(db), _ptr(ws), ws_bytes,
+                                     _stream())
+            check(rc, "fvta_reader_bwd")
+            outs.append((dx, dk, db))
+        (dxt, dkt, dbt), (dxi, dki, dbi) = outs
+        return (dxt, dxi, None, None, None, None, None, None, dkt, dbt, dki, dbi, None, None, None)

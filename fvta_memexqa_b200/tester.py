@@ -46,12 +46,13 @@ class Tester:
         n = batch_data.num_examples
         yp = np_(yp)[:n]
         C, C_win, att_logits, q_att_logits = np_(m.C), m.C_win, np_(m.att_logits), np_(m.q_att_logits)
-        masks = {k: np_(dfeed[k]) for k in ("at_mask", "ad_mask", "when_mask", "where_mask", "pts_mask",
-                                            "pis_mask", "q_mask")}
+        host = dfeed["_host"]
+        masks = {k: np_(host[k]) for k in ("at_mask", "ad_mask", "when_mask", "where_mask", "pts_mask",
+                                           "pis_mask", "q_mask")}
         C, C_win, att_logits, q_att_logits, at_mask, pts_mask, pis_mask, q_mask = self.trim(
             [C, C_win, att_logits, q_att_logits, masks["at_mask"], masks["pts_mask"], masks["pis_mask"],
              masks["q_mask"]], n)
-        ids = {k: np_(dfeed[k]) for k in ("at", "ad", "when", "where", "pts", "pis", "q")}
+        ids = {k: np_(host[k]) for k in ("at", "ad", "when", "where", "pts", "pis", "q")}
         return (yp, C, C_win, att_logits, q_att_logits, at_mask, masks["ad_mask"], masks["when_mask"],
                 masks["where_mask"], pts_mask, pis_mask, q_mask, m.hat_len, m.had_len, m.hwhen_len,
                 m.hwhere_len, m.hpts_len, m.hpis_len, m.JXP, np_(m.warp_h), np_(m.hall), ids["at"],

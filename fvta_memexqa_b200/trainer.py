@@ -42,58 +42,74 @@ class Trainer:
         return loss
 
     # ---------------------------------------------------------------- CUDA-graph execution
-    def enable_graph(self, example_feed, warmup=3):
-        """Capture the whole device step (forward, backward, all-reduce, Adadelta) into one CUDA
-        graph over static input buffers.  At the reference shape the step is ~100 short kernels
-        and launch-latency bound, so replaying a graph is the difference between the GPU and
-        the Python interpreter setting the pace.  Requires pinned padded shapes: every later
-        batch must have exactly the shapes of ``example_feed``."""
+    def enable_graph(self, example_feed=None, warmup=3):
+        """Run the whole device step (forward, backward, all-reduce, Adadelta) as ONE CUDA graph
+        over static input buffers.  At the reference shape the step is ~100 short kernels and
+        launch-latency bound, so replaying a graph is the difference between the GPU and the
+        Python interpreter setting the pace.  Requires pinned padded shapes; graphs are keyed by
+        the packed-token buckets (packing.build_pack) and captured on first use."""
+        self._graphs = {}
+        self._graph_warmup = warmup
+        if example_feed is not None:
+            self._capture(self.model.to_device(example_feed))
+        return self
+
+    def _capture(self, dfeed):
+        from . import _lib
+        lib = _lib.load()
         m = self.model
-        self._static = {k: (v.clone() if isinstance(v, torch.Tensor) else v)
-                        for k, v in m.to_device(example_feed).items()}
+        ps = m.params
+        meta = dfeed["_meta"]
+        key = (meta["text_cap"], meta["img_cap"])
+        static = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in dfeed.items()}
+        # warm-up and capture must not move the weights
+        snap = [t.clone() for t in (ps.flat, ps.accum, ps.accum_update)]
+        step0 = m.global_step
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self._device_step(self._static)
+            for _ in range(self._graph_warmup):
+                self._device_step(static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        from . import _lib
-        lib = _lib.load()
-        self._graph = torch.cuda.CUDAGraph()
+        graph = torch.cuda.CUDAGraph()
         n0 = lib.fvta_launch_count()
-        with torch.cuda.graph(self._graph):
-            self._static_loss = self._device_step(self._static)
+        with torch.cuda.graph(graph):
+            loss = self._device_step(static)
         self.launches_per_step = int(lib.fvta_launch_count() - n0)   # library kernels in the graph
-        m.global_step -= warmup + 1      # warm-up and capture do not count as training steps
-        # ...but they did move the weights: the caller snapshots/restores if that matters
-        self.global_step = m.global_step
-        return self
+        for t, s0 in zip((ps.flat, ps.accum, ps.accum_update), snap):
+            t.copy_(s0)
+        m.global_step = step0
+        self.global_step = step0
+        self._graphs[key] = (graph, static, loss)
+        return self._graphs[key]
 
-    def _load_static(self, feed):
-        for k, v in feed.items():
-            dst = self._static.get(k)
+    def graph_step(self, feed):
+        """Replay the captured step on a new batch (host feed or device step input).  Returns the
+        loss tensor (device)."""
+        dfeed = self.model.to_device(feed)
+        meta = dfeed["_meta"]
+        key = (meta["text_cap"], meta["img_cap"])
+        entry = self._graphs.get(key) or self._capture(dfeed)
+        graph, static, loss = entry
+        for k, v in dfeed.items():
+            dst = static.get(k)
             if isinstance(dst, torch.Tensor):
                 if dst.shape != v.shape:
                     raise ValueError("graph step: %s has shape %s, captured %s (pin the padded shapes)"
                                      % (k, tuple(v.shape), tuple(dst.shape)))
                 dst.copy_(v, non_blocking=True)
-
-    def graph_step(self, feed):
-        """Replay the captured step on a new batch (host or device tensors).  Returns the loss
-        tensor (device)."""
-        self._load_static(feed)
-        self._graph.replay()
+        graph.replay()
         self.model.global_step += 1
         self.global_step = self.model.global_step
-        return self._static_loss
+        return loss
 
     def step(self, sess, batch, get_summary=False):
         """trainer.py:30-40.  ``sess`` is accepted for signature parity (the reference asserts
         a tf.Session; here it is an opaque context and may be None)."""
         batchIdx, batch_data = batch
         feed = self.model.get_feed_dict(batch_data, is_train=True)
-        if getattr(self, "_graph", None) is not None:
+        if getattr(self, "_graphs", None) is not None:
             loss = self.graph_step(feed)
         else:
             loss = self._device_step(self.model.to_device(feed))

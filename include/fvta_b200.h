@@ -151,6 +151,45 @@ int fvta_bilstm_bwd(const FvtaLstmDesc* desc, const float* x, const int32_t* len
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Packed reader: the same BiLSTM over sequences whose valid tokens are PACKED (no padding rows)
+ * and whose outputs are written straight into an output arena at per-sequence row offsets --
+ * which is how all seven text call sites of model_v2.py:694-812 (one shared cell) run as ONE
+ * launch and land directly in the context tensor hall[N,K,M,JMAX,2d] of model_v2.py:862-914
+ * (the tf.pad / tf.stack copies disappear).  fw and bw share `kernel`/`bias`.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B;     /* sequences */
+  int32_t ntok;  /* packed token rows (>= sum of lengths; extra rows are ignored) */
+  int32_t In;    /* input width */
+  int32_t d;     /* hidden size */
+  int32_t Jmax;  /* upper bound on any sequence length */
+} FvtaReaderDesc;
+
+size_t fvta_reader_workspace_bytes(const FvtaReaderDesc* desc);
+size_t fvta_reader_reserve_floats(const FvtaReaderDesc* desc);
+
+/*
+ * x_tok        [ntok,In]   inputs of the valid tokens, sequence after sequence
+ * seq_tok_off  [B] int32   first token row of each sequence
+ * seq_len      [B] int32   valid length (0 allowed)
+ * seq_out_row  [B] int64   arena row receiving step 0 of the sequence (step t -> row+t);
+ *                          negative: outputs are not stored (only `last` is wanted)
+ * out_arena    [rows,2d]   caller-zeroed; fw in [:d], bw in [d:]
+ * last         [B,2d]      final h of each direction
+ */
+int fvta_reader_fwd(const FvtaReaderDesc* desc, const float* x_tok, const int32_t* seq_tok_off,
+                    const int32_t* seq_len, const int64_t* seq_out_row, const float* kernel,
+                    const float* bias, float* out_arena, float* last, float* reserve, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* d_out_arena [rows,2d], d_last [B,2d] (nullable) -> d_x_tok [ntok,In] (overwritten),
+ * d_kernel [In+d,4d], d_bias [4d] ACCUMULATED (+=). */
+int fvta_reader_bwd(const FvtaReaderDesc* desc, const float* x_tok, const int32_t* seq_tok_off,
+                    const int32_t* seq_len, const int64_t* seq_out_row, const float* kernel,
+                    const float* reserve, const float* d_out_arena, const float* d_last, float* d_x_tok,
+                    float* d_kernel, float* d_bias, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * fp32 GEMM with fused epilogue: C[M,N] = act(A[M,K] @ B[K,N] + bias[N]).
  * Replaces `linear` (model_v2.py:75-100: tf.matmul + bias + optional tanh).
  * act: 0 none, 1 tanh, 2 relu.  trans_a/trans_b: operand stored transposed.
