@@ -91,6 +91,18 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
   }
 }
 
+// bias + activation over a finished split-K sum
+__global__ void gemm_epilogue(int M, int N, float* __restrict__ C, int ldc, const float* __restrict__ bias, int act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const int m = i / N, n = i - m * N;
+  float v = C[(size_t)m * ldc + n];
+  if (bias) v += bias[n];
+  if (act == 1) v = tanhf(v);
+  else if (act == 2) v = fmaxf(v, 0.f);
+  C[(size_t)m * ldc + n] = v;
+}
+
 }  // namespace fvta
 
 extern "C" int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t trans_a,
@@ -105,20 +117,36 @@ extern "C" int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_
   if (grid.y > 65535) return FVTA_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   // Weight-gradient GEMMs are short and fat (M, N ~ 200, K = tokens): split K over the SMs.
+  // Short-and-fat products (weight gradients: M, N ~ 200, K = tokens; the image transform:
+  // M = photos, K = 2537) leave most SMs idle with one CTA per output tile: split K over the SMs
+  // and add the partial tiles atomically.  A non-accumulating call zeroes C first and applies
+  // bias / activation in a second tiny kernel.
   int kps = K > 0 ? K : 1;
-  if (accumulate && K >= 512) {
+  bool split_epilogue = false;
+  if (K >= 512) {
     const int tiles = (int)(grid.x * grid.y);
-    int splits = (2 * 148 + tiles - 1) / tiles;
+    int splits = (148 + tiles - 1) / tiles;          // about one wave; more only adds atomic traffic
     const int max_splits = (K + 127) / 128;
     if (splits > max_splits) splits = max_splits;
     if (splits > 1) {
       kps = round_up((K + splits - 1) / splits, BK);
       grid.z = (K + kps - 1) / kps;
+      if (!accumulate) {
+        cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st);
+        if (e != cudaSuccess) { set_last_error("gemm memset", e); return FVTA_E_LAUNCH; }
+        split_epilogue = (bias != nullptr) || act != 0;
+        accumulate = 1;
+      }
     }
   }
-  if (!trans_a && !trans_b) gemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate, kps);
-  else if (!trans_a && trans_b) gemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate, kps);
-  else if (trans_a && !trans_b) gemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate, kps);
-  else gemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, bias, act, C, ldc, accumulate, kps);
-  return check_launch("gemm_kernel");
+  const float* kbias = split_epilogue ? nullptr : bias;
+  const int kact = split_epilogue ? 0 : act;
+  if (!trans_a && !trans_b) gemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, kbias, kact, C, ldc, accumulate, kps);
+  else if (!trans_a && trans_b) gemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, kbias, kact, C, ldc, accumulate, kps);
+  else if (trans_a && !trans_b) gemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, kbias, kact, C, ldc, accumulate, kps);
+  else gemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, kbias, kact, C, ldc, accumulate, kps);
+  int rc = check_launch("gemm_kernel");
+  if (rc || !split_epilogue) return rc;
+  gemm_epilogue<<<(M * N + 255) / 256, 256, 0, st>>>(M, N, C, ldc, bias, act);
+  return check_launch("gemm_epilogue");
 }

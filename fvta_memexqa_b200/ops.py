@@ -182,7 +182,8 @@ class LinearFn(torch.autograd.Function):
         dy = dy.reshape(-1, W.shape[1]).contiguous()
         if ctx.add_tanh:
             dy = dy * (1.0 - y * y)
-        dx = gemm(dy, W, trans_b=True).reshape(ctx.xshape)
+        # the image features and other fed inputs need no gradient: skip that GEMM
+        dx = gemm(dy, W, trans_b=True).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
         dW = gemm(flat, dy, trans_a=True)
         db = dy.sum(0)
         return dx, dW, db, None
