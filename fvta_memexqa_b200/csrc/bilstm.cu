@@ -47,6 +47,101 @@ struct SeqAddr {
   __device__ __forceinline__ long long out0(int b, int J) const { return out_row ? out_row[b] : (long long)b * J; }
 };
 
+// Forward recurrence for d <= 64: thread g keeps column g of W_h in registers, h lives in shared
+// memory as float4 rows (one broadcast LDS.128 feeds four FMAs of each of the kSG sequences) and
+// the projected input of the NEXT step is fetched while the current step computes.
+template <int D4MAX>
+__global__ void __launch_bounds__(256) bilstm_rec_fwd_reg(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
+                                                          const float* __restrict__ xp_fw, const float* __restrict__ xp_bw,
+                                                          const float* __restrict__ wh_fw, const float* __restrict__ wh_bw,
+                                                          float* __restrict__ out, float* __restrict__ last,
+                                                          float* __restrict__ reserve) {
+  constexpr int HS = 4 * D4MAX;                      // padded h row
+  __shared__ __align__(16) float h_s[kSG][HS];
+  __shared__ float c_s[kSG][HS];
+  __shared__ float g_s[kSG][4 * HS];
+  __shared__ int len_s[kSG];
+  __shared__ int tok_s[kSG];
+  __shared__ long long orow_s[kSG];
+  const int d = L.d, G = 4 * d;
+  const int dir = blockIdx.y;
+  const float* wh_g = dir == 0 ? wh_fw : wh_bw;
+  const float* xp = dir == 0 ? xp_fw : xp_bw;
+  const int b0 = blockIdx.x * kSG;
+  const int g = threadIdx.x;
+  float w[HS];
+#pragma unroll
+  for (int e = 0; e < HS; ++e) w[e] = (g < G && e < d) ? wh_g[(size_t)e * G + g] : 0.f;
+  for (int i = threadIdx.x; i < kSG * HS; i += blockDim.x) { (&h_s[0][0])[i] = 0.f; (&c_s[0][0])[i] = 0.f; }
+  if (threadIdx.x < kSG) {
+    const int b = b0 + threadIdx.x;
+    len_s[threadIdx.x] = (b < L.B) ? min(lens[b], L.J) : 0;
+    tok_s[threadIdx.x] = (b < L.B) ? A.tok0(b, L.J) : 0;
+    orow_s[threadIdx.x] = (b < L.B) ? A.out0(b, L.J) : -1;
+  }
+  __syncthreads();
+  int maxlen = 0;
+#pragma unroll
+  for (int s = 0; s < kSG; ++s) maxlen = max(maxlen, len_s[s]);
+  auto fetch = [&](int step, float (&dst)[kSG]) {
+#pragma unroll
+    for (int s = 0; s < kSG; ++s) {
+      const int len = len_s[s];
+      const int t = dir == 0 ? step : len - 1 - step;
+      dst[s] = (g < G && step < len) ? xp[((size_t)tok_s[s] + t) * G + g] : 0.f;
+    }
+  };
+  float xnext[kSG];
+  fetch(0, xnext);
+  for (int step = 0; step < maxlen; ++step) {
+    float acc[kSG];
+#pragma unroll
+    for (int s = 0; s < kSG; ++s) acc[s] = xnext[s];
+    if (step + 1 < maxlen) fetch(step + 1, xnext);
+#pragma unroll
+    for (int e4 = 0; e4 < D4MAX; ++e4) {
+#pragma unroll
+      for (int s = 0; s < kSG; ++s) {
+        const float4 hv = *reinterpret_cast<const float4*>(&h_s[s][e4 * 4]);
+        acc[s] = fmaf(hv.x, w[e4 * 4 + 0], acc[s]);
+        acc[s] = fmaf(hv.y, w[e4 * 4 + 1], acc[s]);
+        acc[s] = fmaf(hv.z, w[e4 * 4 + 2], acc[s]);
+        acc[s] = fmaf(hv.w, w[e4 * 4 + 3], acc[s]);
+      }
+    }
+    if (g < G) {
+#pragma unroll
+      for (int s = 0; s < kSG; ++s) g_s[s][g] = acc[s];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) {
+      const int s = i / d, e = i - s * d;
+      const int len = len_s[s];
+      if (step < len) {
+        const int t = dir == 0 ? step : len - 1 - step;
+        const float* gs = g_s[s];
+        const float ig = sigmoidf_(gs[e]);
+        const float jg = tanhf(gs[d + e]);
+        const float fg = sigmoidf_(gs[2 * d + e] + 1.0f);  // forget_bias = 1.0 [TF]
+        const float og = sigmoidf_(gs[3 * d + e]);
+        const float hp = h_s[s][e];
+        const float c = fmaf(c_s[s][e], fg, ig * jg);
+        const float h = tanhf(c) * og;
+        c_s[s][e] = c;
+        h_s[s][e] = h;
+        if (orow_s[s] >= 0) out[((size_t)orow_s[s] + t) * 2 * d + dir * d + e] = h;
+        float* r = reserve + ((size_t)dir * A.ntok + tok_s[s] + t) * kResW * d;
+        r[e] = ig; r[d + e] = jg; r[2 * d + e] = fg; r[3 * d + e] = og; r[4 * d + e] = c; r[5 * d + e] = hp;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) {
+    const int s = i / d, e = i - s * d;
+    if (b0 + s < L.B) last[(size_t)(b0 + s) * 2 * d + dir * d + e] = h_s[s][e];
+  }
+}
+
 // grid (ceil(B/kSG), 2); block: multiple of 32
 __global__ void bilstm_rec_fwd(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
                                const float* __restrict__ xp_fw, const float* __restrict__ xp_bw,
@@ -211,6 +306,16 @@ __global__ void bilstm_rec_bwd(FvtaLstmDesc L, SeqAddr A, const int32_t* __restr
   }
 }
 
+__global__ void add_inplace4(size_t n4, float4* __restrict__ a, const float4* __restrict__ b) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    float4 x = a[i];
+    const float4 y = b[i];
+    x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    a[i] = x;
+  }
+}
+
 // out[n] += sum_m A[m][n]
 __global__ void colsum_accumulate(int M, int N, const float* __restrict__ A, int lda, float* __restrict__ out) {
   __shared__ float red[8][33];
@@ -266,6 +371,15 @@ static int lstm_fwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x
   if (e != cudaSuccess) { set_last_error("bilstm_rec_fwd smem attr", e); return FVTA_E_LAUNCH; }
   int threads = round_up(G < 1024 ? G : 1024, 32);
   dim3 grid((L.B + kSG - 1) / kSG, 2);
+  if (L.d <= 64) {   // the reference's hidden sizes (50, 100 is the flag default): W_h column in registers
+    if (L.d <= 52)
+      bilstm_rec_fwd_reg<13><<<grid, threads, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+                                                        kernel_bw + (size_t)L.In * G, out, last, reserve);
+    else
+      bilstm_rec_fwd_reg<16><<<grid, threads, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+                                                        kernel_bw + (size_t)L.In * G, out, last, reserve);
+    return check_launch("bilstm_rec_fwd_reg");
+  }
   bilstm_rec_fwd<<<grid, threads, plan.bytes, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
                                                    kernel_bw + (size_t)L.In * G, out, last, reserve);
   return check_launch("bilstm_rec_fwd");
@@ -292,6 +406,27 @@ static int lstm_bwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x
   if (rc) return rc;
   const float* dgs[2] = {dg, dg + (size_t)NT * G};
   const float* ress[2] = {reserve, reserve + (size_t)NT * kResW * L.d};
+  if (kernel_fw == kernel_bw && d_kernel_fw == d_kernel_bw && d_bias_fw == d_bias_bw) {
+    // One cell for both directions (the reference's case): x is common, so
+    //   d_x = (dg_fw + dg_bw) @ Wx^T,   d kernel[:In] += x^T @ (dg_fw + dg_bw),
+    // and h_prev / dg of the two directions are contiguous in memory, so
+    //   d kernel[In:] += [h_prev_fw ; h_prev_bw]^T @ [dg_fw ; dg_bw]   is one product with K = 2*ntok.
+    rc = fvta_gemm(L.d, G, 2 * NT, reserve + 5 * L.d, kResW * L.d, 1, dg, G, 0, nullptr, 0,
+                   d_kernel_fw + (size_t)L.In * G, G, 1, stream);
+    if (rc) return rc;
+    const size_t n4 = ((size_t)NT * G) / 4;   // G = 4d: always a multiple of 4
+    add_inplace4<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, reinterpret_cast<float4*>(dg),
+                                                               reinterpret_cast<const float4*>(dgs[1]));
+    rc = check_launch("add_inplace4");
+    if (rc) return rc;
+    rc = fvta_gemm(NT, L.In, G, dg, G, 0, kernel_fw, G, 1, nullptr, 0, d_x, L.In, 0, stream);
+    if (rc) return rc;
+    rc = fvta_gemm(L.In, G, NT, x, L.In, 1, dg, G, 0, nullptr, 0, d_kernel_fw, G, 1, stream);
+    if (rc) return rc;
+    dim3 cg((G + 31) / 32, 64);
+    colsum_accumulate<<<cg, 256, 0, st>>>(NT, G, dg, G, d_bias_fw);
+    return check_launch("colsum_accumulate");
+  }
   // d_x = dg_fw @ Wx_fw^T + dg_bw @ Wx_bw^T
   rc = fvta_gemm(NT, L.In, G, dgs[0], G, 0, kernel_fw, G, 1, nullptr, 0, d_x, L.In, 0, stream);
   if (rc) return rc;

@@ -123,10 +123,10 @@ extern "C" int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_
   // bias / activation in a second tiny kernel.
   int kps = K > 0 ? K : 1;
   bool split_epilogue = false;
-  if (K >= 512) {
+  if (K >= 128) {
     const int tiles = (int)(grid.x * grid.y);
     int splits = (148 + tiles - 1) / tiles;          // about one wave; more only adds atomic traffic
-    const int max_splits = (K + 127) / 128;
+    const int max_splits = (K + 63) / 64;            // at least four k-tiles per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits > 1) {
       kps = round_up((K + splits - 1) / splits, BK);
