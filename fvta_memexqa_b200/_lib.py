@@ -43,6 +43,7 @@ SYMBOLS = {
     "fvta_version": (ctypes.c_int, []),
     "fvta_last_error": (ctypes.c_char_p, []),
     "fvta_launch_count": (ctypes.c_ulonglong, []),
+    "fvta_attn_fwd_set_stages": (None, [ctypes.c_int]),
     "fvta_attn_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(FvtaAttnDesc)]),
     "fvta_attn_stats_floats": (ctypes.c_size_t, [ctypes.POINTER(FvtaAttnDesc)]),
     "fvta_attn_fwd": (ctypes.c_int, [ctypes.POINTER(FvtaAttnDesc), c_float_p, c_u8_p, c_float_p, c_u8_p,
@@ -73,6 +74,10 @@ SYMBOLS = {
     "fvta_gemm": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_float_p, ctypes.c_int32,
                                  ctypes.c_int32, c_float_p, ctypes.c_int32, ctypes.c_int32, c_float_p,
                                  ctypes.c_int32, c_float_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
+    "fvta_charcnn_fwd": (ctypes.c_int, [ctypes.c_int32] * 5 + [c_i32_p, c_float_p, c_float_p, c_float_p, c_u8_p,
+                                                                 ctypes.c_void_p]),
+    "fvta_charcnn_bwd": (ctypes.c_int, [ctypes.c_int32] * 5 + [c_i32_p, c_float_p, c_u8_p, c_float_p, c_float_p,
+                                                                 c_float_p, ctypes.c_void_p]),
     "fvta_adadelta": (ctypes.c_int, [ctypes.c_int64, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                      ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                      ctypes.c_void_p]),

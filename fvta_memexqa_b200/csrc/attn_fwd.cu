@@ -371,6 +371,11 @@ int attn_fwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hal
                     const uint8_t* hq_mask, float* ws, float* g1_all, float* a_logits, float* c_col, float* stats,
                     cudaStream_t st);
 
+// Diagnostic: which stages fvta_attn_fwd launches (bit 0 operand folding, bit 1 the tile kernel,
+// bit 2 the combine).  bench.py times the dominant kernel alone with stages = 2 after one full
+// call has filled the workspace.  Default 7; not for production use.
+int g_attn_stages = 7;
+
 // FVTA_FORCE_FFMA=1 pins the CUDA-core forward (A/B measurements, debugging)
 static bool fvta_force_ffma() {
   static int v = -1;
@@ -410,14 +415,17 @@ extern "C" int fvta_attn_fwd(const FvtaAttnDesc* desc, const float* hall, const 
   if (attn_tile_smem_bytes(d, L.JQP, L.Dp) > 227 * 1024) return FVTA_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
-  rc = attn_prep_launch(d, L, *params, hq, lq, ws, st);
-  if (rc) return rc;
+  const int stages = g_attn_stages;
+  if (stages & 1) {
+    rc = attn_prep_launch(d, L, *params, hq, lq, ws, st);
+    if (rc) return rc;
+  }
   if (warp_h == nullptr && !fvta_force_ffma()) {
     // tensor-core path (attn_fwd_tc.cu) when the shape/flags are covered; 1 = not covered
     rc = attn_fwd_tc_try(d, L, hall, hall_mask, hq_mask, ws, g1_all, a_logits, c_col, stats, st);
     if (rc <= 0) return rc;
   }
-  switch (L.JQP) {
+  if (stages & 2) switch (L.JQP) {
     case 4: rc = launch_tile_fwd<1>(d, L, hall, hall_mask, hq_mask, ws, a_logits, c_col, warp_h, st); break;
     case 8: rc = launch_tile_fwd<2>(d, L, hall, hall_mask, hq_mask, ws, a_logits, c_col, warp_h, st); break;
     case 16: rc = launch_tile_fwd<4>(d, L, hall, hall_mask, hq_mask, ws, a_logits, c_col, warp_h, st); break;
@@ -427,5 +435,8 @@ extern "C" int fvta_attn_fwd(const FvtaAttnDesc* desc, const float* hall, const 
     default: return FVTA_E_SHAPE;
   }
   if (rc) return rc;
+  if (!(stages & 4)) return FVTA_OK;
   return attn_combine_launch(d, ws + L.part_stat, ws + L.part_o, g1_all, stats, L.nt, L.Dp, st);
 }
+
+extern "C" void fvta_attn_fwd_set_stages(int mask) { fvta::g_attn_stages = mask & 7; }

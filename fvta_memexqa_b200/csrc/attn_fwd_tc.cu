@@ -42,6 +42,7 @@ __device__ long long g_tc_trace[4][kTraceTiles][8];
 
 int attn_combine_launch(const FvtaAttnDesc& d, const float* part_stat, const float* part_o, float* g1_all,
                         float* stats, int nt, int Dp, cudaStream_t st);
+extern int g_attn_stages;
 
 constexpr int kTcThreads = 576;  // warps 0-7 split, 8-15 softmax, warp 16 TMA, warp 17 MMA
 constexpr int kTcStages = 3;
@@ -635,9 +636,13 @@ int attn_fwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hal
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return 1;
   __half* qB = reinterpret_cast<__half*>(ws + L.qB);
-  attn_prep_qb<<<d.N, 256, 0, st>>>(d, ws + L.qeffT, qB, L.Dp, L.JQP, pl.KC);
-  int rc = check_launch("attn_prep_qb");
-  if (rc) return rc;
+  int rc = FVTA_OK;
+  if (g_attn_stages & 1) {
+    attn_prep_qb<<<d.N, 256, 0, st>>>(d, ws + L.qeffT, qB, L.Dp, L.JQP, pl.KC);
+    rc = check_launch("attn_prep_qb");
+    if (rc) return rc;
+  }
+  if (!(g_attn_stages & 2)) return (g_attn_stages & 4) ? attn_combine_launch(d, ws + L.part_stat, ws + L.part_o, g1_all, stats, pl.slabs, L.Dp, st) : FVTA_OK;
   const bool has_lin = (d.simi == 1 || d.simi == 3);   // w_lin is identically zero otherwise
   auto kern = has_lin ? attn_fwd_tc<true> : attn_fwd_tc<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
@@ -648,6 +653,7 @@ int attn_fwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hal
                                           L.JQP);
   rc = check_launch("attn_fwd_tc");
   if (rc) return rc;
+  if (!(g_attn_stages & 4)) return FVTA_OK;
   return attn_combine_launch(d, ws + L.part_stat, ws + L.part_o, g1_all, stats, pl.slabs, L.Dp, st);
 }
 

@@ -1,0 +1,121 @@
+// Character CNN over words (replaces conv1d, model_v2.py:52-70: 1 x height VALID conv over the
+// embedded characters, + bias, ReLU, max over positions) for the undropped case.
+//
+// The conv output at a position depends only on the `height` character IDS in its window:
+//   out[w,p,:] = bias + sum_h  char_emb[id[w,p+h]] @ filter[h]      = bias + sum_h table[h][id[w,p+h]][:]
+// with table[h] = char_emb @ filter[h]  ([VC,cdim] x [cdim,cw], a few MFLOP, done by the caller).
+// So instead of a [words*positions, height*cdim] x [height*cdim, cw] GEMM (4 GFLOP per step at
+// the reference shape, the largest FLOP term of the whole model) the layer is a gather-add over
+// an L2-resident table: 5 loads per output.  Same function; only the fp32 summation order
+// differs (per-tap partial sums are formed first).
+//
+// Backward routes d y through the max (first arg-max position; ReLU-dead outputs get nothing)
+// into d table with atomics; the caller turns d table into d char_emb / d filter with the same
+// tiny matrix products.
+#include "common.cuh"
+
+namespace fvta {
+
+constexpr int kCnnWordsPerBlock = 8;
+
+// grid ceil(ntok / 8), block 8 x 32: lane = group of 4 output channels, threadIdx.y = word
+__global__ void charcnn_fwd_kernel(int ntok, int W, int VC, int cw, int height, const int32_t* __restrict__ ids,
+                                   const float* __restrict__ table, const float* __restrict__ bias,
+                                   float* __restrict__ y, uint8_t* __restrict__ argpos) {
+  __shared__ int id_s[kCnnWordsPerBlock][64];
+  const int wl = threadIdx.y, lane = threadIdx.x;
+  const int w = blockIdx.x * kCnnWordsPerBlock + wl;
+  if (w < ntok)
+    for (int i = lane; i < W; i += 32) {
+      const int v = ids[(size_t)w * W + i];
+      id_s[wl][i] = (v >= 0 && v < VC) ? v : 0;
+    }
+  __syncthreads();
+  if (w >= ntok) return;
+  const int npos = W - height + 1;
+  const int cw4 = cw >> 2;
+  for (int o4 = lane; o4 < cw4; o4 += 32) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias + o4 * 4);
+    float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    int bp0 = 0, bp1 = 0, bp2 = 0, bp3 = 0;
+    for (int p = 0; p < npos; ++p) {
+      float4 a = b4;
+      for (int h = 0; h < height; ++h) {
+        const float4 t = *reinterpret_cast<const float4*>(table + ((size_t)h * VC + id_s[wl][p + h]) * cw + o4 * 4);
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      if (a.x > best.x) { best.x = a.x; bp0 = p; }
+      if (a.y > best.y) { best.y = a.y; bp1 = p; }
+      if (a.z > best.z) { best.z = a.z; bp2 = p; }
+      if (a.w > best.w) { best.w = a.w; bp3 = p; }
+    }
+    // relu(max_p) == max_p relu
+    const float4 out = make_float4(fmaxf(best.x, 0.f), fmaxf(best.y, 0.f), fmaxf(best.z, 0.f), fmaxf(best.w, 0.f));
+    *reinterpret_cast<float4*>(y + (size_t)w * cw + o4 * 4) = out;
+    *reinterpret_cast<uchar4*>(argpos + (size_t)w * cw + o4 * 4) =
+        make_uchar4((unsigned char)bp0, (unsigned char)bp1, (unsigned char)bp2, (unsigned char)bp3);
+  }
+}
+
+__global__ void charcnn_bwd_kernel(int ntok, int W, int VC, int cw, int height, const int32_t* __restrict__ ids,
+                                   const float* __restrict__ y, const uint8_t* __restrict__ argpos,
+                                   const float* __restrict__ dy, float* __restrict__ d_table,
+                                   float* __restrict__ d_bias) {
+  __shared__ int id_s[kCnnWordsPerBlock][64];
+  __shared__ float db_s[kCnnWordsPerBlock][129];
+  const int wl = threadIdx.y, lane = threadIdx.x;
+  const int w = blockIdx.x * kCnnWordsPerBlock + wl;
+  if (w < ntok)
+    for (int i = lane; i < W; i += 32) {
+      const int v = ids[(size_t)w * W + i];
+      id_s[wl][i] = (v >= 0 && v < VC) ? v : 0;
+    }
+  __syncthreads();
+  for (int o = lane; o < cw; o += 32) {
+    float g = 0.f;
+    if (w < ntok && y[(size_t)w * cw + o] > 0.f) {   // ReLU alive
+      g = dy[(size_t)w * cw + o];
+      const int p = argpos[(size_t)w * cw + o];
+      for (int h = 0; h < height; ++h) atomicAdd(d_table + ((size_t)h * VC + id_s[wl][p + h]) * cw + o, g);
+    }
+    if (o < 128) db_s[wl][o] = g;
+  }
+  __syncthreads();
+  if (wl == 0)
+    for (int o = lane; o < cw && o < 128; o += 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < kCnnWordsPerBlock; ++i) s += db_s[i][o];
+      if (s != 0.f) atomicAdd(d_bias + o, s);
+    }
+}
+
+}  // namespace fvta
+
+extern "C" int fvta_charcnn_fwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t height,
+                                const int32_t* ids, const float* table, const float* bias, float* y,
+                                uint8_t* argpos, void* stream) {
+  using namespace fvta;
+  if (ntok < 0 || W <= 0 || VC <= 0 || cw <= 0 || height <= 0) return FVTA_E_BADARG;
+  if (ntok == 0) return FVTA_OK;
+  if (!ids || !table || !bias || !y || !argpos) return FVTA_E_BADARG;
+  if ((cw & 3) != 0 || cw > 128 || W > 64 || W < height || W - height + 1 > 255) return FVTA_E_SHAPE;
+  dim3 block(32, kCnnWordsPerBlock);
+  charcnn_fwd_kernel<<<(ntok + kCnnWordsPerBlock - 1) / kCnnWordsPerBlock, block, 0, (cudaStream_t)stream>>>(
+      ntok, W, VC, cw, height, ids, table, bias, y, argpos);
+  return check_launch("charcnn_fwd_kernel");
+}
+
+extern "C" int fvta_charcnn_bwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t height,
+                                const int32_t* ids, const float* y, const uint8_t* argpos, const float* dy,
+                                float* d_table, float* d_bias, void* stream) {
+  using namespace fvta;
+  if (ntok < 0 || W <= 0 || VC <= 0 || cw <= 0 || height <= 0) return FVTA_E_BADARG;
+  if (ntok == 0) return FVTA_OK;
+  if (!ids || !y || !argpos || !dy || !d_table || !d_bias) return FVTA_E_BADARG;
+  if ((cw & 3) != 0 || cw > 128 || W > 64 || W < height) return FVTA_E_SHAPE;
+  dim3 block(32, kCnnWordsPerBlock);
+  charcnn_bwd_kernel<<<(ntok + kCnnWordsPerBlock - 1) / kCnnWordsPerBlock, block, 0, (cudaStream_t)stream>>>(
+      ntok, W, VC, cw, height, ids, y, argpos, dy, d_table, d_bias);
+  return check_launch("charcnn_bwd_kernel");
+}

@@ -267,11 +267,18 @@ class Model:
                         emb((ids - VW).clamp(min=0), glove))
         if not cfg.use_char:
             return A
-        Ac = emb(ids_c, v["emb/var/char_emb"])                          # [cap, W, cdim]
-        if is_train and cfg.keep_prob < 1.0:                            # conv1d input dropout (:60-61)
-            Ac = torch.nn.functional.dropout(Ac, 1.0 - cfg.keep_prob, True)
         filt = v["emb/conv/conv1d/filter"]                              # [1,5,cdim,cwdim]
         height, cdim, cw = filt.shape[1], filt.shape[2], filt.shape[3]
+        dropped = is_train and cfg.keep_prob < 1.0                      # conv1d input dropout (:60-61)
+        if not dropped and cw % 4 == 0 and cw <= 128 and ids_c.shape[1] <= 64:
+            # a window's conv output depends only on its `height` char ids: tabulate
+            # char_emb @ filter[h] once ([height,VC,cw], a few MFLOP) and gather-add (csrc/charcnn.cu)
+            table = torch.matmul(v["emb/var/char_emb"].unsqueeze(0), filt[0])
+            xc = ops.CharCnnTableFn.apply(table, v["emb/conv/conv1d/bias"], ids_c)
+            return torch.cat([xc, A], dim=-1)
+        Ac = emb(ids_c.long(), v["emb/var/char_emb"])                   # [cap, W, cdim]
+        if dropped:
+            Ac = torch.nn.functional.dropout(Ac, 1.0 - cfg.keep_prob, True)
         win = Ac.unfold(1, height, 1)                                   # [cap, W-4, cdim, 5]
         npos = win.shape[1]
         flat = win.reshape(-1, cdim * height)

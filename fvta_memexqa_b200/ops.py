@@ -67,7 +67,7 @@ def _attn_params(W, b, WH_W, WH_b, WC_W, WC_b):
 
 
 def attn_forward(cfg, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=None,
-                 want_logits=False, want_c=False, want_warp_h=False):
+                 want_logits=False, want_c=False, want_warp_h=False, reuse=None):
     """fvta_attn_fwd.  hall [N,K,T,D], hq [N,JQ,D] -> dict(g1_all, a_logits, c_col, warp_h, stats)."""
     lib = _lib.load()
     f32 = torch.float32
@@ -87,10 +87,13 @@ def attn_forward(cfg, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W=None, WH_b=No
     if ws_bytes == 0:
         raise _lib.FvtaError("fvta_attn: unsupported shape/flags N=%d K=%d T=%d D=%d JQ=%d simi=%d"
                              % (N, K, T, D, JQ, cfg.simiMatrix))
-    ws = torch.empty(ws_bytes // 4, dtype=f32, device=dev)
-    stats = torch.empty(lib.fvta_attn_stats_floats(ctypes.byref(desc)), dtype=f32, device=dev)
-    g1_all = torch.empty(N, D, dtype=f32, device=dev)
-    a_logits = torch.empty(N, K, T, JQ, dtype=f32, device=dev) if want_logits else None
+    if reuse is not None:     # benchmark loops: reuse the buffers of an earlier call (no allocator traffic)
+        ws, stats, g1_all, a_logits = reuse["ws"], reuse["stats"], reuse["g1_all"], reuse["a_logits"]
+    else:
+        ws = torch.empty(ws_bytes // 4, dtype=f32, device=dev)
+        stats = torch.empty(lib.fvta_attn_stats_floats(ctypes.byref(desc)), dtype=f32, device=dev)
+        g1_all = torch.empty(N, D, dtype=f32, device=dev)
+        a_logits = torch.empty(N, K, T, JQ, dtype=f32, device=dev) if want_logits else None
     c_col = torch.empty(N, T, dtype=f32, device=dev) if (want_c and cfg.use_time_warp) else None
     warp_h = torch.empty(N, K, T, D, dtype=f32, device=dev) if (want_warp_h and cfg.use_time_warp) else None
     params = _attn_params(W, b, WH_W, WH_b, WC_W, WC_b)
@@ -365,3 +368,44 @@ class ReaderFn(torch.autograd.Function):
             outs.append((dx, dk, db))
         (dxt, dkt, dbt), (dxi, dki, dbi) = outs
         return (dxt, dxi, None, None, None, None, None, None, dkt, dbt, dki, dbi, None, None, None)
+
+
+# ---------------------------------------------------------------------------------------------
+# character CNN through the per-character table
+# ---------------------------------------------------------------------------------------------
+class CharCnnTableFn(torch.autograd.Function):
+    """y[w,:] = relu(max_p(bias + sum_h table[h][ids[w,p+h]]))  (fvta_charcnn_fwd/bwd).
+    table [height,VC,cw] = char_emb @ filter[h] is produced by the caller with ordinary (tiny)
+    matrix products, so autograd carries d table back to char_emb and the filter."""
+
+    @staticmethod
+    def forward(ctx, table, bias, ids):
+        lib = _lib.load()
+        f32 = torch.float32
+        table, bias = _req(table, f32, "table"), _req(bias, f32, "bias")
+        ids = _req(ids, torch.int32, "char ids")
+        H, VC, cw = table.shape
+        ntok, W = ids.shape
+        y = torch.empty(ntok, cw, dtype=f32, device=table.device)
+        argpos = torch.empty(ntok, cw, dtype=torch.uint8, device=table.device)
+        rc = lib.fvta_charcnn_fwd(ntok, W, VC, cw, H, _ptr(ids), _ptr(table), _ptr(bias), _ptr(y), _ptr(argpos),
+                                  _stream())
+        check(rc, "fvta_charcnn_fwd")
+        ctx.save_for_backward(ids, y, argpos)
+        ctx.shape = (H, VC, cw, ntok, W)
+        ctx.mark_non_differentiable(argpos)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        f32 = torch.float32
+        ids, y, argpos = ctx.saved_tensors
+        H, VC, cw, ntok, W = ctx.shape
+        dy = _req(dy, f32, "dy")
+        d_table = torch.zeros(H, VC, cw, dtype=f32, device=dy.device)
+        d_bias = torch.zeros(cw, dtype=f32, device=dy.device)
+        rc = lib.fvta_charcnn_bwd(ntok, W, VC, cw, H, _ptr(ids), _ptr(y), _ptr(argpos), _ptr(dy), _ptr(d_table),
+                                  _ptr(d_bias), _stream())
+        check(rc, "fvta_charcnn_bwd")
+        return d_table, d_bias, None

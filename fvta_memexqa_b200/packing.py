@@ -64,7 +64,7 @@ def build_pack(feed, config, bucket=512):
         ids.append(feed[site].reshape(-1, J)[prefix].long())
         if use_char:
             c = feed[site + "_c"]
-            cids.append(c.reshape(-1, J, c.shape[-1])[prefix].long())
+            cids.append(c.reshape(-1, J, c.shape[-1])[prefix].to(torch.int32))
         lens_all.append(lens)
         outs.append(seq_out[site].long())
         ranges[site] = (b0, b0 + m2.shape[0])
@@ -80,7 +80,7 @@ def build_pack(feed, config, bucket=512):
          "text_seq_out": torch.cat(outs)}
     if use_char:
         W = cids[0].shape[-1]
-        tc = torch.zeros(cap, W, dtype=torch.int64)
+        tc = torch.zeros(cap, W, dtype=torch.int32)
         tc[:ntok] = torch.cat(cids)
         t["text_tok_cids"] = tc
     # image reader: sequences (n, m) over photos; tokens are rows of image_emb_mat

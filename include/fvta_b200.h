@@ -77,6 +77,10 @@ typedef struct {      /* gradients, same shapes as FvtaAttnParams; each is OVERW
   float* WC_b;
 } FvtaAttnGrads;
 
+/* Diagnostic knob for benchmarks: which stages fvta_attn_fwd launches -- bit 0 operand folding,
+ * bit 1 the tile kernel, bit 2 the combine (default 7).  Process-wide; leave at 7 in production. */
+void fvta_attn_fwd_set_stages(int mask);
+
 /* Bytes of scratch the fwd/bwd calls need, and floats of `stats` fwd saves for bwd. */
 size_t fvta_attn_workspace_bytes(const FvtaAttnDesc* desc);
 size_t fvta_attn_stats_floats(const FvtaAttnDesc* desc);
@@ -198,6 +202,20 @@ int fvta_reader_bwd(const FvtaReaderDesc* desc, const float* x_tok, const int32_
 int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t trans_a,
               const float* B, int32_t ldb, int32_t trans_b, const float* bias, int32_t act,
               float* C, int32_t ldc, int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Character CNN (replaces conv1d, model_v2.py:52-70, when its input dropout is off): the conv
+ * output of a window depends only on its `height` character ids, so with
+ * table[h] = char_emb @ filter[h] (caller, [height,VC,cw]) the layer is
+ *   y[w,:] = relu( max_p ( bias + sum_h table[h][ids[w,p+h]][:] ) ),  p in [0, W-height].
+ * argpos [ntok,cw] u8 records the arg-max position for the backward, which accumulates
+ * d_table / d_bias (+=, caller zeroes them).  cw % 4 == 0, cw <= 128, W <= 64.
+ * ---------------------------------------------------------------------------------------- */
+int fvta_charcnn_fwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t height, const int32_t* ids,
+                     const float* table, const float* bias, float* y, uint8_t* argpos, void* stream);
+int fvta_charcnn_bwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t height, const int32_t* ids,
+                     const float* y, const uint8_t* argpos, const float* dy, float* d_table, float* d_bias,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Adadelta over one flat buffer.  Replaces tf.train.AdadeltaOptimizer(lr).apply_gradients

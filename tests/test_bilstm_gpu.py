@@ -80,3 +80,38 @@ def test_bilstm_parity(cuda_device, case):
     # outputs past the length are exactly zero
     pad = (torch.arange(J).unsqueeze(0) >= lens.unsqueeze(1))
     assert out.detach().cpu()[pad].abs().max().item() == 0.0 if pad.any() else True
+
+
+@pytest.mark.parametrize("shape", [(7, 6, 15, 6, 8), (300, 16, 80, 100, 100), (33, 9, 40, 12, 24)])
+def test_charcnn_table_parity(cuda_device, shape):
+    """fvta_charcnn_fwd/bwd (per-character table + gather-add) vs the oracle's conv1d
+    (model_v2.py:52-70): outputs and the gradients of char_emb, filter and bias."""
+    ntok, W, VC, cdim, cw = shape
+    dev = cuda_device
+    g = torch.Generator().manual_seed(ntok)
+    ids = torch.randint(0, VC, (ntok, W), generator=g)
+    emb = torch.randn(VC, cdim, generator=g) * 0.5
+    filt = torch.randn(1, 5, cdim, cw, generator=g) * 0.1
+    bias = torch.randn(cw, generator=g) * 0.1
+    dy = torch.randn(ntok, cw, generator=g)
+
+    def oracle(dtype):
+        e = emb.to(dtype).clone().requires_grad_(True)
+        f = filt.to(dtype).clone().requires_grad_(True)
+        b = bias.to(dtype).clone().requires_grad_(True)
+        x = e[ids].unsqueeze(0)                      # [1, ntok, W, cdim]
+        out = tf_ops.conv1d(x, f, b)[0]
+        (out * dy.to(dtype)).sum().backward()
+        return out, e.grad, f.grad, b.grad
+
+    ref = oracle(torch.float64)
+    ref32 = oracle(torch.float32)
+    e = emb.to(dev).requires_grad_(True)
+    f = filt.to(dev).requires_grad_(True)
+    b = bias.to(dev).requires_grad_(True)
+    table = torch.matmul(e.unsqueeze(0), f[0])
+    y = ops.CharCnnTableFn.apply(table, b, ids.to(torch.int32).to(dev))
+    (y * dy.to(dev)).sum().backward()
+    for name, a, r, r32 in zip(("y", "d_emb", "d_filter", "d_bias"), (y, e.grad, f.grad, b.grad), ref, ref32):
+        tol = max(TOL, 3 * rel_err(r32, r))
+        assert rel_err(a, r) < tol, (name, rel_err(a, r))
