@@ -319,6 +319,11 @@ def run_own(args):
     sync_all()
     t_e2e = dp.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
     if rank != 0:
         return
     total = PER_GPU_BATCH * world * args.steps
@@ -344,6 +349,9 @@ def run_own(args):
                 "sample": "%d QAs, micro-batches of 1 (README.MD:146-148), literal torch-CPU oracle of "
                           "model_v2.py (TensorFlow 1.x cannot run here), fwd+bwd+Adadelta, %.1f s" % (n, t)}
     print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 def main():

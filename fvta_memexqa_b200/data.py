@@ -23,6 +23,16 @@ class TensorBatch:
         self.num_examples = num_examples
         self.data = {}
         self.shared = {}
+        self._step_input = {}
+
+    def step_input(self, model, is_train):
+        """The packed, pinned host buffer of this batch (Model.host_step_input), built once: what a
+        data-loader worker hands to the training loop."""
+        if is_train not in self._step_input:
+            feed = dict(self.feed)
+            feed["is_train"] = is_train
+            self._step_input[is_train] = model.host_step_input(feed)
+        return self._step_input[is_train]
 
     def h2d_bytes(self):
         return sum(v.numel() * v.element_size() for v in self.feed.values() if isinstance(v, torch.Tensor))
@@ -47,7 +57,9 @@ class SyntheticDataset:
         if key not in self._cache:
             cfg = self.config
             # fixed-size photo table so every batch has identical shapes (CUDA-graph replay)
-            pool = cfg.batch_size * cfg.max_num_albums * cfg.max_num_photos
+            # pidx2feat holds the batch's own photos (utils.py:127-143); a fixed size (about the
+            # expected number of valid photos, rounded up) keeps every batch the same shape
+            pool = (cfg.batch_size * cfg.max_num_albums * cfg.max_num_photos * 7 // 16 + 63) // 64 * 64
             feed = make_feed(cfg, seed=self.seed + 17 * key[0], num_examples=n_ex, num_photos_pool=pool)
             self._cache[key] = TensorBatch(feed, n_ex, pin=self.pin)
         return self._cache[key]

@@ -214,6 +214,8 @@ class Model:
     def get_feed_dict(self, batch, is_train=False):
         """model_v2.py:1099-1565: batch -> {placeholder: array}.  Batches that already carry
         tensors (synthetic data, the vectorised input pipeline) pass through unchanged."""
+        if hasattr(batch, "step_input"):      # a batch that caches its packed, pinned step input
+            return batch.step_input(self, is_train)
         feed = getattr(batch, "feed", None)
         if feed is None and isinstance(batch, dict):
             feed = batch
@@ -227,30 +229,39 @@ class Model:
     # tensors the device step consumes besides the packed reader inputs
     _DEVICE_KEYS = ("q_mask", "y", "existing_emb_mat", "image_emb_mat")
 
-    def to_device(self, feed, pack=None):
-        """Host feed -> device step inputs.  The host packs the valid tokens and the per-sequence
-        arena rows (packing.build_pack); only those, the question mask, the labels and the two
-        embedding tables are copied (non-blocking when the host tensors are pinned)."""
-        if "_meta" in feed:
-            return feed                      # already a device step input
-        from .packing import build_pack
+    def host_step_input(self, feed):
+        """Everything the device step reads, as ONE pinned host buffer (packing.to_blob): the packed
+        reader inputs, the question mask, the labels and the two embedding tables.  A data loader
+        builds this once per batch (TensorBatch caches it); to_device then issues a single copy."""
+        from .packing import build_pack, to_blob
         host = {k: (torch.as_tensor(v) if not isinstance(v, torch.Tensor) and hasattr(v, "shape") else v)
                 for k, v in feed.items()}
-        if pack is None:
-            pack = build_pack(host, self.config)
-        tensors, meta = pack
-        out = {"_meta": meta, "_host": host, "is_train": feed.get("is_train", False)}
+        tensors, meta = build_pack(host, self.config)
         for k in self._DEVICE_KEYS:
             if k in host and host[k] is not None:
-                out[k] = host[k].to(self.device, non_blocking=True)
-        for k, v in tensors.items():
-            out[k] = v.to(self.device, non_blocking=True)
+                tensors[k] = host[k]
+        blob, index = to_blob(tensors)
+        meta["blob_bytes"] = blob.numel()
+        return {"blob": blob, "index": index, "meta": meta, "host": host}
+
+    def to_device(self, feed, pack=None):
+        """Host feed (or a cached host_step_input) -> device step input: one non-blocking copy of
+        the blob, typed views into it."""
+        if "_meta" in feed:
+            return feed                      # already a device step input
+        from .packing import blob_views
+        hsi = feed if "blob" in feed else self.host_step_input(feed)
+        dev_blob = hsi["blob"].to(self.device, non_blocking=True)
+        out = blob_views(dev_blob, hsi["index"])
+        out["_blob"] = dev_blob
+        out["_meta"] = hsi["meta"]
+        out["_host"] = hsi["host"]
+        out["is_train"] = hsi["host"].get("is_train", False)
         return out
 
     @staticmethod
     def h2d_bytes(dfeed):
-        return sum(v.numel() * v.element_size() for k, v in dfeed.items()
-                   if isinstance(v, torch.Tensor) and not k.startswith("_"))
+        return dfeed["_blob"].numel()
 
     # ------------------------------------------------------------------ forward
     def _embed_tokens(self, ids, ids_c, glove, is_train):

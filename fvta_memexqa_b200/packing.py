@@ -112,3 +112,33 @@ def build_pack(feed, config, bucket=512):
                 text_Jmax=max(JQ, JXA, JD, JT, JG, JXP, JA), img_Jmax=JI,
                 q_range=ranges["q"], choices_range=ranges["choices"])
     return t, meta
+
+
+def to_blob(tensors, pin=True):
+    """Concatenate CPU tensors into ONE (pinned) byte buffer so a step's inputs travel in a single
+    host->device copy.  Returns (blob uint8 [nbytes], index: name -> (offset, shape, dtype))."""
+    index, off = {}, 0
+    for k, v in tensors.items():
+        v = v.contiguous()
+        index[k] = (off, tuple(v.shape), v.dtype)
+        off += (v.numel() * v.element_size() + 255) // 256 * 256
+    blob = torch.empty(max(off, 256), dtype=torch.uint8)
+    if pin and torch.cuda.is_available():
+        blob = blob.pin_memory()
+    for k, v in tensors.items():
+        o, shape, dtype = index[k]
+        n = v.numel() * v.element_size()
+        blob[o:o + n] = v.contiguous().view(-1).view(torch.uint8)
+    return blob, index
+
+
+def blob_views(dev_blob, index):
+    """Typed views into a device copy of the blob."""
+    out = {}
+    for k, (o, shape, dtype) in index.items():
+        n = 1
+        for s_ in shape:
+            n *= s_
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        out[k] = dev_blob[o:o + nbytes].view(dtype).view(shape)
+    return out

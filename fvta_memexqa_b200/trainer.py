@@ -60,8 +60,14 @@ class Trainer:
         m = self.model
         ps = m.params
         meta = dfeed["_meta"]
-        key = (meta["text_cap"], meta["img_cap"])
-        static = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in dfeed.items()}
+        key = (meta["text_cap"], meta["img_cap"], meta["blob_bytes"])
+        from .packing import blob_views
+        hsi_index = {k: (v.data_ptr() - dfeed["_blob"].data_ptr(), tuple(v.shape), v.dtype)
+                     for k, v in dfeed.items() if isinstance(v, torch.Tensor) and k != "_blob"}
+        static_blob = dfeed["_blob"].clone()
+        static = blob_views(static_blob, hsi_index)
+        static.update({k: v for k, v in dfeed.items() if not isinstance(v, torch.Tensor)})
+        static["_blob"] = static_blob
         # warm-up and capture must not move the weights
         snap = [t.clone() for t in (ps.flat, ps.accum, ps.accum_update)]
         step0 = m.global_step
@@ -87,18 +93,22 @@ class Trainer:
     def graph_step(self, feed):
         """Replay the captured step on a new batch (host feed or device step input).  Returns the
         loss tensor (device)."""
-        dfeed = self.model.to_device(feed)
-        meta = dfeed["_meta"]
-        key = (meta["text_cap"], meta["img_cap"])
-        entry = self._graphs.get(key) or self._capture(dfeed)
+        meta = feed["meta"] if "blob" in feed else None
+        dfeed = None
+        if meta is None:
+            dfeed = self.model.to_device(feed)
+            meta = dfeed["_meta"]
+        key = (meta["text_cap"], meta["img_cap"], meta["blob_bytes"])
+        entry = self._graphs.get(key)
+        if entry is None:
+            dfeed = dfeed if dfeed is not None else self.model.to_device(feed)
+            entry = self._capture(dfeed)
         graph, static, loss = entry
-        for k, v in dfeed.items():
-            dst = static.get(k)
-            if isinstance(dst, torch.Tensor):
-                if dst.shape != v.shape:
-                    raise ValueError("graph step: %s has shape %s, captured %s (pin the padded shapes)"
-                                     % (k, tuple(v.shape), tuple(dst.shape)))
-                dst.copy_(v, non_blocking=True)
+        src = feed["blob"] if "blob" in feed else dfeed["_blob"]     # pinned host blob: copy it straight in
+        if src.numel() != static["_blob"].numel():
+            raise ValueError("graph step: step input is %d bytes, captured %d (pin the padded shapes)"
+                             % (src.numel(), static["_blob"].numel()))
+        static["_blob"].copy_(src, non_blocking=True)
         graph.replay()
         self.model.global_step += 1
         self.global_step = self.model.global_step
