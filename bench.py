@@ -62,14 +62,15 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
+        self.samples = []      # (host time, csv line)
         self.proc = None
+        self.window = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -77,7 +78,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def mark(self, t0, t1):
+        """Host-clock window of the timed region; samples inside it are the ones reported."""
+        self.window = (t0, t1)
 
     def stop(self):
         if self.proc is None:
@@ -89,7 +94,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.samples:
+        lines = [l for (t, l) in self.samples if self.window and self.window[0] <= t <= self.window[1]]
+        scope = "timed region"
+        if not lines:   # region shorter than the sampling period: use the run's samples under load
+            lines = [l for (_, l) in self.samples[-25:]]
+            scope = "whole run (timed region shorter than one nvidia-smi period)"
+        for line in lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 6:
                 continue
@@ -102,7 +112,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
 # ------------------------------------------------------------------------------------------
@@ -257,6 +267,9 @@ def run_own(args):
     dp = DataParallel()
     rank, world = dp.rank, dp.world_size
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()       # nvidia-smi takes ~100 ms to come up: start it before building the model
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dp.device = dev
@@ -289,10 +302,8 @@ def run_own(args):
         flush.zero_()
         device_step(dfeeds[i % len(dfeeds)])
     sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = lib.fvta_launch_count()
+    th0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -304,7 +315,7 @@ def run_own(args):
     if not args.no_graph:
         launches = trainer.launches_per_step * args.steps   # replayed graph nodes
     t_dev = dp.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.mark(th0, time.perf_counter())
 
     # ---- end-to-end leg: Trainer.step from pinned host tensors, loss read back -----------
     for i in range(max(1, args.warmup // 2)):
@@ -318,6 +329,7 @@ def run_own(args):
     e1.record()
     sync_all()
     t_e2e = dp.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
         import torch.distributed as dist
