@@ -252,7 +252,11 @@ def attention_roofline(dev, iters=10, with_logits=False):
 # own arm
 # ------------------------------------------------------------------------------------------
 def run_own(args):
+    import signal
     import torch
+    # a wedged collective must not hold N GPUs until someone else's timeout: give up after 5 min
+    signal.signal(signal.SIGALRM, lambda *_: os._exit(17))
+    signal.alarm(300)
     from fvta_memexqa_b200 import _lib
     from fvta_memexqa_b200.config import fvta_config
     from fvta_memexqa_b200.data import SyntheticDataset
@@ -280,6 +284,8 @@ def run_own(args):
     trainer = Trainer(model, cfg, dp=dp if world > 1 else None)
     data = SyntheticDataset(cfg, num_examples=PER_GPU_BATCH * 4, seed=1234 + 1000 * rank, pin=True)
     batches = list(data.get_batches(PER_GPU_BATCH, num_steps=4, shuffle=False))
+    # one packed-size bucket for every batch of every rank -> one graph, captured in lockstep
+    dp.pin_caps(model, [b[1] for b in batches])
     dfeeds = [model.to_device(model.get_feed_dict(b[1], is_train=True)) for b in batches]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     h2d = max(model.h2d_bytes(df) for df in dfeeds)
@@ -331,12 +337,8 @@ def run_own(args):
     t_e2e = dp.max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        if rank != 0:
-            dist.destroy_process_group()
     if rank != 0:
+        _shutdown_dist(world)
         return
     total = PER_GPU_BATCH * world * args.steps
     line = {"metric": METRIC, "value": total / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -360,10 +362,21 @@ def run_own(args):
                 "value": n / t, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "%d QAs, micro-batches of 1 (README.MD:146-148), literal torch-CPU oracle of "
                           "model_v2.py (TensorFlow 1.x cannot run here), fwd+bwd+Adadelta, %.1f s" % (n, t)}
-    print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)      # the line is out before any teardown can stall
+    _shutdown_dist(world)
+
+
+def _shutdown_dist(world):
+    """Tear the process group down without letting a slow NCCL teardown hold the GPUs: the
+    measurement is finished, so after a short grace period the process simply exits."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    sys.stdout.flush()
+    t = threading.Thread(target=lambda: dist.destroy_process_group(), daemon=True)
+    t.start()
+    t.join(timeout=10.0)
+    os._exit(0)
 
 
 def main():

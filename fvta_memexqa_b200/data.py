@@ -28,11 +28,12 @@ class TensorBatch:
     def step_input(self, model, is_train):
         """The packed, pinned host buffer of this batch (Model.host_step_input), built once: what a
         data-loader worker hands to the training loop."""
-        if is_train not in self._step_input:
+        key = (is_train, getattr(model, "pin_text_cap", 0), getattr(model, "pin_img_cap", 0))
+        if key not in self._step_input:
             feed = dict(self.feed)
             feed["is_train"] = is_train
-            self._step_input[is_train] = model.host_step_input(feed)
-        return self._step_input[is_train]
+            self._step_input[key] = model.host_step_input(feed)
+        return self._step_input[key]
 
     def h2d_bytes(self):
         return sum(v.numel() * v.element_size() for v in self.feed.values() if isinstance(v, torch.Tensor))

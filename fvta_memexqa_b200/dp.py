@@ -55,6 +55,21 @@ class DataParallel:
             t = t / self.world_size
         return t
 
+    def pin_caps(self, model, batches):
+        """Pin the packed-token sizes to the maximum over every batch of every rank, so that all
+        ranks build ONE step graph and capture it in lockstep (a rank that captured an extra
+        bucket would issue all-reduces its peers never join)."""
+        caps = [0, 0]
+        for b in batches:
+            meta = model.get_feed_dict(b, is_train=True)["meta"]
+            caps = [max(caps[0], meta["text_cap"]), max(caps[1], meta["img_cap"])]
+        if self.world_size > 1:
+            t = torch.tensor(caps, dtype=torch.int64, device=self.device if self.device is not None else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            caps = [int(v) for v in t.tolist()]
+        model.pin_text_cap, model.pin_img_cap = caps
+        return caps
+
     def broadcast_params(self, flat):
         if self.world_size > 1:
             dist.broadcast(flat, src=0)

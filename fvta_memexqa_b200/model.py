@@ -236,7 +236,8 @@ class Model:
         from .packing import build_pack, to_blob
         host = {k: (torch.as_tensor(v) if not isinstance(v, torch.Tensor) and hasattr(v, "shape") else v)
                 for k, v in feed.items()}
-        tensors, meta = build_pack(host, self.config)
+        tensors, meta = build_pack(host, self.config, min_text_cap=getattr(self, "pin_text_cap", 0),
+                                   min_img_cap=getattr(self, "pin_img_cap", 0))
         for k in self._DEVICE_KEYS:
             if k in host and host[k] is not None:
                 tensors[k] = host[k]

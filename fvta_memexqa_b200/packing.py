@@ -21,9 +21,10 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
-def build_pack(feed, config, bucket=512):
+def build_pack(feed, config, bucket=512, min_text_cap=0, min_img_cap=0):
     """feed: placeholder-name -> CPU tensor.  Returns (tensors: dict name -> CPU tensor,
-    meta: dict of python ints)."""
+    meta: dict of python ints).  ``min_text_cap`` / ``min_img_cap`` pin the packed sizes (data
+    parallel runs pin them to the global maxima so every rank replays the same single graph)."""
     N = feed["q"].shape[0]
     M = feed["at"].shape[1]
     JXA, JD = feed["at"].shape[2], feed["ad"].shape[2]
@@ -71,7 +72,7 @@ def build_pack(feed, config, bucket=512):
         b0 += m2.shape[0]
     lens_t = torch.cat(lens_all)
     ntok = int(lens_t.sum())
-    cap = max(bucket, _round_up(ntok, bucket))
+    cap = max(bucket, _round_up(ntok, bucket), min_text_cap)
     tok_ids = torch.zeros(cap, dtype=torch.int64)
     tok_ids[:ntok] = torch.cat(ids)
     t = {"text_tok_ids": tok_ids,
@@ -89,7 +90,7 @@ def build_pack(feed, config, bucket=512):
     pprefix = torch.arange(JI).view(1, JI) < plens.view(-1, 1)
     pidx = feed["pis"].reshape(-1, JI)[pprefix].long()
     nimg = int(plens.sum())
-    icap = max(64, _round_up(nimg, 64))
+    icap = max(64, _round_up(nimg, 64), min_img_cap)
     tp = torch.zeros(icap, dtype=torch.int64)
     tp[:nimg] = pidx
     t["img_tok_pidx"] = tp
