@@ -111,3 +111,29 @@ def test_step_vis_surface(cuda_device):
     assert yp.shape == (2, 4) and C.shape == (2, T, T) and att_logits.shape == (2, 6, T, 4)
     # tester.py:27-28 trim() turns every non-ndarray (the scalar window) into -1
     assert q_att.shape == (2, 4, 1) and C_win == -1
+
+
+def test_main_train_then_test_roundtrip(cuda_device, tmp_path):
+    """The reference's CLI end to end on a synthetic dataset in the reference's on-disk format:
+    main.py --is_train (list-of-lists batches -> get_feed_dict -> Trainer.step, periodic save +
+    validation, best checkpoint) then --is_test --load_best (restore, Tester.step, answers.json)."""
+    import json
+    import os
+    import main as cli
+    from fvta_memexqa_b200.config import get_args
+    base = [str(tmp_path / "prepro"), str(tmp_path / "models"), "--modelname", "fvta_t", "--synthetic", "24",
+            "--batch_size", "4", "--hidden_size", "8", "--image_feat_dim", "16", "--use_image_trans",
+            "--image_trans_dim", "12", "--use_char", "--char_emb_size", "6", "--char_out_size", "8", "--add_tanh",
+            "--simiMatrix", "2", "--use_question_att", "--use_3d", "--use_time_warp", "--warp_type", "5",
+            "--num_albums_thres", "4", "--num_photos_thres", "8"]
+    cfg = get_args(base + ["--is_train", "--num_epochs", "1", "--save_period", "3", "--val_num_batches", "2"])
+    model = cli.train(cfg)
+    assert model.global_step == 6                                   # ceil(24/4) steps
+    assert os.path.exists(cfg.self_summary_path)
+    assert any(f.endswith(".pt") for f in os.listdir(cfg.save_dir))
+    assert any(f.endswith(".pt") for f in os.listdir(cfg.save_dir_best))
+    cfg_t = get_args(base + ["--is_test", "--load_best", "--get_yp"])
+    acc = cli.test(cfg_t)
+    assert 0.0 <= acc <= 1.0
+    answers = json.load(open(os.path.join(cfg_t.val_path, "answers.json")))
+    assert len(answers) == 6 and all(0 <= v < 4 for v in answers.values())   # test split = synthetic // 4
