@@ -34,27 +34,39 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
   const int kbeg = blockIdx.z * k_per_split;
   const int kend = min(K, kbeg + k_per_split);
   const bool atomic_out = gridDim.z > 1;
+
+  // each thread moves 4 elements of the A tile and 4 of the B tile per k-tile; the next k-tile is
+  // fetched into registers while the current one is multiplied (these products are short and
+  // latency-bound, not FLOP-bound)
+  int am[4], ak[4], bn[4], bk[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = tid + q * 256;
+    if (TA) { am[q] = i % BM; ak[q] = i / BM; } else { ak[q] = i % BK; am[q] = i / BK; }
+    if (TB) { bk[q] = i % BK; bn[q] = i / BK; } else { bn[q] = i % BN; bk[q] = i / BN; }
+  }
+  float ar[4], br[4];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int gm = m0 + am[q], gka = k0 + ak[q];
+      ar[q] = (gm < M && gka < kend) ? (TA ? A[(size_t)gka * lda + gm] : A[(size_t)gm * lda + gka]) : 0.f;
+      const int gn = n0 + bn[q], gkb = k0 + bk[q];
+      br[q] = (gn < N && gkb < kend) ? (TB ? B[(size_t)gn * ldb + gkb] : B[(size_t)gkb * ldb + gn]) : 0.f;
+    }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { As[ak[q]][am[q]] = ar[q]; Bs[bk[q]][bn[q]] = br[q]; }
+  };
+  if (kbeg < kend) {
+    gload(kbeg);
+    sstore();
+  }
+  __syncthreads();
   for (int k0 = kbeg; k0 < kend; k0 += BK) {
-    // A tile: BM x BK
-    for (int i = tid; i < BM * BK; i += 256) {
-      int m, k;
-      if (TA) { m = i % BM; k = i / BM; }   // A stored [K, lda]: m fastest
-      else    { k = i % BK; m = i / BK; }   // A stored [M, lda]: k fastest
-      const int gm = m0 + m, gk = k0 + k;
-      float v = 0.f;
-      if (gm < M && gk < kend) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
-      As[k][m] = v;
-    }
-    for (int i = tid; i < BN * BK; i += 256) {
-      int n, k;
-      if (TB) { k = i % BK; n = i / BK; }   // B stored [N, ldb]: k fastest
-      else    { n = i % BN; k = i / BN; }   // B stored [K, ldb]: n fastest
-      const int gn = n0 + n, gk = k0 + k;
-      float v = 0.f;
-      if (gn < N && gk < kend) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
-      Bs[k][n] = v;
-    }
-    __syncthreads();
+    const bool more = k0 + BK < kend;
+    if (more) gload(k0 + BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
@@ -67,6 +79,10 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, const fl
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
+    if (more) {
+      sstore();
+      __syncthreads();
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -398,7 +398,8 @@ def make_synthetic_raw(num_examples, num_albums=40, seed=0, feat_dim=2537, emb_d
     Stands in for prepro_v1.1/{train,val,test}_{data,shared}.p, which cannot be downloaded here."""
     rnd = random.Random(seed)
     nrng = np.random.RandomState(seed)
-    words = ["w%d" % i for i in range(vocab)]
+    # word lengths 5..10: the char-CNN needs max_word_size >= its filter height 5 (SURVEY C.7)
+    words = ["tok%02d%s" % (i, "abcde"[: i % 6]) for i in range(vocab)]
     glove = set(words[: vocab * 2 // 3])            # the rest are "new" (trainable) words
 
     def sent(lo, hi):

@@ -265,18 +265,21 @@ class Model:
         return dfeed["_blob"].numel()
 
     # ------------------------------------------------------------------ forward
+    def _sink(self, *names):
+        """Gradient views of the named variables (None entries for absent ones): the custom ops
+        accumulate parameter gradients straight into the flat buffer."""
+        return tuple(self.params.grad(n) if n in self.params else None for n in names)
+
     def _embed_tokens(self, ids, ids_c, glove, is_train):
         """model_v2.py:524-620 for the packed valid tokens: word vector (trainable table for ids <
         VW, fed GloVe table otherwise, :596) and the char-CNN (:52-70) concatenated [char, word]."""
         cfg, v = self.config, self.vars
         VW = self.VW
         table = v["emb/word/var/word_emb_mat"]
-        # F.embedding, not advanced indexing: its backward is the sorted segmented reduction
-        # (plain index backward serialises on the heavily repeated ids)
-        emb = torch.nn.functional.embedding
         is_new = ids < VW
-        A = torch.where(is_new.unsqueeze(-1), emb(ids.clamp(max=VW - 1), table),
-                        emb((ids - VW).clamp(min=0), glove))
+        A = torch.where(is_new.unsqueeze(-1),
+                        ops.embed(table, ids.clamp(max=VW - 1), self._sink("emb/word/var/word_emb_mat")[0]),
+                        ops.embed(glove, (ids - VW).clamp(min=0)))
         if not cfg.use_char:
             return A
         filt = v["emb/conv/conv1d/filter"]                              # [1,5,cdim,cwdim]
@@ -286,9 +289,10 @@ class Model:
             # a window's conv output depends only on its `height` char ids: tabulate
             # char_emb @ filter[h] once ([height,VC,cw], a few MFLOP) and gather-add (csrc/charcnn.cu)
             table = torch.matmul(v["emb/var/char_emb"].unsqueeze(0), filt[0])
-            xc = ops.CharCnnTableFn.apply(table, v["emb/conv/conv1d/bias"], ids_c)
+            xc = ops.CharCnnTableFn.apply(table, v["emb/conv/conv1d/bias"], ids_c,
+                                          self._sink("emb/conv/conv1d/bias")[0])
             return torch.cat([xc, A], dim=-1)
-        Ac = emb(ids_c.long(), v["emb/var/char_emb"])                   # [cap, W, cdim]
+        Ac = torch.nn.functional.embedding(ids_c.long(), v["emb/var/char_emb"])   # [cap, W, cdim]
         if dropped:
             Ac = torch.nn.functional.dropout(Ac, 1.0 - cfg.keep_prob, True)
         win = Ac.unfold(1, height, 1)                                   # [cap, W-4, cdim, 5]
@@ -313,17 +317,21 @@ class Model:
             if (is_train and cfg.keep_prob < 1.0) else (lambda t: t)
         # embeddings of the valid tokens only (padding never reaches a consumer: dynamic_rnn ignores it)
         x_text = self._embed_tokens(f["text_tok_ids"], f.get("text_tok_cids"), f["existing_emb_mat"], is_train)
-        x_img = torch.nn.functional.embedding(f["img_tok_pidx"], f["image_emb_mat"])
+        x_img = ops.embed(f["image_emb_mat"], f["img_tok_pidx"])
         if cfg.use_image_trans:                                        # model_v2.py:634-645
             x_img = ops.linear(x_img, v["emb/image/image_transform/image_trans_linear/W"],
-                               v["emb/image/image_transform/image_trans_linear/b"], cfg.add_tanh)
+                               v["emb/image/image_transform/image_trans_linear/b"], cfg.add_tanh,
+                               *self._sink("emb/image/image_transform/image_trans_linear/W",
+                                           "emb/image/image_transform/image_trans_linear/b"))
         # the eight reader call sites (model_v2.py:694-823) + the context tensor (:862-914)
         arena, last_t, last_i = ops.ReaderFn.apply(
             drop(x_text), drop(x_img), f["text_seq_off"], f["text_seq_len"], f["text_seq_out"],
             f["img_seq_off"], f["img_seq_len"], f["img_seq_out"],
             v["reader/text/utext/fw/basic_lstm_cell/kernel"], v["reader/text/utext/fw/basic_lstm_cell/bias"],
             v["reader/image/uimage/fw/basic_lstm_cell/kernel"], v["reader/image/uimage/fw/basic_lstm_cell/bias"],
-            meta["arena_rows"], meta["text_Jmax"], meta["img_Jmax"])
+            meta["arena_rows"], meta["text_Jmax"], meta["img_Jmax"],
+            self._sink("reader/text/utext/fw/basic_lstm_cell/kernel", "reader/text/utext/fw/basic_lstm_cell/bias",
+                       "reader/image/uimage/fw/basic_lstm_cell/kernel", "reader/image/uimage/fw/basic_lstm_cell/bias"))
         hall = arena[:meta["hall_rows"]].view(N, K, M, JMAX, D)
         hall_mask = f["hall_mask"].view(N, K, M, JMAX)
         hq = arena[meta["hq_row0"]:].view(N, JQ, D)
@@ -342,7 +350,11 @@ class Model:
             hall.reshape(N, K, T, D), f["hall_mask"], hq, f["q_mask"], lq if tw else None,
             v.get("attention/all/att_logits/W"), v.get("attention/all/att_logits/b"),
             v.get("time_warp/WH/W") if tw else None, v.get("time_warp/WH/b") if tw else None,
-            v.get("time_warp/WC/W") if tw else None, v.get("time_warp/WC/b") if tw else None)
+            v.get("time_warp/WC/W") if tw else None, v.get("time_warp/WC/b") if tw else None,
+            # fvta_attn_bwd OVERWRITES its parameter gradients: only sink them when nothing else
+            # (weight decay) adds to the same slots through autograd
+            None if cfg.wd else self._sink("attention/all/att_logits/W", "attention/all/att_logits/b",
+                                           "time_warp/WH/W", "time_warp/WH/b", "time_warp/WC/W", "time_warp/WC/b"))
 
         # question attention (model_v2.py:1039-1050)
         q_att = None
@@ -353,7 +365,9 @@ class Model:
                 qcfg, (want_vis, False, False), hq.unsqueeze(1), f["q_mask"].unsqueeze(1),
                 g1_all.unsqueeze(1), ones, None,
                 v.get("question_emb/question_att/att_logits/W"), v.get("question_emb/question_att/att_logits/b"),
-                None, None, None, None)
+                None, None, None, None,
+                None if cfg.wd else self._sink("question_emb/question_att/att_logits/W",
+                                               "question_emb/question_att/att_logits/b") + (None, None, None, None))
         else:
             gq = lq
 
@@ -367,7 +381,8 @@ class Model:
             logits = ops.linear(feat, v["output/choicelogits/W"], v["output/choicelogits/b"], cfg.add_tanh)
         else:
             feat = torch.cat([gqt, g1t, gc, g1t * gc, gqt * gc], 2)
-            logits = ops.linear(feat, v["output/choicelogits/W"], v["output/choicelogits/b"], False)
+            logits = ops.linear(feat, v["output/choicelogits/W"], v["output/choicelogits/b"], False,
+                                *self._sink("output/choicelogits/W", "output/choicelogits/b"))
         logits = logits.squeeze(2)
         self.logits = logits
         self.yp = torch.softmax(logits, dim=-1)

@@ -105,8 +105,9 @@ def attn_forward(cfg, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W=None, WH_b=No
                 desc=desc, saved=(hall, hm, hq, qm, lq))
 
 
-def attn_backward(fwd, d_g1_all, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=None):
-    """fvta_attn_bwd given the dict attn_forward returned.  Returns dict of gradients."""
+def attn_backward(fwd, d_g1_all, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=None, sinks=None):
+    """fvta_attn_bwd given the dict attn_forward returned.  Returns dict of gradients.  `sinks`:
+    optional tensors the six parameter gradients are written into (the entry point overwrites)."""
     lib = _lib.load()
     f32 = torch.float32
     hall, hm, hq, qm, lq = fwd["saved"]
@@ -115,10 +116,14 @@ def attn_backward(fwd, d_g1_all, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=Non
     dev = hall.device
     out = dict(d_hall=torch.empty_like(hall), d_hq=torch.empty_like(hq),
                d_lq=torch.empty_like(lq) if (lq is not None and desc.use_time_warp) else None)
-    gW = torch.empty_like(W) if W is not None else None
-    gb = torch.empty_like(b) if b is not None else None
-    gs = [torch.empty_like(x) if (x is not None and desc.use_time_warp) else None
-          for x in (WH_W, WH_b, WC_W, WC_b)]
+    if sinks is not None:
+        gW, gb = sinks[0], sinks[1]
+        gs = [sk if desc.use_time_warp else None for sk in sinks[2:6]]
+    else:
+        gW = torch.empty_like(W) if W is not None else None
+        gb = torch.empty_like(b) if b is not None else None
+        gs = [torch.empty_like(x) if (x is not None and desc.use_time_warp) else None
+              for x in (WH_W, WH_b, WC_W, WC_b)]
     grads = FvtaAttnGrads(att_W=_ptr(gW), att_b=_ptr(gb), WH_W=_ptr(gs[0]), WH_b=_ptr(gs[1]),
                           WC_W=_ptr(gs[2]), WC_b=_ptr(gs[3]))
     params = _attn_params(W, b, WH_W, WH_b, WC_W, WC_b)
@@ -171,12 +176,16 @@ class LinearFn(torch.autograd.Function):
     """`linear` of the reference (model_v2.py:75-100): flatten, x @ W + b, optional tanh."""
 
     @staticmethod
-    def forward(ctx, x, W, b, add_tanh):
+    def forward(ctx, x, W, b, add_tanh, gW=None, gb=None):
+        """gW / gb: optional gradient sinks (views of the flat gradient buffer).  When given, the
+        backward accumulates into them directly and reports no gradient to autograd, which
+        saves the zero-fill + add that AccumulateGrad would launch per parameter."""
         flat = x.reshape(-1, x.shape[-1])
         y = gemm(flat, W, b, "tanh" if add_tanh else None)
         ctx.save_for_backward(flat, W, y)
         ctx.add_tanh = add_tanh
         ctx.xshape = x.shape
+        ctx.sinks = (gW, gb)
         return y.reshape(*x.shape[:-1], W.shape[1])
 
     @staticmethod
@@ -187,13 +196,18 @@ class LinearFn(torch.autograd.Function):
             dy = dy * (1.0 - y * y)
         # the image features and other fed inputs need no gradient: skip that GEMM
         dx = gemm(dy, W, trans_b=True).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
+        gW, gb = ctx.sinks
+        if gW is not None:
+            gemm(flat, dy, trans_a=True, out=gW, accumulate=True)
+            gb.add_(dy.sum(0))
+            return dx, None, None, None, None, None
         dW = gemm(flat, dy, trans_a=True)
         db = dy.sum(0)
-        return dx, dW, db, None
+        return dx, dW, db, None, None, None
 
 
-def linear(x, W, b, add_tanh=False):
-    return LinearFn.apply(x, W, b, add_tanh)
+def linear(x, W, b, add_tanh=False, gW=None, gb=None):
+    return LinearFn.apply(x, W, b, add_tanh, gW, gb)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -284,12 +298,13 @@ class FvtaAttentionFn(torch.autograd.Function):
     Outputs: g1_all [N,D] (differentiable), a_logits / c_col / warp_h (visualisation; no grad)."""
 
     @staticmethod
-    def forward(ctx, cfg, want, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W, WH_b, WC_W, WC_b):
+    def forward(ctx, cfg, want, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W, WH_b, WC_W, WC_b, sinks=None):
         fwd = attn_forward(cfg, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W, WH_b, WC_W, WC_b,
                            want_logits=want[0], want_c=want[1], want_warp_h=want[2])
         ctx.fwd = fwd
         ctx.params = (W, b, WH_W, WH_b, WC_W, WC_b)
         ctx.has_lq = lq is not None
+        ctx.sinks = sinks       # gradient views for (W, b, WH_W, WH_b, WC_W, WC_b): written in place
         outs = [fwd["g1_all"]]
         for key in ("a_logits", "c_col", "warp_h"):
             t = fwd[key] if fwd[key] is not None else torch.empty(0, device=hall.device)
@@ -300,10 +315,13 @@ class FvtaAttentionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_g1, *_unused):
         W, b, WH_W, WH_b, WC_W, WC_b = ctx.params
-        g = attn_backward(ctx.fwd, d_g1, W, b, WH_W, WH_b, WC_W, WC_b)
+        g = attn_backward(ctx.fwd, d_g1, W, b, WH_W, WH_b, WC_W, WC_b, sinks=ctx.sinks)
         ctx.fwd = None
+        if ctx.sinks is not None:
+            return (None, None, g["d_hall"], None, g["d_hq"], None, g["d_lq"] if ctx.has_lq else None,
+                    None, None, None, None, None, None, None)
         return (None, None, g["d_hall"], None, g["d_hq"], None, g["d_lq"] if ctx.has_lq else None,
-                g["d_att_W"], g["d_att_b"], g["d_WH_W"], g["d_WH_b"], g["d_WC_W"], g["d_WC_b"])
+                g["d_att_W"], g["d_att_b"], g["d_WH_W"], g["d_WH_b"], g["d_WC_W"], g["d_WC_b"], None)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -332,7 +350,7 @@ class ReaderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x_text, x_img, t_off, t_len, t_out, i_off, i_len, i_out, kt, bt, ki, bi, arena_rows,
-                Jmax_t, Jmax_i):
+                Jmax_t, Jmax_i, sinks=None):
         lib = _lib.load()
         f32 = torch.float32
         x_text, x_img = _req(x_text, f32, "x_text"), _req(x_img, f32, "x_img")
@@ -343,6 +361,7 @@ class ReaderFn(torch.autograd.Function):
         last_i, res_i, desc_i = _reader_call(lib, x_img, i_off, i_len, i_out, ki, bi, arena, Jmax_i)
         ctx.save_for_backward(x_text, x_img, t_off, t_len, t_out, i_off, i_len, i_out, kt, ki, res_t, res_i)
         ctx.descs = (desc_t, desc_i)
+        ctx.sinks = sinks       # (g kernel_t, g bias_t, g kernel_i, g bias_i) views of the flat gradient
         return arena, last_t, last_i
 
     @staticmethod
@@ -353,11 +372,16 @@ class ReaderFn(torch.autograd.Function):
         desc_t, desc_i = ctx.descs
         d_arena = _req(d_arena, f32, "d_arena") if d_arena is not None else None
         outs = []
-        for (x, off, ln, orow, k, res, desc, dl) in ((x_text, t_off, t_len, t_out, kt, res_t, desc_t, d_last_t),
-                                                     (x_img, i_off, i_len, i_out, ki, res_i, desc_i, d_last_i)):
+        sinks = ctx.sinks
+        for j, (x, off, ln, orow, k, res, desc, dl) in enumerate(
+                ((x_text, t_off, t_len, t_out, kt, res_t, desc_t, d_last_t),
+                 (x_img, i_off, i_len, i_out, ki, res_i, desc_i, d_last_i))):
             dx = torch.empty_like(x)
-            dk = torch.zeros_like(k)
-            db = torch.zeros(k.shape[1], dtype=f32, device=x.device)
+            if sinks is not None:       # the C entry point accumulates (+=): hand it the flat gradient
+                dk, db = sinks[2 * j], sinks[2 * j + 1]
+            else:
+                dk = torch.zeros_like(k)
+                db = torch.zeros(k.shape[1], dtype=f32, device=x.device)
             dl = _req(dl, f32, "d_last") if dl is not None else None
             ws_bytes = lib.fvta_reader_workspace_bytes(ctypes.byref(desc))
             ws = torch.empty(ws_bytes // 4, dtype=f32, device=x.device)
@@ -367,7 +391,11 @@ class ReaderFn(torch.autograd.Function):
             check(rc, "fvta_reader_bwd")
             outs.append((dx, dk, db))
         (dxt, dkt, dbt), (dxi, dki, dbi) = outs
-        return (dxt, dxi, None, None, None, None, None, None, dkt, dbt, dki, dbi, None, None, None)
+        if not ctx.needs_input_grad[1]:
+            dxi = None
+        if sinks is not None:
+            dkt = dbt = dki = dbi = None
+        return (dxt, dxi, None, None, None, None, None, None, dkt, dbt, dki, dbi, None, None, None, None)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -379,7 +407,8 @@ class CharCnnTableFn(torch.autograd.Function):
     matrix products, so autograd carries d table back to char_emb and the filter."""
 
     @staticmethod
-    def forward(ctx, table, bias, ids):
+    def forward(ctx, table, bias, ids, bias_sink=None):
+        ctx.bias_sink = bias_sink
         lib = _lib.load()
         f32 = torch.float32
         table, bias = _req(table, f32, "table"), _req(bias, f32, "bias")
@@ -404,8 +433,41 @@ class CharCnnTableFn(torch.autograd.Function):
         H, VC, cw, ntok, W = ctx.shape
         dy = _req(dy, f32, "dy")
         d_table = torch.zeros(H, VC, cw, dtype=f32, device=dy.device)
-        d_bias = torch.zeros(cw, dtype=f32, device=dy.device)
+        sink = ctx.bias_sink
+        d_bias = sink if sink is not None else torch.zeros(cw, dtype=f32, device=dy.device)
         rc = lib.fvta_charcnn_bwd(ntok, W, VC, cw, H, _ptr(ids), _ptr(y), _ptr(argpos), _ptr(dy), _ptr(d_table),
                                   _ptr(d_bias), _stream())
         check(rc, "fvta_charcnn_bwd")
-        return d_table, d_bias, None
+        return d_table, (None if sink is not None else d_bias), None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# small plumbing ops
+# ---------------------------------------------------------------------------------------------
+class EmbedFn(torch.autograd.Function):
+    """Row gather whose backward is ONE index_add (atomic scatter-add of the rows) instead of
+    the sort + segmented reduction of F.embedding's dense backward -- the id lists here are a few
+    thousand entries, where the sort's fixed cost dominates."""
+
+    @staticmethod
+    def forward(ctx, table, ids, sink=None):
+        ctx.save_for_backward(ids)
+        ctx.rows = table.shape[0]
+        ctx.sink = sink
+        return table.index_select(0, ids)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids,) = ctx.saved_tensors
+        if ctx.sink is not None:
+            ctx.sink.index_add_(0, ids, dy.contiguous())
+            return None, None, None
+        g = torch.zeros(ctx.rows, dy.shape[1], dtype=dy.dtype, device=dy.device)
+        g.index_add_(0, ids, dy.contiguous())
+        return g, None, None
+
+
+def embed(table, ids, sink=None):
+    if table.requires_grad:
+        return EmbedFn.apply(table, ids, sink)
+    return table.index_select(0, ids)
