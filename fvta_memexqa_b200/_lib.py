@@ -16,7 +16,7 @@ c_i32_p = ctypes.c_void_p
 class FvtaAttnDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "N", "K", "T", "D", "JQ", "simi", "add_tanh", "use_time_warp", "warp_type", "window",
-        "time_warp_att", "has_mask")]
+        "time_warp_att", "has_mask", "ws_from_fwd")]
 
 
 class FvtaAttnParams(ctypes.Structure):
@@ -78,6 +78,8 @@ SYMBOLS = {
                                                                  ctypes.c_void_p]),
     "fvta_charcnn_bwd": (ctypes.c_int, [ctypes.c_int32] * 5 + [c_i32_p, c_float_p, c_u8_p, c_float_p, c_float_p,
                                                                  c_float_p, ctypes.c_void_p]),
+    "fvta_output_loss": (ctypes.c_int, [ctypes.c_int32] * 3 + [c_float_p] * 5 + [c_u8_p] + [c_float_p] * 8 +
+                         [ctypes.c_void_p]),
     "fvta_adadelta": (ctypes.c_int, [ctypes.c_int64, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                      ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                      ctypes.c_void_p]),

@@ -484,8 +484,10 @@ extern "C" int fvta_attn_bwd(const FvtaAttnDesc* desc, const float* hall, const 
   float* ws = (float*)workspace;
   // The folded operands are recomputed (cheap) so the workspace need not survive between
   // the forward and the backward call.
-  rc = attn_prep_launch(d, L, *params, hq, lq, ws, st);
-  if (rc) return rc;
+  if (!d.ws_from_fwd) {
+    rc = attn_prep_launch(d, L, *params, hq, lq, ws, st);
+    if (rc) return rc;
+  }
   cudaError_t e = cudaMemsetAsync(ws + L.dqeffT, 0, (L.drow - L.dqeffT) * sizeof(float), st);
   if (e != cudaSuccess) { set_last_error("attn_bwd memset", e); return FVTA_E_LAUNCH; }
   attn_bwd_prep<<<d.N, d.K * 32, 0, st>>>(d, stats, d_g1_all, ws + L.drow);

@@ -371,25 +371,27 @@ class Model:
         else:
             gq = lq
 
-        # output layer (model_v2.py:1053-1083)
+        # output layer (model_v2.py:1053-1083) + loss (:1085-1096)
         C = lchoices.shape[1]
-        g1t = g1_all.unsqueeze(1).expand(N, C, D)
-        gqt = gq.unsqueeze(1).expand(N, C, D)
-        gc = lchoices
+        yt = f.get("y")
         if cfg.use_eu_output:
+            g1t = g1_all.unsqueeze(1).expand(N, C, D)
+            gqt = gq.unsqueeze(1).expand(N, C, D)
+            gc = lchoices
             feat = torch.cat([gqt, g1t, gc, g1t * gc, gqt * gc, (g1t - gc) * (g1t - gc), (gqt - gc) * (gqt - gc)], 2)
-            logits = ops.linear(feat, v["output/choicelogits/W"], v["output/choicelogits/b"], cfg.add_tanh)
+            logits = ops.linear(feat, v["output/choicelogits/W"], v["output/choicelogits/b"], cfg.add_tanh,
+                                *self._sink("output/choicelogits/W", "output/choicelogits/b")).squeeze(2)
+            self.logits = logits
+            self.yp = torch.softmax(logits, dim=-1)
+            self.loss = self._build_loss(logits, yt) if yt is not None else None
         else:
-            feat = torch.cat([gqt, g1t, gc, g1t * gc, gqt * gc], 2)
-            logits = ops.linear(feat, v["output/choicelogits/W"], v["output/choicelogits/b"], False,
-                                *self._sink("output/choicelogits/W", "output/choicelogits/b"))
-        logits = logits.squeeze(2)
-        self.logits = logits
-        self.yp = torch.softmax(logits, dim=-1)
+            # one launch: logits, yp, mean CE and every gradient of the tail (csrc/output_loss.cu)
+            loss, logits, yp = ops.OutputLossFn.apply(
+                gq, g1_all, lchoices, v["output/choicelogits/W"], v["output/choicelogits/b"], yt,
+                self._sink("output/choicelogits/W", "output/choicelogits/b"), torch.is_grad_enabled())
+            self.logits, self.yp = logits, yp
+            self.loss = (loss + self._wd_loss()) if yt is not None else None
         self.g1_all, self.gq = g1_all, gq
-        self.loss = None
-        if "y" in f and f["y"] is not None:
-            self.loss = self._build_loss(logits, f["y"])
         if want_vis:
             self.hall = hall
             self.att_logits = a_logits
@@ -406,10 +408,15 @@ class Model:
         """model_v2.py:1085-1096: mean over the static batch of softmax-CE (+ wd terms)."""
         cfg = self.config
         losses = -(y.to(logits.dtype) * torch.log_softmax(logits, dim=-1)).sum(-1)
-        loss = losses.mean()
-        if cfg.wd is not None and cfg.wd != 0.0:
-            for name, mult in self._wd_names():
-                loss = loss + mult * cfg.wd * 0.5 * (self.vars[name] ** 2).sum()
+        return losses.mean() + self._wd_loss()
+
+    def _wd_loss(self):
+        cfg = self.config
+        if cfg.wd is None or cfg.wd == 0.0:
+            return 0.0
+        loss = 0.0
+        for name, mult in self._wd_names():
+            loss = loss + mult * cfg.wd * 0.5 * (self.vars[name] ** 2).sum()
         return loss
 
     def _wd_names(self):

@@ -58,7 +58,7 @@ class AttnConfig:
         return FvtaAttnDesc(N=N, K=K, T=T, D=D, JQ=JQ, simi=self.simiMatrix, add_tanh=int(self.add_tanh),
                             use_time_warp=int(self.use_time_warp), warp_type=self.warp_type,
                             window=self.window, time_warp_att=int(self.time_warp_att),
-                            has_mask=int(has_mask))
+                            has_mask=int(has_mask), ws_from_fwd=0)
 
 
 def _attn_params(W, b, WH_W, WH_b, WC_W, WC_b):
@@ -128,6 +128,7 @@ def attn_backward(fwd, d_g1_all, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=Non
                           WC_W=_ptr(gs[2]), WC_b=_ptr(gs[3]))
     params = _attn_params(W, b, WH_W, WH_b, WC_W, WC_b)
     ws = fwd["ws"]
+    desc.ws_from_fwd = 1        # the forward's workspace is kept alive in `fwd`: reuse its folded operands
     rc = lib.fvta_attn_bwd(ctypes.byref(desc), _ptr(hall), _ptr(hm), _ptr(hq), _ptr(qm), _ptr(lq),
                            ctypes.byref(params), _ptr(fwd["stats"]), _ptr(d_g1_all), _ptr(out["d_hall"]),
                            _ptr(out["d_hq"]), _ptr(out["d_lq"]), ctypes.byref(grads), _ptr(ws),
@@ -471,3 +472,44 @@ def embed(table, ids, sink=None):
     if table.requires_grad:
         return EmbedFn.apply(table, ids, sink)
     return table.index_select(0, ids)
+
+
+class OutputLossFn(torch.autograd.Function):
+    """fvta_output_loss: logits / yp / mean CE and all gradients in one launch.  Returns
+    (loss, logits, yp); only `loss` is differentiable.  With sinks, dW / db go straight into the
+    flat gradient buffer during the forward (skipped when autograd is off)."""
+
+    @staticmethod
+    def forward(ctx, gq, g1, gc, W, b, y, sinks, want_grad):
+        lib = _lib.load()
+        f32 = torch.float32
+        gq, g1, gc = _req(gq, f32, "gq"), _req(g1, f32, "g1"), _req(gc, f32, "gc")
+        W, b = _req(W, f32, "W"), _req(b, f32, "b")
+        N, C, D = gc.shape
+        dev = gq.device
+        y8 = _mask_u8(y, "y") if y is not None else None
+        logits = torch.empty(N, C, dtype=f32, device=dev)
+        yp = torch.empty(N, C, dtype=f32, device=dev)
+        loss = torch.zeros((), dtype=f32, device=dev)
+        want = bool(want_grad) and y is not None   # grad mode is always off inside Function.forward
+        if want:
+            d_gq, d_g1, d_gc = torch.empty_like(gq), torch.empty_like(g1), torch.empty_like(gc)
+            dW, db = sinks if sinks is not None else (torch.zeros_like(W), torch.zeros_like(b))
+        else:
+            d_gq = d_g1 = d_gc = dW = db = None
+        rc = lib.fvta_output_loss(N, C, D, _ptr(gq), _ptr(g1), _ptr(gc), _ptr(W), _ptr(b), _ptr(y8), _ptr(logits),
+                                  _ptr(yp), _ptr(loss), _ptr(d_gq), _ptr(d_g1), _ptr(d_gc), _ptr(dW), _ptr(db),
+                                  _stream())
+        check(rc, "fvta_output_loss")
+        ctx.grads = (d_gq, d_g1, d_gc, None if sinks is not None else dW, None if sinks is not None else db)
+        ctx.mark_non_differentiable(logits, yp)
+        return loss, logits, yp
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits, _dyp):
+        d_gq, d_g1, d_gc, dW, db = ctx.grads
+        if d_gq is None:
+            raise _lib.FvtaError("fvta_output_loss was run without gradients")
+        # upstream is 1 for loss.backward(); honour anything else
+        sc = lambda t: None if t is None else t * dloss   # noqa: E731
+        return sc(d_gq), sc(d_g1), sc(d_gc), sc(dW), sc(db), None, None, None

@@ -57,6 +57,8 @@ typedef struct {
   int32_t window;        /* ceil(window_t) for warp_type 5 (model_v2.py:333-337); 3 */
   int32_t time_warp_att; /* --use_time_warp_att (model_v2.py:269-275) */
   int32_t has_mask;      /* 0: hinfo_mask/hq_mask are None (exp_mask skipped, model_v2.py:263) */
+  int32_t ws_from_fwd;   /* fvta_attn_bwd only: 1 = `workspace` still holds what fvta_attn_fwd left
+                            there for these inputs, so the operand folding is not redone */
 } FvtaAttnDesc;
 
 typedef struct {
@@ -216,6 +218,19 @@ int fvta_charcnn_fwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t he
 int fvta_charcnn_bwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t height, const int32_t* ids,
                      const float* y, const uint8_t* argpos, const float* dy, float* d_table, float* d_bias,
                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Output layer + softmax + mean cross-entropy, forward and backward in ONE launch (replaces
+ * model_v2.py:1061-1083, the non-`use_eu_output` branch, and :1088-1090).
+ *   gq [N,D], g1 [N,D], gc [N,C,D] (choice encodings), W [5D,1] = blocks for
+ *   [gq, g1, gc, g1*gc, gq*gc], b [1], y [N,C] u8 (nullable at test time)
+ *   -> logits [N,C], yp [N,C], *loss += mean CE (caller zeroes it; nullable),
+ *      and, when all five gradient pointers are non-null: d_gq, d_g1, d_gc (overwritten),
+ *      dW [5D], db [1] (ACCUMULATED, caller zeroes) for an upstream gradient of 1.
+ * ---------------------------------------------------------------------------------------- */
+int fvta_output_loss(int32_t N, int32_t C, int32_t D, const float* gq, const float* g1, const float* gc,
+                     const float* W, const float* b, const uint8_t* y, float* logits, float* yp, float* loss,
+                     float* d_gq, float* d_g1, float* d_gc, float* dW, float* db, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Adadelta over one flat buffer.  Replaces tf.train.AdadeltaOptimizer(lr).apply_gradients
