@@ -137,3 +137,59 @@ def test_main_train_then_test_roundtrip(cuda_device, tmp_path):
     assert 0.0 <= acc <= 1.0
     answers = json.load(open(os.path.join(cfg_t.val_path, "answers.json")))
     assert len(answers) == 6 and all(0 <= v < 4 for v in answers.values())   # test split = synthetic // 4
+
+
+def _dp_worker(rank, world, port, q):
+    import os
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    from fvta_memexqa_b200.dp import DataParallel
+    dp = DataParallel(backend="nccl")
+    cfg = tiny_config()
+    cfg.batch_size = 2
+    G = 4
+    gcfg = tiny_config()
+    gcfg.batch_size = G
+    gfeed = make_feed(gcfg, seed=5, glove_vocab=10, num_photos_pool=16)
+    lo, hi = dp.shard(G)
+    batched = {k for k, v in gfeed.items() if v.shape[0] == G and k not in ("image_emb_mat", "existing_emb_mat")}
+    feed = {k: (v[lo:hi] if k in batched else v) for k, v in gfeed.items()}
+    model = get_model(cfg)
+    dp.broadcast_params(model.params.flat)
+    trainer = Trainer(model, cfg, dp=dp)
+    loss, _, _ = trainer.step(None, ((), TensorBatch(feed, hi - lo)))
+    if rank == 0:
+        q.put({k: model.params.view(k).detach().cpu() for k in model.params.offsets})
+    dp.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_two_gpu_step_equals_one_gpu_step(cuda_device):
+    """NCCL data parallel (north_star d): two ranks, each half of a 4-sample batch, one all-reduce
+    of the flat gradient -> same post-Adadelta weights as one GPU on the whole batch (padded shapes
+    pinned).  Skipped on a single-GPU box."""
+    import socket
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+    gcfg = tiny_config()
+    gcfg.batch_size = 4
+    gfeed = make_feed(gcfg, seed=5, glove_vocab=10, num_photos_pool=16)
+    model = get_model(gcfg)
+    Trainer(model, gcfg).step(None, ((), TensorBatch(gfeed, 4)))
+    for k, v in got.items():
+        ref = model.params.view(k).detach().cpu()
+        assert rel_err(v, ref) < 1e-4 or (v - ref).abs().max() < 1e-6, k
