@@ -104,11 +104,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Waiting warps must not compete for issue slots with the warps they wait for (the scheduler
+// favours high warp ids, and a try_wait spin loop is always ready): back off between polls.
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
-      "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-      "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned sleep_ns = 40) {
+  while (!mbar_try(bar, parity)) __nanosleep(sleep_ns);
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
@@ -146,18 +153,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// issue only; pair with tmem_ld_wait() before the registers are read
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand: 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     if (lane == 0) {
       for (int i = 0; i < ntile; ++i) {
         const int s = i % kTcStages;
-        mbar_wait(&empty[s], ((i / kTcStages) & 1) ^ 1);
+        mbar_wait(&empty[s], ((i / kTcStages) & 1) ^ 1, 200);
         TC_TRACE(0, i, 0);
         mbar_expect_tx(&full[s], (uint32_t)(rows * D * 4));
         tma_load_3d(ring + s * pl.stage_bytes, &tmap, &full[s], 0, (tile_begin + i) * TB, n * d.K);
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       for (int i = 0; i < ntile; ++i) {
         const uint32_t acc = tmem_base + (uint32_t)((i & 1) * 128);
         for (int kc = 0; kc < pl.KC; ++kc) {
-          mbar_wait(&a_ready[kc], i & 1);
+          mbar_wait(&a_ready[kc], i & 1, 60);
           TC_TRACE(1, i, kc);
           tc_fence_after();
           const int ks_end = min(pl.ksteps, kc * 4 + 4);
@@ -319,9 +324,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       const int s = i % kTcStages, b2 = i & 1;
       TC_TRACE(2, i, 0);
       mbar_wait(&full[s], (i / kTcStages) & 1);
-      TC_TRACE(2, i, 1);
       if (i >= 2) mbar_wait(&ep_done[b2], ((i - 2) >> 1) & 1);             // softmax(i-2) released buffers b2
-      TC_TRACE(2, i, 2);
+      TC_TRACE(2, i, 1);
       // packed fp32x2 arithmetic (FFMA2/FMUL2): this loop is issue-bound, not FMA-pipe-bound
       float2 zd2 = make_float2(0.f, 0.f), qd2 = make_float2(0.f, 0.f), ln2 = make_float2(0.f, 0.f);
       const float* hrow = reinterpret_cast<const float*>(ring + s * pl.stage_bytes) + (size_t)r * D;
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int kc = 0; kc < pl.KC; ++kc) {
         if (i >= 1) mbar_wait(&a_free[kc], (i - 1) & 1);   // MMA(i-1) has read this operand chunk
-        TC_TRACE(2, i, 3 + kc);
+        TC_TRACE(2, i, 2 + 2 * kc);
         if (active) {
           const int c_end = min(nch, kc * 8 + 8);
 #pragma unroll 2
@@ -382,12 +386,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
             }
           }
         }
+        TC_TRACE(2, i, 3 + 2 * kc);
         fence_async_smem();   // written through the generic proxy; UMMA reads via the async proxy
         mbar_arrive(&a_ready[kc]);
       }
       const float zdot = zd2.x + zd2.y, quad = qd2.x + qd2.y, lin = ln2.x + ln2.y;
       zq_s[(b2 * 2 + h) * 128 + r] = make_float4(zdot, quad, lin, 0.f);
-      TC_TRACE(2, i, 5);
       named_bar_sync(1, 256);
       TC_TRACE(2, i, 6);
       if (h == 0 && active) {
@@ -399,8 +403,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         if (d.use_time_warp) {
           float z = zc;
           for (int kk = 0; kk < d.K; ++kk) z += zq0[kk * TB + tt].x + zq1[kk * TB + tt].x;
-          float tz, cnt;
-          g = gate_from_z(d, z, t < d.T ? t : d.T - 1, tz, cnt);
+          const int tc = t < d.T ? t : d.T - 1;
+          const float tz = 1.f - 2.f * rcp_approx(exp2f_approx(z * 2.885390081777927f) + 1.f);   // tanh(z)
+          g = tz * window_count(tc, d.T, d.warp_type, d.window);
           if (c_col != nullptr && k == 0 && t < d.T) c_col[(size_t)n * d.T + t] = tz;
         }
         float c1, c0v;
@@ -428,9 +433,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
 #pragma unroll
     for (int q = 0; q < 2; ++q) o_acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     float l_acc = 0.f, smax = -INFINITY, ties = 0.f, am_t = 3.0e38f, am_j = 0.f;
-    float colr[16], capr[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { colr[j] = col_s[16 * h + j]; capr[j] = cap_s[16 * h + j]; }
+    const float4* col4 = reinterpret_cast<const float4*>(col_s + 16 * h);
+    const float4* cap4 = reinterpret_cast<const float4*>(cap_s + 16 * h);
 
     for (int i = 0; i < ntile; ++i) {
       const int s = i % kTcStages, b2 = i & 1;
@@ -441,9 +445,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       if (in_range && d.has_mask) mh_u = hall_mask[((size_t)n * d.K + k) * d.T + t];
       TC_TRACE(3, i, 0);
       mbar_wait(&st_ready[b2], (i >> 1) & 1);
-      TC_TRACE(3, i, 1);
       mbar_wait(&acc_full[b2], (i >> 1) & 1);
-      TC_TRACE(3, i, 2);
+      TC_TRACE(3, i, 1);
       tc_fence_after();
       const float2 st = st_s[b2 * 128 + r];
       const float p_c1 = st.x, p_c0 = cosine ? 0.f : st.y, p_g = cosine ? st.y : st.x;
@@ -451,14 +454,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b2 * 128 + 16 * h);
       float P[16];
       {
-        float x[16];
-        tmem_ld16(taddr, P);
-        tmem_ld16(taddr + 32, x);
+        uint32_t x0[16], x1[16];
+        tmem_ld16_issue(taddr, x0);
+        tmem_ld16_issue(taddr + 32, x1);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) P[j] += x[j];
+        for (int j = 0; j < 16; ++j) P[j] = __uint_as_float(x0[j]) + __uint_as_float(x1[j]);
       }
       tc_fence_before();
-      TC_TRACE(3, i, 3);
+      TC_TRACE(3, i, 2);
       const bool mh = in_range && mh_u != 0;
       // branch-free logits: P[] is overwritten by the masked logits a[].  |th| <= 1 here, so
       // th + (-1e30) == -1e30 exactly: exp_mask is a min with the per-column cap
@@ -466,22 +470,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       const float2 c1c1 = make_float2(p_c1, p_c1), c0c0 = make_float2(p_c0, p_c0);
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
-        float2 S = __fadd2_rn(__ffma2_rn(c1c1, make_float2(P[j], P[j + 1]), c0c0), make_float2(colr[j], colr[j + 1]));
+        const float4 cq = col4[j >> 2], kq = cap4[j >> 2];
+        const float colr0 = (j & 2) ? cq.z : cq.x, colr1 = (j & 2) ? cq.w : cq.y;
+        const float capr0 = (j & 2) ? kq.z : kq.x, capr1 = (j & 2) ? kq.w : kq.y;
+        float2 S = __fadd2_rn(__ffma2_rn(c1c1, make_float2(P[j], P[j + 1]), c0c0), make_float2(colr0, colr1));
         if (tanh_on) {  // tanh(x) = 1 - 2 / (1 + e^{2x}), packed
           const float2 e2 = __fmul2_rn(S, make_float2(2.885390081777927f, 2.885390081777927f));  // 2*log2(e)
           const float2 den = __fadd2_rn(make_float2(exp2f_approx(e2.x), exp2f_approx(e2.y)), make_float2(1.f, 1.f));
           S = __ffma2_rn(make_float2(rcp_approx(den.x), rcp_approx(den.y)), make_float2(-2.f, -2.f), make_float2(1.f, 1.f));
         }
-        const float a0 = fminf(S.x, capr[j]);
-        const float a1 = fminf(S.y, capr[j + 1]);
+        const float a0 = fminf(S.x, capr0);
+        const float a1 = fminf(S.y, capr1);
         P[j] = a0; P[j + 1] = a1;
         m = fmaxf(m, fmaxf(a0, a1));
       }
       if (!mh) {   // masked context row: every logit is -1e30 (padding columns stay -inf)
         m = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { P[j] = fminf(capr[j], FVTA_VERY_NEGATIVE); m = fmaxf(m, P[j]); }
+        for (int j = 0; j < 16; ++j) { P[j] = fminf(cap_s[16 * h + j], FVTA_VERY_NEGATIVE); m = fmaxf(m, P[j]); }
       }
+      TC_TRACE(3, i, 3);
       mx_s[(b2 * 2 + h) * 128 + r] = m;
       if (a_logits != nullptr && in_range) {
         float* arow = a_logits + (((size_t)n * d.K + k) * d.T + t) * d.JQ + 16 * h;
@@ -496,8 +504,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
             if (16 * h + j < d.JQ) arow[j] = P[j];
         }
       }
-      TC_TRACE(3, i, 4);
       named_bar_sync(2, 256);
+      TC_TRACE(3, i, 4);
       m = fmaxf(m, mx_s[(b2 * 2 + (h ^ 1)) * 128 + r]);   // full-row maximum
       float w = 0.f;
       if (in_range) {
@@ -518,9 +526,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       }
       float* wg = wg_s + b2 * 128;
       if (h == 0) wg[r] = w * p_g;
-      TC_TRACE(3, i, 5);
       named_bar_sync(3, 256);
-      TC_TRACE(3, i, 6);
+      TC_TRACE(3, i, 5);
       // pass 2: o[k2][d4] += sum_tt w*g*h.  Work unit = (float4 feature group, half of the tile's
       // positions): 2*K*D/4 units over the 256 softmax threads, short independent FFMA2 chains.
 #pragma unroll
@@ -534,16 +541,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
           const float* hp = tile + ((size_t)k2 * TB + t_lo) * D + d4 * 4;
           const float* wp = wg + k2 * TB + t_lo;
           float2 oa = make_float2(o_acc[q].x, o_acc[q].y), ob = make_float2(o_acc[q].z, o_acc[q].w);
-#pragma unroll 5
-          for (int t2 = 0; t2 < t_hi - t_lo; ++t2) {
-            const float4 hv = *reinterpret_cast<const float4*>(hp + (size_t)t2 * D);
-            const float ww = wp[t2];
-            const float2 w2 = make_float2(ww, ww);
-            oa = __ffma2_rn(w2, make_float2(hv.x, hv.y), oa);
-            ob = __ffma2_rn(w2, make_float2(hv.z, hv.w), ob);
+          const int nrow = t_hi - t_lo;
+          // batches of 5 rows: all loads of a batch are issued before its FFMA2s (rows past the
+          // range re-read the last row with weight 0)
+          for (int t0 = 0; t0 < nrow; t0 += 5) {
+            float4 hv[5];
+            float ww[5];
+#pragma unroll
+            for (int e = 0; e < 5; ++e) {
+              const int t2 = min(t0 + e, nrow - 1);
+              hv[e] = *reinterpret_cast<const float4*>(hp + (size_t)t2 * D);
+              ww[e] = (t0 + e < nrow) ? wp[t2] : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 5; ++e) {
+              const float2 w2 = make_float2(ww[e], ww[e]);
+              oa = __ffma2_rn(w2, make_float2(hv[e].x, hv[e].y), oa);
+              ob = __ffma2_rn(w2, make_float2(hv[e].z, hv[e].w), ob);
+            }
           }
           o_acc[q] = make_float4(oa.x, oa.y, ob.x, ob.y);
         }
+        if (q == 0) TC_TRACE(3, i, 6);
       }
       mbar_arrive(&empty[s]);
       mbar_arrive(&ep_done[b2]);

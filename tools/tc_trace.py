@@ -25,9 +25,9 @@ import numpy as np
 a = np.array(buf[:], dtype=np.int64).reshape(4, NT, 8)
 t0 = a[a > 0].min()
 names = {0: ("TMA", ["issue"]), 1: ("MMA", ["a_rdy0", "a_rdy1", "commit"]),
-         2: ("split", ["top", "full", "ep_done", "a_free0", "a_free1", "done", "bar1", "st_rdy"]),
-         3: ("softmax", ["top", "st_rdy", "acc_full", "ldtm", "logits", "w", "bar3", "done"])}
-for i in range(2, 14):
+         2: ("split", ["top", "waits", "free0", "chunk0", "free1", "chunk1", "bar1", "end"]),
+         3: ("softmax", ["top", "waits", "ldtm", "logits", "bar2", "bar3", "unit0", "end"])}
+for i in range(6, 12):
     print("tile %d" % i)
     for role in range(4):
         nm, evs = names[role]
