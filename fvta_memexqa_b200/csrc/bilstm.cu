@@ -29,7 +29,7 @@ struct LstmSmemPlan {
 __host__ __device__ inline LstmSmemPlan lstm_smem_plan(int d) {
   LstmSmemPlan p;
   size_t w = (size_t)d * (4 * d + 1) * sizeof(float);
-  size_t rest = (size_t)kSG * (d + d + 4 * d) * sizeof(float) + 64;
+  size_t rest = (size_t)kSG * (d + d + 4 * d + 4 * d) * sizeof(float) + 128;   // h/dh, c/dc, gates, partials, alignment
   p.w_in_smem = (w + rest) <= 200 * 1024;
   p.wstride = p.w_in_smem ? 4 * d + 1 : 4 * d;
   p.bytes = (p.w_in_smem ? w : 0) + rest;
@@ -235,9 +235,10 @@ __global__ void bilstm_rec_bwd(FvtaLstmDesc L, SeqAddr A, const int32_t* __restr
   const int dir = blockIdx.y;
   const float* wh_g = dir == 0 ? wh_fw : wh_bw;
   float* w_s = sm;
-  float* dh_s = sm + (plan.w_in_smem ? (size_t)d * plan.wstride : 0);  // [kSG][d]
-  float* dc_s = dh_s + kSG * d;                                        // [kSG][d]
-  float* dg_s = dc_s + kSG * d;                                        // [kSG][4d]
+  // every region starts on a 16-byte boundary (float4 reads of the transposed d gates)
+  float* dh_s = sm + (plan.w_in_smem ? round_up_sz((size_t)d * plan.wstride, 4) : 0);  // [kSG][d]
+  float* dc_s = dh_s + round_up(kSG * d, 4);                                          // [kSG][d]
+  float* dg_s = dc_s + round_up(kSG * d, 4);                                          // [4d][kSG] + partials
   __shared__ int len_s[kSG];
   __shared__ int tok_s[kSG];
   __shared__ long long orow_s[kSG];
@@ -259,6 +260,14 @@ __global__ void bilstm_rec_bwd(FvtaLstmDesc L, SeqAddr A, const int32_t* __restr
   const int ws = plan.wstride;
   float* dgd = dgates + (size_t)dir * A.ntok * G;
 
+  // d gates of the current step live transposed in shared memory, dgT[g][kSG] (sequence index
+  // contiguous), so the d h_prev product reads them as two broadcast float4s per g while W_h[e][g]
+  // is read once per g for all kSG sequences: thread (e, quarter) accumulates one quarter of the g
+  // range (= one gate block) for the kSG sequences, the four quarters are summed through shared
+  // memory.  (One LDS per multiply-add, as in a (sequence, e) mapping, makes this loop LSU-bound.)
+  float* dgT = dg_s;                        // [4d][kSG]
+  float* part_s = dg_s + (size_t)G * kSG;   // [4][kSG][d]
+  const int nq = (int)blockDim.x >= 4 * d ? 4 : ((int)blockDim.x >= 2 * d ? 2 : 1);   // quarters run in parallel
   for (int step = maxlen - 1; step >= 0; --step) {
     for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) {
       const int s = i / d, e = i - s * d;
@@ -287,19 +296,39 @@ __global__ void bilstm_rec_bwd(FvtaLstmDesc L, SeqAddr A, const int32_t* __restr
         float* o = dgd + ((size_t)tok_s[s] + t) * G;
         o[e] = dgi; o[d + e] = dgj; o[2 * d + e] = dgf; o[3 * d + e] = dgo;
       }
-      float* gs = dg_s + s * G;
-      gs[e] = dgi; gs[d + e] = dgj; gs[2 * d + e] = dgf; gs[3 * d + e] = dgo;
+      dgT[(size_t)e * kSG + s] = dgi;
+      dgT[(size_t)(d + e) * kSG + s] = dgj;
+      dgT[(size_t)(2 * d + e) * kSG + s] = dgf;
+      dgT[(size_t)(3 * d + e) * kSG + s] = dgo;
     }
     __syncthreads();
-    // d h_prev[s][e] = sum_g dgates[s][g] * Wh[e][g]
+    // partial d h_prev over one part of the g range
+    for (int i = threadIdx.x; i < nq * d; i += blockDim.x) {
+      const int qtr = i / d, e = i - qtr * d;
+      const int g0 = qtr * (G / nq), g1 = g0 + G / nq;
+      const float* wr = W + (size_t)e * ws;
+      float acc[kSG];
+#pragma unroll
+      for (int q = 0; q < kSG; ++q) acc[q] = 0.f;
+      for (int g = g0; g < g1; ++g) {
+        const float w = wr[g];
+        const float4 a0 = *reinterpret_cast<const float4*>(dgT + (size_t)g * kSG);
+        const float4 a1 = *reinterpret_cast<const float4*>(dgT + (size_t)g * kSG + 4);
+        acc[0] = fmaf(a0.x, w, acc[0]); acc[1] = fmaf(a0.y, w, acc[1]);
+        acc[2] = fmaf(a0.z, w, acc[2]); acc[3] = fmaf(a0.w, w, acc[3]);
+        acc[4] = fmaf(a1.x, w, acc[4]); acc[5] = fmaf(a1.y, w, acc[5]);
+        acc[6] = fmaf(a1.z, w, acc[6]); acc[7] = fmaf(a1.w, w, acc[7]);
+      }
+#pragma unroll
+      for (int q = 0; q < kSG; ++q) part_s[((size_t)qtr * kSG + q) * d + e] = acc[q];
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) {
-      const int s = i / d, e = i - s * d;
+      const int s = i / d;
       if (step < len_s[s]) {
-        const float* gs = dg_s + s * G;
-        const float* wr = W + (size_t)e * ws;
-        float acc = 0.f;
-        for (int g = 0; g < G; ++g) acc = fmaf(gs[g], wr[g], acc);
-        dh_s[i] = acc;
+        float v = 0.f;
+        for (int q = 0; q < nq; ++q) v += part_s[(size_t)q * kSG * d + i];
+        dh_s[i] = v;
       }
     }
     __syncthreads();
