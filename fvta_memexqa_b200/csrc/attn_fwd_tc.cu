@@ -73,7 +73,6 @@ __host__ __device__ inline size_t tc_smem_bytes(int KC, int stage_bytes, int Dp)
 
 static bool tc_make_plan(const FvtaAttnDesc& d, TcPlan& p) {
   if ((d.D & 3) != 0 || d.D > 128 || d.D < 8 || d.JQ > kTcJQP || d.K > 8) return false;
-  if (2 * d.K * (d.D / 4) > 512) return false;   // weighted-sum work units over 256 threads x 2
   const bool bounded = (d.simi == 4) || d.add_tanh;
   if (!bounded || d.time_warp_att) return false;
   p.KC = (d.D + 63) / 64;
@@ -320,17 +319,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     uint8_t* ahi_row = a_hi + r * 128;
     uint8_t* alo_row = a_lo + r * 128;
     const float zc = d.use_time_warp ? zconst[n] : 0.f;
+    uint32_t sw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sw[j] = (uint32_t)(((h + 2 * j) ^ (r & 7)) << 4);
     for (int i = 0; i < ntile; ++i) {
       const int s = i % kTcStages, b2 = i & 1;
       TC_TRACE(2, i, 0);
       mbar_wait(&full[s], (i / kTcStages) & 1);
       if (i >= 2) mbar_wait(&ep_done[b2], ((i - 2) >> 1) & 1);             // softmax(i-2) released buffers b2
       TC_TRACE(2, i, 1);
-      // packed fp32x2 arithmetic (FFMA2/FMUL2): this loop is issue-bound, not FMA-pipe-bound
-      float2 zd2 = make_float2(0.f, 0.f), qd2 = make_float2(0.f, 0.f), ln2 = make_float2(0.f, 0.f);
+      // packed fp32x2 arithmetic (FFMA2/FMUL2); two accumulator sets keep the dependent chains short
+      float2 zdA = make_float2(0.f, 0.f), qdA = make_float2(0.f, 0.f), lnA = make_float2(0.f, 0.f);
+      float2 zdB = make_float2(0.f, 0.f), qdB = make_float2(0.f, 0.f), lnB = make_float2(0.f, 0.f);
       const float* hrow = reinterpret_cast<const float*>(ring + s * pl.stage_bytes) + (size_t)r * D;
       const float2 neg1 = make_float2(-1.f, -1.f);
-      auto split_store = [&](int c, const float4& v0, const float4& v1) {
+      auto split_store = [&](uint32_t off, const float4& v0, const float4& v1) {
         const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
         const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
         // residual x - fp16(x) is exact in fp32; below 2^-14 it lands on fp16 subnormals whose
@@ -341,7 +344,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         const float2 r3 = __ffma2_rn(__half22float2(h3), neg1, make_float2(v1.z, v1.w));
         const __half2 l0 = __floats2half2_rn(r0.x, r0.y), l1 = __floats2half2_rn(r1.x, r1.y);
         const __half2 l2 = __floats2half2_rn(r2.x, r2.y), l3 = __floats2half2_rn(r3.x, r3.y);
-        const uint32_t off = (uint32_t)((c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4));
         uint4 ph, plo;
         ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
         ph.z = *reinterpret_cast<const uint32_t*>(&h2); ph.w = *reinterpret_cast<const uint32_t*>(&h3);
@@ -350,19 +352,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         *reinterpret_cast<uint4*>(ahi_row + off) = ph;
         *reinterpret_cast<uint4*>(alo_row + off) = plo;
       };
-      auto stats4 = [&](int d0, const float4& v) {
+      auto stats4 = [&](int d0, const float4& v, float2& zd, float2& qd, float2& ln) {
         const float4 cu = *reinterpret_cast<const float4*>(coef_s + d0);
         const float4 cq = *reinterpret_cast<const float4*>(coef_s + 2 * Dp + d0);
         const float2 a01 = make_float2(v.x, v.y), a23 = make_float2(v.z, v.w);
         const float2 s01 = __fmul2_rn(a01, a01), s23 = __fmul2_rn(a23, a23);
-        zd2 = __ffma2_rn(make_float2(cu.x, cu.y), s01, zd2);
-        zd2 = __ffma2_rn(make_float2(cu.z, cu.w), s23, zd2);
-        qd2 = __ffma2_rn(make_float2(cq.x, cq.y), s01, qd2);
-        qd2 = __ffma2_rn(make_float2(cq.z, cq.w), s23, qd2);
+        zd = __ffma2_rn(make_float2(cu.x, cu.y), s01, zd);
+        zd = __ffma2_rn(make_float2(cu.z, cu.w), s23, zd);
+        qd = __ffma2_rn(make_float2(cq.x, cq.y), s01, qd);
+        qd = __ffma2_rn(make_float2(cq.z, cq.w), s23, qd);
         if (HAS_LIN) {
           const float4 cl = *reinterpret_cast<const float4*>(coef_s + Dp + d0);
-          ln2 = __ffma2_rn(make_float2(cl.x, cl.y), a01, ln2);
-          ln2 = __ffma2_rn(make_float2(cl.z, cl.w), a23, ln2);
+          ln = __ffma2_rn(make_float2(cl.x, cl.y), a01, ln);
+          ln = __ffma2_rn(make_float2(cl.z, cl.w), a23, ln);
         }
       };
       const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -371,18 +373,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         TC_TRACE(2, i, 2 + 2 * kc);
         if (active) {
           const int c_end = min(nch, kc * 8 + 8);
-#pragma unroll 2
-          for (int c = kc * 8 + h; c < c_end; c += 2) {
-            if (c < nfull) {
-              const float4 v0 = *reinterpret_cast<const float4*>(hrow + c * 8);
-              const float4 v1 = *reinterpret_cast<const float4*>(hrow + c * 8 + 4);
-              stats4(c * 8, v0);
-              stats4(c * 8 + 4, v1);
-              split_store(c, v0, v1);
-            } else {  // D % 8 == 4 leaves a half chunk; the rest is zero padding up to the k-step
-              float4 v0 = zero4;
-              if (c * 8 < D) { v0 = *reinterpret_cast<const float4*>(hrow + c * 8); stats4(c * 8, v0); }
-              split_store(c, v0, zero4);
+          // this thread's chunks of the 64-feature group: c = 8 kc + h + 2 j, swizzled 16-byte slot sw[j]
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = kc * 8 + h + 2 * j;
+            if (c < c_end) {
+              const uint32_t off = (uint32_t)(kc * 16384) + sw[j];
+              if (c < nfull) {
+                const float4 v0 = *reinterpret_cast<const float4*>(hrow + c * 8);
+                const float4 v1 = *reinterpret_cast<const float4*>(hrow + c * 8 + 4);
+                stats4(c * 8, v0, zdA, qdA, lnA);
+                stats4(c * 8 + 4, v1, zdB, qdB, lnB);
+                split_store(off, v0, v1);
+              } else {  // D % 8 == 4 leaves a half chunk; the rest is zero padding up to the k-step
+                float4 v0 = zero4;
+                if (c * 8 < D) { v0 = *reinterpret_cast<const float4*>(hrow + c * 8); stats4(c * 8, v0, zdA, qdA, lnA); }
+                split_store(off, v0, zero4);
+              }
             }
           }
         }
@@ -390,6 +397,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         fence_async_smem();   // written through the generic proxy; UMMA reads via the async proxy
         mbar_arrive(&a_ready[kc]);
       }
+      const float2 zd2 = __fadd2_rn(zdA, zdB), qd2 = __fadd2_rn(qdA, qdB), ln2 = __fadd2_rn(lnA, lnB);
       const float zdot = zd2.x + zd2.y, quad = qd2.x + qd2.y, lin = ln2.x + ln2.y;
       zq_s[(b2 * 2 + h) * 128 + r] = make_float4(zdot, quad, lin, 0.f);
       named_bar_sync(1, 256);
@@ -425,10 +433,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     const int k = active ? r / TB : 0, tt = active ? r - k * TB : 0;
     const bool tanh_on = d.add_tanh && d.simi != 4;
     const bool cosine = d.simi == 4;
+    // pass 2 mapping: thread u = part * D4 + d4 owns the float4 feature group d4 over the tile rows
+    // [wr0, wr1) (rows are k-major: r = k * TB + tt).  A range never spans more than two modalities
+    // (its length <= TB because K <= 256 / D4), hence two accumulators.
     const int D4 = D >> 2;
-    const int npair = d.K * D4;      // float4 feature groups of the weighted sum
-    const int nunit = 2 * npair;     // x two halves of the tile's positions
-    const int TBh = (TB + 1) >> 1;
+    const int nparts = 256 / D4;
+    const bool ws_on = tid < nparts * D4;
+    const int ws_d4 = tid % D4, ws_part = tid / D4;
+    const int wr0 = ws_on ? (ws_part * rows) / nparts : 0;
+    const int wr1 = ws_on ? ((ws_part + 1) * rows) / nparts : 0;
+    const int ws_kb = (wr0 / TB + 1) * TB;                 // first row of the next modality
+    const int ws_n0 = max(min(wr1, ws_kb) - wr0, 0);       // rows accumulated into o_acc[0]
+    const int ws_n1 = (wr1 - wr0) - ws_n0;                 //                      into o_acc[1]
+    const int ws_off = wr0 * D + ws_d4 * 4;
     float4 o_acc[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) o_acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -484,7 +501,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         P[j] = a0; P[j + 1] = a1;
         m = fmaxf(m, fmaxf(a0, a1));
       }
-      if (!mh) {   // masked context row: every logit is -1e30 (padding columns stay -inf)
+      if (__any_sync(0xffffffffu, !mh) && !mh) {   // masked context row: every logit is -1e30 (padding columns stay -inf)
         m = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 16; ++j) { P[j] = fminf(cap_s[16 * h + j], FVTA_VERY_NEGATIVE); m = fmaxf(m, P[j]); }
@@ -508,8 +525,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       TC_TRACE(3, i, 4);
       m = fmaxf(m, mx_s[(b2 * 2 + (h ^ 1)) * 128 + r]);   // full-row maximum
       float w = 0.f;
-      if (in_range) {
-        if (m >= smax) {   // rare after the first tiles: count ties / record the position lazily
+      // a new (or tied) running maximum is rare after the first tiles: keep the bookkeeping behind a
+      // warp-uniform branch so it costs nothing when no lane needs it
+      const bool newmax = in_range && m >= smax;
+      if (__any_sync(0xffffffffu, newmax)) {
+        if (newmax) {
           if (m > smax) { smax = m; ties = 0.f; am_t = 3.0e38f; }
           int cnt = 0, jm = -1;
 #pragma unroll
@@ -521,6 +541,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
           ties += (float)cnt;
           if (jm >= 0 && (float)t < am_t) { am_t = (float)t; am_j = (float)(16 * h + jm); }
         }
+      }
+      if (in_range) {
         w = (m <= -1e29f) ? kMaskedWeight : expf(m - 1.f);
         if (h == 0) l_acc += w;
       }
@@ -528,41 +550,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       if (h == 0) wg[r] = w * p_g;
       named_bar_sync(3, 256);
       TC_TRACE(3, i, 5);
-      // pass 2: o[k2][d4] += sum_tt w*g*h.  Work unit = (float4 feature group, half of the tile's
-      // positions): 2*K*D/4 units over the 256 softmax threads, short independent FFMA2 chains.
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int u = tid + q * 256;
-        if (u < nunit) {
-          const int half = u >= npair ? 1 : 0;
-          const int p = u - half * npair;
-          const int k2 = p / D4, d4 = p - k2 * D4;
-          const int t_lo = half ? TBh : 0, t_hi = half ? TB : TBh;
-          const float* hp = tile + ((size_t)k2 * TB + t_lo) * D + d4 * 4;
-          const float* wp = wg + k2 * TB + t_lo;
-          float2 oa = make_float2(o_acc[q].x, o_acc[q].y), ob = make_float2(o_acc[q].z, o_acc[q].w);
-          const int nrow = t_hi - t_lo;
-          // batches of 5 rows: all loads of a batch are issued before its FFMA2s (rows past the
-          // range re-read the last row with weight 0)
-          for (int t0 = 0; t0 < nrow; t0 += 5) {
-            float4 hv[5];
-            float ww[5];
-#pragma unroll
-            for (int e = 0; e < 5; ++e) {
-              const int t2 = min(t0 + e, nrow - 1);
-              hv[e] = *reinterpret_cast<const float4*>(hp + (size_t)t2 * D);
-              ww[e] = (t0 + e < nrow) ? wp[t2] : 0.f;
-            }
-#pragma unroll
-            for (int e = 0; e < 5; ++e) {
-              const float2 w2 = make_float2(ww[e], ww[e]);
-              oa = __ffma2_rn(w2, make_float2(hv[e].x, hv[e].y), oa);
-              ob = __ffma2_rn(w2, make_float2(hv[e].z, hv[e].w), ob);
-            }
+      // pass 2: o[k][d4] += sum_rows (w*g) * h over this thread's row range, four rows per batch
+      if (ws_on) {
+        const float* hp = tile + ws_off;
+        const float* wp = wg + wr0;
+        auto wsum = [&](int nrow, float4& acc) {
+          float2 oa = make_float2(acc.x, acc.y), ob = make_float2(acc.z, acc.w);
+          int t2 = 0;
+          for (; t2 + 4 <= nrow; t2 += 4) {
+            const float4 h0 = *reinterpret_cast<const float4*>(hp);
+            const float4 h1 = *reinterpret_cast<const float4*>(hp + D);
+            const float4 h2 = *reinterpret_cast<const float4*>(hp + 2 * D);
+            const float4 h3 = *reinterpret_cast<const float4*>(hp + 3 * D);
+            const float w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+            oa = __ffma2_rn(make_float2(w0, w0), make_float2(h0.x, h0.y), oa);
+            ob = __ffma2_rn(make_float2(w0, w0), make_float2(h0.z, h0.w), ob);
+            oa = __ffma2_rn(make_float2(w1, w1), make_float2(h1.x, h1.y), oa);
+            ob = __ffma2_rn(make_float2(w1, w1), make_float2(h1.z, h1.w), ob);
+            oa = __ffma2_rn(make_float2(w2, w2), make_float2(h2.x, h2.y), oa);
+            ob = __ffma2_rn(make_float2(w2, w2), make_float2(h2.z, h2.w), ob);
+            oa = __ffma2_rn(make_float2(w3, w3), make_float2(h3.x, h3.y), oa);
+            ob = __ffma2_rn(make_float2(w3, w3), make_float2(h3.z, h3.w), ob);
+            hp += 4 * D;
+            wp += 4;
           }
-          o_acc[q] = make_float4(oa.x, oa.y, ob.x, ob.y);
-        }
-        if (q == 0) TC_TRACE(3, i, 6);
+          for (; t2 < nrow; ++t2) {
+            const float4 h0 = *reinterpret_cast<const float4*>(hp);
+            const float w0 = wp[0];
+            oa = __ffma2_rn(make_float2(w0, w0), make_float2(h0.x, h0.y), oa);
+            ob = __ffma2_rn(make_float2(w0, w0), make_float2(h0.z, h0.w), ob);
+            hp += D;
+            wp += 1;
+          }
+          acc = make_float4(oa.x, oa.y, ob.x, ob.y);
+        };
+        wsum(ws_n0, o_acc[0]);
+        TC_TRACE(3, i, 6);
+        wsum(ws_n1, o_acc[1]);
       }
       mbar_arrive(&empty[s]);
       mbar_arrive(&ep_done[b2]);
@@ -588,23 +612,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       float* ps = part_stat + (((size_t)n * pl.slabs + slab) * d.K + tid) * kPartW;
       ps[0] = 1.f; ps[1] = l; ps[2] = sm; ps[3] = ti; ps[4] = at; ps[5] = aj; ps[6] = 0.f; ps[7] = 0.f;
     }
-    // the two position-halves of a feature group live on different threads: the first stores its
-    // partial sum, the second adds to it after a barrier (this CTA owns the part_o slab exclusively)
-    for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int u = tid + q * 256;
-        if (u < nunit && (u >= npair ? 1 : 0) == pass) {
-          const int p = u - pass * npair;
-          const int k2 = p / D4, d4 = p - k2 * D4;
-          float4* dst = reinterpret_cast<float4*>(part_o + (((size_t)n * pl.slabs + slab) * d.K + k2) * Dp + d4 * 4);
-          float4 v = o_acc[q];
-          if (pass == 1) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-          *dst = v;
+    // the row ranges of one feature group live on nparts threads: stage every thread's two partial
+    // sums in shared memory (over red_s, once the statistics above are out) and add them per
+    // (modality, feature group) in a fixed order, so the result does not depend on scheduling
+    named_bar_sync(2, 256);
+    float4* stg = reinterpret_cast<float4*>(red_s);   // [256][2]
+    if (ws_on) { stg[tid * 2] = o_acc[0]; stg[tid * 2 + 1] = o_acc[1]; }
+    named_bar_sync(2, 256);
+    for (int idx = tid; idx < d.K * D4; idx += 256) {
+      const int k2 = idx / D4, d4 = idx - k2 * D4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int pp = 0; pp < nparts; ++pp) {
+        const int q0 = (pp * rows) / nparts, q1 = ((pp + 1) * rows) / nparts;
+        if (q1 <= q0) continue;
+        const int klo = q0 / TB;
+        int slot = -1;
+        if (klo == k2) slot = 0;
+        else if (klo + 1 == k2 && q1 > (klo + 1) * TB) slot = 1;
+        if (slot >= 0) {
+          const float4 o = stg[(pp * D4 + d4) * 2 + slot];
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
         }
       }
-      __threadfence_block();
-      named_bar_sync(2, 256);
+      *reinterpret_cast<float4*>(part_o + (((size_t)n * pl.slabs + slab) * d.K + k2) * Dp + d4 * 4) = v;
     }
   }
   tc_fence_before();
