@@ -74,10 +74,18 @@ SYMBOLS = {
     "fvta_gemm": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_float_p, ctypes.c_int32,
                                  ctypes.c_int32, c_float_p, ctypes.c_int32, ctypes.c_int32, c_float_p,
                                  ctypes.c_int32, c_float_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
-    "fvta_charcnn_fwd": (ctypes.c_int, [ctypes.c_int32] * 5 + [c_i32_p, c_float_p, c_float_p, c_float_p, c_u8_p,
+    "fvta_charcnn_fwd": (ctypes.c_int, [ctypes.c_int32] * 5 + [c_i32_p, c_float_p, c_float_p, c_float_p,
+                                                                 ctypes.c_int32, c_u8_p, ctypes.c_void_p]),
+    "fvta_charcnn_bwd": (ctypes.c_int, [ctypes.c_int32] * 5 + [c_i32_p, c_float_p, ctypes.c_int32, c_u8_p, c_float_p,
+                                                                 ctypes.c_int32, c_float_p, c_float_p,
                                                                  ctypes.c_void_p]),
-    "fvta_charcnn_bwd": (ctypes.c_int, [ctypes.c_int32] * 5 + [c_i32_p, c_float_p, c_u8_p, c_float_p, c_float_p,
-                                                                 c_float_p, ctypes.c_void_p]),
+    "fvta_embed_rows": (ctypes.c_int, [ctypes.c_int32] * 4 + [ctypes.c_void_p, c_float_p, c_float_p, c_float_p,
+                                                                ctypes.c_int32, ctypes.c_void_p]),
+    "fvta_embed_rows_bwd": (ctypes.c_int, [ctypes.c_int32] * 3 + [ctypes.c_void_p, c_float_p, ctypes.c_int32,
+                                                                    c_float_p, ctypes.c_void_p]),
+    "fvta_bias_act_grad": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, c_float_p, ctypes.c_int32, c_float_p,
+                                          ctypes.c_int32, ctypes.c_int32, c_float_p, ctypes.c_int32, c_float_p,
+                                          ctypes.c_void_p]),
     "fvta_output_loss": (ctypes.c_int, [ctypes.c_int32] * 3 + [c_float_p] * 5 + [c_u8_p] + [c_float_p] * 8 +
                          [ctypes.c_void_p]),
     "fvta_adadelta": (ctypes.c_int, [ctypes.c_int64, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,

@@ -21,7 +21,7 @@ constexpr int kCnnWordsPerBlock = 8;
 // grid ceil(ntok / 8), block 8 x 32: lane = group of 4 output channels, threadIdx.y = word
 __global__ void charcnn_fwd_kernel(int ntok, int W, int VC, int cw, int height, const int32_t* __restrict__ ids,
                                    const float* __restrict__ table, const float* __restrict__ bias,
-                                   float* __restrict__ y, uint8_t* __restrict__ argpos) {
+                                   float* __restrict__ y, int ldy, uint8_t* __restrict__ argpos) {
   __shared__ int id_s[kCnnWordsPerBlock][64];
   const int wl = threadIdx.y, lane = threadIdx.x;
   const int w = blockIdx.x * kCnnWordsPerBlock + wl;
@@ -51,15 +51,15 @@ __global__ void charcnn_fwd_kernel(int ntok, int W, int VC, int cw, int height, 
     }
     // relu(max_p) == max_p relu
     const float4 out = make_float4(fmaxf(best.x, 0.f), fmaxf(best.y, 0.f), fmaxf(best.z, 0.f), fmaxf(best.w, 0.f));
-    *reinterpret_cast<float4*>(y + (size_t)w * cw + o4 * 4) = out;
+    *reinterpret_cast<float4*>(y + (size_t)w * ldy + o4 * 4) = out;
     *reinterpret_cast<uchar4*>(argpos + (size_t)w * cw + o4 * 4) =
         make_uchar4((unsigned char)bp0, (unsigned char)bp1, (unsigned char)bp2, (unsigned char)bp3);
   }
 }
 
 __global__ void charcnn_bwd_kernel(int ntok, int W, int VC, int cw, int height, const int32_t* __restrict__ ids,
-                                   const float* __restrict__ y, const uint8_t* __restrict__ argpos,
-                                   const float* __restrict__ dy, float* __restrict__ d_table,
+                                   const float* __restrict__ y, int ldy, const uint8_t* __restrict__ argpos,
+                                   const float* __restrict__ dy, int lddy, float* __restrict__ d_table,
                                    float* __restrict__ d_bias) {
   __shared__ int id_s[kCnnWordsPerBlock][64];
   __shared__ float db_s[kCnnWordsPerBlock][129];
@@ -73,8 +73,8 @@ __global__ void charcnn_bwd_kernel(int ntok, int W, int VC, int cw, int height, 
   __syncthreads();
   for (int o = lane; o < cw; o += 32) {
     float g = 0.f;
-    if (w < ntok && y[(size_t)w * cw + o] > 0.f) {   // ReLU alive
-      g = dy[(size_t)w * cw + o];
+    if (w < ntok && y[(size_t)w * ldy + o] > 0.f) {   // ReLU alive
+      g = dy[(size_t)w * lddy + o];
       const int p = argpos[(size_t)w * cw + o];
       for (int h = 0; h < height; ++h) atomicAdd(d_table + ((size_t)h * VC + id_s[wl][p + h]) * cw + o, g);
     }
@@ -94,28 +94,30 @@ __global__ void charcnn_bwd_kernel(int ntok, int W, int VC, int cw, int height, 
 
 extern "C" int fvta_charcnn_fwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t height,
                                 const int32_t* ids, const float* table, const float* bias, float* y,
-                                uint8_t* argpos, void* stream) {
+                                int32_t ldy, uint8_t* argpos, void* stream) {
   using namespace fvta;
   if (ntok < 0 || W <= 0 || VC <= 0 || cw <= 0 || height <= 0) return FVTA_E_BADARG;
   if (ntok == 0) return FVTA_OK;
   if (!ids || !table || !bias || !y || !argpos) return FVTA_E_BADARG;
   if ((cw & 3) != 0 || cw > 128 || W > 64 || W < height || W - height + 1 > 255) return FVTA_E_SHAPE;
+  if (ldy < cw || (ldy & 3) != 0 || (reinterpret_cast<uintptr_t>(y) & 15) != 0) return FVTA_E_BADARG;
   dim3 block(32, kCnnWordsPerBlock);
   charcnn_fwd_kernel<<<(ntok + kCnnWordsPerBlock - 1) / kCnnWordsPerBlock, block, 0, (cudaStream_t)stream>>>(
-      ntok, W, VC, cw, height, ids, table, bias, y, argpos);
+      ntok, W, VC, cw, height, ids, table, bias, y, ldy, argpos);
   return check_launch("charcnn_fwd_kernel");
 }
 
 extern "C" int fvta_charcnn_bwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t height,
-                                const int32_t* ids, const float* y, const uint8_t* argpos, const float* dy,
-                                float* d_table, float* d_bias, void* stream) {
+                                const int32_t* ids, const float* y, int32_t ldy, const uint8_t* argpos,
+                                const float* dy, int32_t lddy, float* d_table, float* d_bias, void* stream) {
   using namespace fvta;
   if (ntok < 0 || W <= 0 || VC <= 0 || cw <= 0 || height <= 0) return FVTA_E_BADARG;
   if (ntok == 0) return FVTA_OK;
   if (!ids || !y || !argpos || !dy || !d_table || !d_bias) return FVTA_E_BADARG;
   if ((cw & 3) != 0 || cw > 128 || W > 64 || W < height) return FVTA_E_SHAPE;
+  if (ldy < cw || lddy < cw) return FVTA_E_BADARG;
   dim3 block(32, kCnnWordsPerBlock);
   charcnn_bwd_kernel<<<(ntok + kCnnWordsPerBlock - 1) / kCnnWordsPerBlock, block, 0, (cudaStream_t)stream>>>(
-      ntok, W, VC, cw, height, ids, y, argpos, dy, d_table, d_bias);
+      ntok, W, VC, cw, height, ids, y, ldy, argpos, dy, lddy, d_table, d_bias);
   return check_launch("charcnn_bwd_kernel");
 }

@@ -276,22 +276,24 @@ class Model:
         cfg, v = self.config, self.vars
         VW = self.VW
         table = v["emb/word/var/word_emb_mat"]
+        if cfg.use_char:
+            filt = v["emb/conv/conv1d/filter"]                          # [1,5,cdim,cwdim]
+            height, cdim, cw = filt.shape[1], filt.shape[2], filt.shape[3]
+            dropped = is_train and cfg.keep_prob < 1.0                  # conv1d input dropout (:60-61)
+            table_ok = (not dropped and cw % 4 == 0 and cw <= 128 and ids_c.shape[1] <= 64
+                        and ids_c.shape[1] - height + 1 <= 255)
+        if not cfg.use_char or table_ok:
+            # a window's conv output depends only on its `height` char ids: tabulate
+            # char_emb @ filter[h] once ([height,VC,cw], a few MFLOP) and gather-add (csrc/charcnn.cu);
+            # the word vectors land next to it in the same buffer (csrc/embed.cu)
+            ctab = torch.matmul(v["emb/var/char_emb"].unsqueeze(0), filt[0]) if cfg.use_char else None
+            return ops.TokenEmbedFn.apply(table, glove, ids, ctab, v["emb/conv/conv1d/bias"] if cfg.use_char else None,
+                                          ids_c if cfg.use_char else None,
+                                          self._sink("emb/word/var/word_emb_mat", "emb/conv/conv1d/bias"))
         is_new = ids < VW
         A = torch.where(is_new.unsqueeze(-1),
                         ops.embed(table, ids.clamp(max=VW - 1), self._sink("emb/word/var/word_emb_mat")[0]),
                         ops.embed(glove, (ids - VW).clamp(min=0)))
-        if not cfg.use_char:
-            return A
-        filt = v["emb/conv/conv1d/filter"]                              # [1,5,cdim,cwdim]
-        height, cdim, cw = filt.shape[1], filt.shape[2], filt.shape[3]
-        dropped = is_train and cfg.keep_prob < 1.0                      # conv1d input dropout (:60-61)
-        if not dropped and cw % 4 == 0 and cw <= 128 and ids_c.shape[1] <= 64:
-            # a window's conv output depends only on its `height` char ids: tabulate
-            # char_emb @ filter[h] once ([height,VC,cw], a few MFLOP) and gather-add (csrc/charcnn.cu)
-            table = torch.matmul(v["emb/var/char_emb"].unsqueeze(0), filt[0])
-            xc = ops.CharCnnTableFn.apply(table, v["emb/conv/conv1d/bias"], ids_c,
-                                          self._sink("emb/conv/conv1d/bias")[0])
-            return torch.cat([xc, A], dim=-1)
         Ac = torch.nn.functional.embedding(ids_c.long(), v["emb/var/char_emb"])   # [cap, W, cdim]
         if dropped:
             Ac = torch.nn.functional.dropout(Ac, 1.0 - cfg.keep_prob, True)
@@ -345,6 +347,9 @@ class Model:
         acfg = ops.AttnConfig(cfg.simiMatrix, cfg.add_tanh, cfg.use_time_warp, cfg.warp_type,
                               self.window_t, cfg.use_time_warp_att)
         tw = cfg.use_time_warp
+        # both attentions write their context / question gradients straight into one arena-shaped buffer
+        asink = ops.ArenaGradSink(arena, meta["hall_rows"], meta["hq_row0"]) \
+            if (torch.is_grad_enabled() and arena.requires_grad) else None
         g1_all, a_logits, c_col, warp_h = ops.FvtaAttentionFn.apply(
             acfg, (want_vis, want_vis and tw, want_vis and tw),
             hall.reshape(N, K, T, D), f["hall_mask"], hq, f["q_mask"], lq if tw else None,
@@ -354,20 +359,22 @@ class Model:
             # fvta_attn_bwd OVERWRITES its parameter gradients: only sink them when nothing else
             # (weight decay) adds to the same slots through autograd
             None if cfg.wd else self._sink("attention/all/att_logits/W", "attention/all/att_logits/b",
-                                           "time_warp/WH/W", "time_warp/WH/b", "time_warp/WC/W", "time_warp/WC/b"))
+                                           "time_warp/WH/W", "time_warp/WH/b", "time_warp/WC/W", "time_warp/WC/b"),
+            arena if asink is not None else None, (asink, "context") if asink is not None else None)
 
         # question attention (model_v2.py:1039-1050)
         q_att = None
         if cfg.use_question_att:
             qcfg = ops.AttnConfig(cfg.simiMatrix, cfg.add_tanh, False, 1, 3.0, False)
-            ones = torch.ones(N, 1, dtype=torch.bool, device=hq.device)
+            ones = self._ones_mask(N, hq.device)
             gq, q_att, _, _ = ops.FvtaAttentionFn.apply(
                 qcfg, (want_vis, False, False), hq.unsqueeze(1), f["q_mask"].unsqueeze(1),
                 g1_all.unsqueeze(1), ones, None,
                 v.get("question_emb/question_att/att_logits/W"), v.get("question_emb/question_att/att_logits/b"),
                 None, None, None, None,
                 None if cfg.wd else self._sink("question_emb/question_att/att_logits/W",
-                                               "question_emb/question_att/att_logits/b") + (None, None, None, None))
+                                               "question_emb/question_att/att_logits/b") + (None, None, None, None),
+                None, (asink, "question") if asink is not None else None)
         else:
             gq = lq
 
@@ -390,7 +397,8 @@ class Model:
                 gq, g1_all, lchoices, v["output/choicelogits/W"], v["output/choicelogits/b"], yt,
                 self._sink("output/choicelogits/W", "output/choicelogits/b"), torch.is_grad_enabled())
             self.logits, self.yp = logits, yp
-            self.loss = (loss + self._wd_loss()) if yt is not None else None
+            wdl = self._wd_loss()
+            self.loss = (loss if isinstance(wdl, float) and wdl == 0.0 else loss + wdl) if yt is not None else None
         self.g1_all, self.gq = g1_all, gq
         if want_vis:
             self.hall = hall
@@ -409,6 +417,13 @@ class Model:
         cfg = self.config
         losses = -(y.to(logits.dtype) * torch.log_softmax(logits, dim=-1)).sum(-1)
         return losses.mean() + self._wd_loss()
+
+    def _ones_mask(self, N, device):
+        """[N,1] all-true mask of the question attention's single 'question word' (cached)."""
+        m = getattr(self, "_ones_cache", None)
+        if m is None or m.shape[0] != N or m.device != device:
+            m = self._ones_cache = torch.ones(N, 1, dtype=torch.bool, device=device)
+        return m
 
     def _wd_loss(self):
         cfg = self.config

@@ -105,16 +105,22 @@ def attn_forward(cfg, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W=None, WH_b=No
                 desc=desc, saved=(hall, hm, hq, qm, lq))
 
 
-def attn_backward(fwd, d_g1_all, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=None, sinks=None):
+def attn_backward(fwd, d_g1_all, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=None, sinks=None,
+                  d_hall_out=None, d_hq_out=None):
     """fvta_attn_bwd given the dict attn_forward returned.  Returns dict of gradients.  `sinks`:
-    optional tensors the six parameter gradients are written into (the entry point overwrites)."""
+    optional tensors the six parameter gradients are written into (the entry point overwrites).
+    d_hall_out / d_hq_out: optional contiguous tensors to receive d_hall / d_hq (overwritten)."""
     lib = _lib.load()
     f32 = torch.float32
     hall, hm, hq, qm, lq = fwd["saved"]
     desc = fwd["desc"]
     d_g1_all = _req(d_g1_all, f32, "d_g1_all")
     dev = hall.device
-    out = dict(d_hall=torch.empty_like(hall), d_hq=torch.empty_like(hq),
+    for t, ref, nme in ((d_hall_out, hall, "d_hall_out"), (d_hq_out, hq, "d_hq_out")):
+        if t is not None and (t.numel() != ref.numel() or not t.is_contiguous() or t.dtype != f32):
+            raise _lib.FvtaError("%s must be a contiguous fp32 tensor of %d elements" % (nme, ref.numel()))
+    out = dict(d_hall=d_hall_out if d_hall_out is not None else torch.empty_like(hall),
+               d_hq=d_hq_out if d_hq_out is not None else torch.empty_like(hq),
                d_lq=torch.empty_like(lq) if (lq is not None and desc.use_time_warp) else None)
     if sinks is not None:
         gW, gb = sinks[0], sinks[1]
@@ -191,19 +197,24 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        lib = _lib.load()
         flat, W, y = ctx.saved_tensors
-        dy = dy.reshape(-1, W.shape[1]).contiguous()
-        if ctx.add_tanh:
-            dy = dy * (1.0 - y * y)
-        # the image features and other fed inputs need no gradient: skip that GEMM
-        dx = gemm(dy, W, trans_b=True).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
+        N = W.shape[1]
+        dy = _req(dy.reshape(-1, N), torch.float32, "dy")
         gW, gb = ctx.sinks
+        db = gb if gb is not None else torch.zeros(N, dtype=dy.dtype, device=dy.device)
+        # d z = d y * (1 - y^2) and d b += column sums, one launch (csrc/embed.cu)
+        dz = torch.empty_like(dy) if ctx.add_tanh else dy
+        rc = lib.fvta_bias_act_grad(dy.shape[0], N, _ptr(dy), N, _ptr(y) if ctx.add_tanh else None, N,
+                                    1 if ctx.add_tanh else 0, _ptr(dz) if ctx.add_tanh else None, N, _ptr(db),
+                                    _stream())
+        check(rc, "fvta_bias_act_grad")
+        # the image features and other fed inputs need no gradient: skip that GEMM
+        dx = gemm(dz, W, trans_b=True).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
         if gW is not None:
-            gemm(flat, dy, trans_a=True, out=gW, accumulate=True)
-            gb.add_(dy.sum(0))
+            gemm(flat, dz, trans_a=True, out=gW, accumulate=True)
             return dx, None, None, None, None, None
-        dW = gemm(flat, dy, trans_a=True)
-        db = dy.sum(0)
+        dW = gemm(flat, dz, trans_a=True)
         return dx, dW, db, None, None, None
 
 
@@ -293,19 +304,48 @@ def bilstm(x, lens, kernel, bias):
 # ---------------------------------------------------------------------------------------------
 # attention as an autograd op
 # ---------------------------------------------------------------------------------------------
+class ArenaGradSink:
+    """Gradient buffer of the context-tensor arena [hall rows | hq rows] x D that the attention
+    backwards write into directly.  Without it autograd materialises one zero-filled arena per
+    slice (hall, hq) and adds them -- three arena-sized launches per step for nothing."""
+
+    def __init__(self, arena, hall_rows, hq_row0):
+        self.buf = torch.empty_like(arena)
+        self.hall_rows, self.hq_row0 = hall_rows, hq_row0
+        self.hq_written = False
+
+    def hall(self):
+        return self.buf[:self.hall_rows]
+
+    def hq(self):
+        return self.buf[self.hq_row0:]
+
+
 class FvtaAttentionFn(torch.autograd.Function):
     """Time-warp gate + attention_3d (model_v2.py:953-1024) as one differentiable op.
     Inputs: hall [N,K,T,D], hall_mask, hq, hq_mask, lq, W, b, WH_W, WH_b, WC_W, WC_b.
-    Outputs: g1_all [N,D] (differentiable), a_logits / c_col / warp_h (visualisation; no grad)."""
+    Outputs: g1_all [N,D] (differentiable), a_logits / c_col / warp_h (visualisation; no grad).
+
+    Optional: `sinks` (gradient views for the six parameters, written in place), and
+    `asink = (ArenaGradSink, role)` with `anchor` = the arena tensor when hall / hq are slices of
+    the reader's arena:
+      role "context":  hall = arena hall rows, hq = arena hq rows.  d_hall goes straight into the
+                       sink, d_hq is written (or added, if the question attention got there first)
+                       into its hq rows, and the whole sink is reported as the gradient of `anchor`;
+      role "question": hall = arena hq rows (question attention, model_v2.py:1044).  d_hall is
+                       written into the sink's hq rows; nothing is reported for them here (the
+                       context op, which autograd necessarily runs later, reports the sink)."""
 
     @staticmethod
-    def forward(ctx, cfg, want, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W, WH_b, WC_W, WC_b, sinks=None):
+    def forward(ctx, cfg, want, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W, WH_b, WC_W, WC_b, sinks=None,
+                anchor=None, asink=None):
         fwd = attn_forward(cfg, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W, WH_b, WC_W, WC_b,
                            want_logits=want[0], want_c=want[1], want_warp_h=want[2])
         ctx.fwd = fwd
         ctx.params = (W, b, WH_W, WH_b, WC_W, WC_b)
         ctx.has_lq = lq is not None
         ctx.sinks = sinks       # gradient views for (W, b, WH_W, WH_b, WC_W, WC_b): written in place
+        ctx.asink = asink
         outs = [fwd["g1_all"]]
         for key in ("a_logits", "c_col", "warp_h"):
             t = fwd[key] if fwd[key] is not None else torch.empty(0, device=hall.device)
@@ -316,13 +356,37 @@ class FvtaAttentionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_g1, *_unused):
         W, b, WH_W, WH_b, WC_W, WC_b = ctx.params
-        g = attn_backward(ctx.fwd, d_g1, W, b, WH_W, WH_b, WC_W, WC_b, sinks=ctx.sinks)
+        d_hall_out = d_hq_out = None
+        sink = role = None
+        add_hq = False
+        if ctx.asink is not None:
+            sink, role = ctx.asink
+            if role == "context":
+                d_hall_out = sink.hall()
+                add_hq = sink.hq_written
+                d_hq_out = None if add_hq else sink.hq()
+            else:
+                d_hall_out = sink.hq()
+        g = attn_backward(ctx.fwd, d_g1, W, b, WH_W, WH_b, WC_W, WC_b, sinks=ctx.sinks,
+                          d_hall_out=d_hall_out, d_hq_out=d_hq_out)
         ctx.fwd = None
+        d_hall, d_hq, d_anchor = g["d_hall"], g["d_hq"], None
+        if sink is not None:
+            d_hall = None
+            if role == "context":
+                if add_hq:
+                    sink.hq().add_(d_hq.reshape(sink.hq().shape))
+                d_hq = None
+                d_anchor = sink.buf
+            else:
+                sink.hq_written = True
+        d_lq = g["d_lq"] if ctx.has_lq else None
         if ctx.sinks is not None:
-            return (None, None, g["d_hall"], None, g["d_hq"], None, g["d_lq"] if ctx.has_lq else None,
-                    None, None, None, None, None, None, None)
-        return (None, None, g["d_hall"], None, g["d_hq"], None, g["d_lq"] if ctx.has_lq else None,
-                g["d_att_W"], g["d_att_b"], g["d_WH_W"], g["d_WH_b"], g["d_WC_W"], g["d_WC_b"], None)
+            return (None, None, d_hall, None, d_hq, None, d_lq, None, None, None, None, None, None, None,
+                    d_anchor, None)
+        return (None, None, d_hall, None, d_hq, None, d_lq,
+                g["d_att_W"], g["d_att_b"], g["d_WH_W"], g["d_WH_b"], g["d_WC_W"], g["d_WC_b"], None,
+                d_anchor, None)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -418,7 +482,7 @@ class CharCnnTableFn(torch.autograd.Function):
         ntok, W = ids.shape
         y = torch.empty(ntok, cw, dtype=f32, device=table.device)
         argpos = torch.empty(ntok, cw, dtype=torch.uint8, device=table.device)
-        rc = lib.fvta_charcnn_fwd(ntok, W, VC, cw, H, _ptr(ids), _ptr(table), _ptr(bias), _ptr(y), _ptr(argpos),
+        rc = lib.fvta_charcnn_fwd(ntok, W, VC, cw, H, _ptr(ids), _ptr(table), _ptr(bias), _ptr(y), cw, _ptr(argpos),
                                   _stream())
         check(rc, "fvta_charcnn_fwd")
         ctx.save_for_backward(ids, y, argpos)
@@ -436,10 +500,71 @@ class CharCnnTableFn(torch.autograd.Function):
         d_table = torch.zeros(H, VC, cw, dtype=f32, device=dy.device)
         sink = ctx.bias_sink
         d_bias = sink if sink is not None else torch.zeros(cw, dtype=f32, device=dy.device)
-        rc = lib.fvta_charcnn_bwd(ntok, W, VC, cw, H, _ptr(ids), _ptr(y), _ptr(argpos), _ptr(dy), _ptr(d_table),
-                                  _ptr(d_bias), _stream())
+        rc = lib.fvta_charcnn_bwd(ntok, W, VC, cw, H, _ptr(ids), _ptr(y), cw, _ptr(argpos), _ptr(dy), cw,
+                                  _ptr(d_table), _ptr(d_bias), _stream())
         check(rc, "fvta_charcnn_bwd")
         return d_table, (None if sink is not None else d_bias), None, None
+
+
+class TokenEmbedFn(torch.autograd.Function):
+    """The reader's token features (model_v2.py:524-620) in one [ntok, cw + wd] buffer:
+    columns [0, cw) the char-CNN of the word (table form, see CharCnnTableFn; absent when
+    char_table is None), columns [cw, cw + wd) the word vector (trainable table for ids < VW, the
+    fed GloVe table otherwise, :596).  Two launches forward, two backward, no concat / select
+    plumbing.  sinks = (gradient view of the word table, of the conv bias) or None."""
+
+    @staticmethod
+    def forward(ctx, word_table, glove, ids, char_table, char_bias, ids_c, sinks=None):
+        lib = _lib.load()
+        f32 = torch.float32
+        word_table, glove = _req(word_table, f32, "word table"), _req(glove, f32, "fed word table")
+        ids = _req(ids, torch.int64, "token ids")
+        ntok, wd = ids.shape[0], word_table.shape[1]
+        VW, VF = word_table.shape[0], (glove.shape[0] if glove is not None else 0)
+        cw = char_table.shape[2] if char_table is not None else 0
+        ld = cw + wd
+        out = torch.empty(ntok, ld, dtype=f32, device=word_table.device)
+        argpos = None
+        if char_table is not None:
+            char_table, char_bias = _req(char_table, f32, "char table"), _req(char_bias, f32, "conv bias")
+            ids_c = _req(ids_c, torch.int32, "char ids")
+            H, VC, _ = char_table.shape
+            W = ids_c.shape[1]
+            argpos = torch.empty(ntok, cw, dtype=torch.uint8, device=out.device)
+            rc = lib.fvta_charcnn_fwd(ntok, W, VC, cw, H, _ptr(ids_c), _ptr(char_table), _ptr(char_bias), _ptr(out),
+                                      ld, _ptr(argpos), _stream())
+            check(rc, "fvta_charcnn_fwd")
+            ctx.cshape = (H, VC, cw, W)
+        rc = lib.fvta_embed_rows(ntok, wd, VW, VF, _ptr(ids), _ptr(word_table), _ptr(glove),
+                                 ctypes.c_void_p(out.data_ptr() + 4 * cw), ld, _stream())
+        check(rc, "fvta_embed_rows")
+        ctx.save_for_backward(ids, ids_c if char_table is not None else None, out, argpos)
+        ctx.dims = (ntok, wd, VW, cw, ld)
+        ctx.sinks = sinks
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        f32 = torch.float32
+        ids, ids_c, out, argpos = ctx.saved_tensors
+        ntok, wd, VW, cw, ld = ctx.dims
+        dy = _req(dy, f32, "dy")
+        g_word, g_bias = ctx.sinks if ctx.sinks is not None else (None, None)
+        d_table = d_bias = None
+        if cw:
+            H, VC, _, W = ctx.cshape
+            d_table = torch.zeros(H, VC, cw, dtype=f32, device=dy.device)
+            d_bias = g_bias if g_bias is not None else torch.zeros(cw, dtype=f32, device=dy.device)
+            rc = lib.fvta_charcnn_bwd(ntok, W, VC, cw, H, _ptr(ids_c), _ptr(out), ld, _ptr(argpos), _ptr(dy), ld,
+                                      _ptr(d_table), _ptr(d_bias), _stream())
+            check(rc, "fvta_charcnn_bwd")
+        d_word = g_word if g_word is not None else torch.zeros(VW, wd, dtype=f32, device=dy.device)
+        rc = lib.fvta_embed_rows_bwd(ntok, wd, VW, _ptr(ids), ctypes.c_void_p(dy.data_ptr() + 4 * cw), ld,
+                                     _ptr(d_word), _stream())
+        check(rc, "fvta_embed_rows_bwd")
+        return (None if g_word is not None else d_word, None, None, d_table,
+                None if (g_bias is not None or not cw) else d_bias, None, None)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -492,8 +617,13 @@ class OutputLossFn(torch.autograd.Function):
         yp = torch.empty(N, C, dtype=f32, device=dev)
         loss = torch.zeros((), dtype=f32, device=dev)
         want = bool(want_grad) and y is not None   # grad mode is always off inside Function.forward
+        gbuf = None
         if want:
-            d_gq, d_g1, d_gc = torch.empty_like(gq), torch.empty_like(g1), torch.empty_like(gc)
+            # one buffer so that the backward scales all three with a single launch
+            seg = (N * D + 3) // 4 * 4          # keep every segment 16-byte aligned
+            gbuf = torch.empty(2 * seg + N * C * D, dtype=f32, device=dev)
+            d_gq, d_g1 = gbuf[:N * D].view(N, D), gbuf[seg:seg + N * D].view(N, D)
+            d_gc = gbuf[2 * seg:].view(N, C, D)
             dW, db = sinks if sinks is not None else (torch.zeros_like(W), torch.zeros_like(b))
         else:
             d_gq = d_g1 = d_gc = dW = db = None
@@ -501,15 +631,18 @@ class OutputLossFn(torch.autograd.Function):
                                   _ptr(yp), _ptr(loss), _ptr(d_gq), _ptr(d_g1), _ptr(d_gc), _ptr(dW), _ptr(db),
                                   _stream())
         check(rc, "fvta_output_loss")
-        ctx.grads = (d_gq, d_g1, d_gc, None if sinks is not None else dW, None if sinks is not None else db)
+        ctx.grads = (gbuf, (N, C, D), None if sinks is not None else dW, None if sinks is not None else db)
         ctx.mark_non_differentiable(logits, yp)
         return loss, logits, yp
 
     @staticmethod
     def backward(ctx, dloss, _dlogits, _dyp):
-        d_gq, d_g1, d_gc, dW, db = ctx.grads
-        if d_gq is None:
+        gbuf, (N, C, D), dW, db = ctx.grads
+        if gbuf is None:
             raise _lib.FvtaError("fvta_output_loss was run without gradients")
         # upstream is 1 for loss.backward(); honour anything else
         sc = lambda t: None if t is None else t * dloss   # noqa: E731
-        return sc(d_gq), sc(d_g1), sc(d_gc), sc(dW), sc(db), None, None, None
+        g = gbuf * dloss
+        seg = (N * D + 3) // 4 * 4
+        return (g[:N * D].view(N, D), g[seg:seg + N * D].view(N, D), g[2 * seg:].view(N, C, D), sc(dW), sc(db),
+                None, None, None)

@@ -212,12 +212,35 @@ int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int3
  *   y[w,:] = relu( max_p ( bias + sum_h table[h][ids[w,p+h]][:] ) ),  p in [0, W-height].
  * argpos [ntok,cw] u8 records the arg-max position for the backward, which accumulates
  * d_table / d_bias (+=, caller zeroes them).  cw % 4 == 0, cw <= 128, W <= 64.
+ * y and dy are addressed with row strides ldy / lddy (floats; ldy % 4 == 0, y 16-byte aligned) so
+ * the features can live inside the [char | word] token matrix of model_v2.py:617.
  * ---------------------------------------------------------------------------------------- */
 int fvta_charcnn_fwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t height, const int32_t* ids,
-                     const float* table, const float* bias, float* y, uint8_t* argpos, void* stream);
-int fvta_charcnn_bwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t height, const int32_t* ids,
-                     const float* y, const uint8_t* argpos, const float* dy, float* d_table, float* d_bias,
+                     const float* table, const float* bias, float* y, int32_t ldy, uint8_t* argpos,
                      void* stream);
+int fvta_charcnn_bwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t height, const int32_t* ids,
+                     const float* y, int32_t ldy, const uint8_t* argpos, const float* dy, int32_t lddy,
+                     float* d_table, float* d_bias, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Word vectors of the packed tokens (replaces the tf.concat of the trainable and the fed
+ * embedding table + tf.nn.embedding_lookup, model_v2.py:590-600):
+ *   out[i, 0:dim] = ids[i] < VW ? table_new[ids[i]] : table_fixed[ids[i] - VW]   (row stride ld_out)
+ * and its backward, d_table_new[ids[i]] += dy[i, 0:dim] for ids[i] < VW (caller zeroes; the fed
+ * table is not trained).  Ids are clamped into [0, VW + VF).
+ * ---------------------------------------------------------------------------------------- */
+int fvta_embed_rows(int32_t ntok, int32_t dim, int32_t VW, int32_t VF, const int64_t* ids,
+                    const float* table_new, const float* table_fixed, float* out, int32_t ld_out, void* stream);
+int fvta_embed_rows_bwd(int32_t ntok, int32_t dim, int32_t VW, const int64_t* ids, const float* dy,
+                        int32_t ld_dy, float* d_table_new, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Bias / activation part of the backward of `linear` (model_v2.py:75-100):
+ *   dz[M,N] = dy * act'(y)   (act 1: tanh, y = tanh output; 2: relu; 0: dz is not written, dz == dy)
+ *   db[N]  += column sums of dz   (nullable)
+ * ---------------------------------------------------------------------------------------- */
+int fvta_bias_act_grad(int32_t M, int32_t N, const float* dy, int32_t ld_dy, const float* y, int32_t ld_y,
+                       int32_t act, float* dz, int32_t ld_dz, float* db, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Output layer + softmax + mean cross-entropy, forward and backward in ONE launch (replaces

@@ -115,3 +115,85 @@ def test_charcnn_table_parity(cuda_device, shape):
     for name, a, r, r32 in zip(("y", "d_emb", "d_filter", "d_bias"), (y, e.grad, f.grad, b.grad), ref, ref32):
         tol = max(TOL, 3 * rel_err(r32, r))
         assert rel_err(a, r) < tol, (name, rel_err(a, r))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_char,sink", [(True, False), (True, True), (False, False)])
+def test_token_embed_parity(cuda_device, use_char, sink):
+    """TokenEmbedFn (fvta_embed_rows + fvta_charcnn_* into one [char | word] buffer) vs the
+    reference formulation: concat(trainable table, fed table) lookup (model_v2.py:590-600) next to
+    the conv1d features (:617), outputs and every gradient."""
+    dev = cuda_device
+    ntok, W, VC, cdim, cw, VW, VF, wd = 77, 9, 30, 8, 12, 5, 40, 16
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, VW + VF, (ntok,), generator=g)
+    ids[:6] = torch.tensor([0, VW - 1, VW, VW + VF - 1, 1, 1])
+    ids_c = torch.randint(0, VC, (ntok, W), generator=g)
+    new = torch.randn(VW, wd, generator=g)
+    fixed = torch.randn(VF, wd, generator=g)
+    emb = torch.randn(VC, cdim, generator=g) * 0.5
+    filt = torch.randn(1, 5, cdim, cw, generator=g) * 0.1
+    bias = torch.randn(cw, generator=g) * 0.1
+    dy = torch.randn(ntok, (cw if use_char else 0) + wd, generator=g)
+
+    def oracle(dtype):
+        n_ = new.to(dtype).clone().requires_grad_(True)
+        e = emb.to(dtype).clone().requires_grad_(True)
+        f = filt.to(dtype).clone().requires_grad_(True)
+        b = bias.to(dtype).clone().requires_grad_(True)
+        A = torch.cat([n_, fixed.to(dtype)], 0)[ids]
+        if use_char:
+            xc = tf_ops.conv1d(e[ids_c].unsqueeze(0), f, b)[0]
+            A = torch.cat([xc, A], -1)
+        (A * dy.to(dtype)).sum().backward()
+        return (A, n_.grad) + ((e.grad, f.grad, b.grad) if use_char else ())
+
+    ref, ref32 = oracle(torch.float64), oracle(torch.float32)
+    n_ = new.to(dev).requires_grad_(True)
+    e = emb.to(dev).requires_grad_(True)
+    f = filt.to(dev).requires_grad_(True)
+    b = bias.to(dev).requires_grad_(True)
+    g_new = torch.zeros(VW, wd, device=dev)
+    g_bias = torch.zeros(cw, device=dev)
+    table = torch.matmul(e.unsqueeze(0), f[0]) if use_char else None
+    out = ops.TokenEmbedFn.apply(n_, fixed.to(dev), ids.to(dev), table, b if use_char else None,
+                                 ids_c.to(torch.int32).to(dev) if use_char else None,
+                                 (g_new, g_bias if use_char else None) if sink else None)
+    (out * dy.to(dev)).sum().backward()
+    got = (out, g_new if sink else n_.grad) + ((e.grad, f.grad, g_bias if sink else b.grad) if use_char else ())
+    if sink:
+        assert n_.grad is None and b.grad is None
+    for name, a, r, r32 in zip(("out", "d_new", "d_emb", "d_filter", "d_bias"), got, ref, ref32):
+        tol = max(TOL, 3 * rel_err(r32, r))
+        assert rel_err(a, r) < tol, (name, rel_err(a, r))
+    # the word-vector columns are copies: bit-exact
+    assert torch.equal(out[:, (cw if use_char else 0):].cpu(), torch.cat([new, fixed], 0)[ids])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("add_tanh,sink,need_dx", [(True, True, False), (True, False, True), (False, True, True)])
+def test_linear_backward_parity(cuda_device, add_tanh, sink, need_dx):
+    """LinearFn (fvta_gemm + fvta_bias_act_grad) vs torch: y, dx, dW, db (model_v2.py:75-100)."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(11)
+    M, K, N = 203, 37, 52
+    x, W, b, dy = (torch.randn(*s, generator=g) for s in ((M, K), (K, N), (N,), (M, N)))
+    W = W * 0.2
+
+    def oracle(dtype):
+        x_, W_, b_ = (t.to(dtype).clone().requires_grad_(True) for t in (x, W, b))
+        y = x_ @ W_ + b_
+        y = torch.tanh(y) if add_tanh else y
+        (y * dy.to(dtype)).sum().backward()
+        return y, x_.grad, W_.grad, b_.grad
+
+    ref, ref32 = oracle(torch.float64), oracle(torch.float32)
+    x_ = x.to(dev).requires_grad_(need_dx)
+    W_, b_ = W.to(dev).requires_grad_(True), b.to(dev).requires_grad_(True)
+    gW, gb = torch.zeros(K, N, device=dev), torch.zeros(N, device=dev)
+    y = ops.linear(x_, W_, b_, add_tanh, *((gW, gb) if sink else (None, None)))
+    (y * dy.to(dev)).sum().backward()
+    got = (y, x_.grad if need_dx else ref[1], gW if sink else W_.grad, gb if sink else b_.grad)
+    for name, a, r, r32 in zip(("y", "dx", "dW", "db"), got, ref, ref32):
+        tol = max(TOL, 3 * rel_err(r32, r))
+        assert rel_err(a.cpu().double(), r) < tol, (name, rel_err(a.cpu().double(), r))
