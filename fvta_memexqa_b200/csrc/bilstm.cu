@@ -343,6 +343,118 @@ __global__ void bilstm_rec_bwd(FvtaLstmDesc L, SeqAddr A, const int32_t* __restr
   }
 }
 
+// BPTT for kSG * d <= blockDim.x (every thread owns ONE (unit e, sequence s) item, s fastest):
+//   * the item's cell-state gradient lives in a register for the whole sequence;
+//   * the saved gates / cell states / incoming d out of the NEXT step to process are fetched while
+//     the d h_prev product of the current one runs (global latency off the per-step critical path);
+//   * d gates go to shared memory transposed, dgT[g][kSG] (conflict-free with this item order), the
+//     d h_prev product reads them as broadcast float4s against one W_h element per g (packed
+//     fp32x2 FMAs) and leaves per-gate-block partials part[q][e][kSG] that the next step's item
+//     threads add up -- two barriers per step.
+// Shared memory: W_h [d][4d+1] | dgT [4d][kSG] | part [4][d][kSG].
+template <int BT>
+__global__ void __launch_bounds__(BT, BT <= 256 ? 4 : (BT <= 416 ? 3 : 1))
+bilstm_rec_bwd_item(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
+                                    const float* __restrict__ wh_fw, const float* __restrict__ wh_bw,
+                                    const float* __restrict__ reserve, const float* __restrict__ d_out,
+                                    const float* __restrict__ d_last, float* __restrict__ dgates) {
+  static_assert(kSG == 8, "item layout below assumes 8 sequences per CTA");
+  extern __shared__ __align__(16) float sm[];
+  const int d = L.d, G = 4 * d;
+  const int wsd = G + 1;
+  const int dir = blockIdx.y;
+  const float* wh_g = dir == 0 ? wh_fw : wh_bw;
+  float* w_s = sm;                                              // [d][4d+1]
+  float* dgT = sm + round_up_sz((size_t)d * wsd, 4);            // [4d][kSG]
+  float* part_s = dgT + (size_t)G * kSG;                        // [4][d][kSG]
+  __shared__ int len_s[kSG];
+  const int b0 = blockIdx.x * kSG;
+  for (int i = threadIdx.x; i < d * G; i += blockDim.x) w_s[(i / G) * wsd + (i % G)] = wh_g[i];
+  for (int i = threadIdx.x; i < 4 * d * kSG; i += blockDim.x) part_s[i] = 0.f;
+  if (threadIdx.x < kSG) {
+    const int b = b0 + threadIdx.x;
+    len_s[threadIdx.x] = (b < L.B) ? min(lens[b], L.J) : 0;
+  }
+  __syncthreads();
+  int maxlen = 0;
+#pragma unroll
+  for (int q = 0; q < kSG; ++q) maxlen = max(maxlen, len_s[q]);
+
+  // ---- item state ----
+  const bool item = threadIdx.x < kSG * d;
+  const int e = threadIdx.x / kSG, s = threadIdx.x % kSG;
+  const int b = b0 + s;
+  const int len = item ? len_s[s] : 0;
+  const int tok0 = (item && b < L.B) ? A.tok0(b, L.J) : 0;
+  const long long orow = (item && b < L.B) ? A.out0(b, L.J) : -1;
+  const float* res = reserve + ((size_t)dir * A.ntok + tok0) * kResW * d + e;   // + t * kResW * d + slot * d
+  const float* dout_p = (d_out && orow >= 0) ? d_out + (size_t)orow * 2 * d + dir * d + e : nullptr;
+  float* dgd = dgates + ((size_t)dir * A.ntok + tok0) * G + e;
+  float dc = 0.f;
+  float ig = 0.f, jg = 0.f, fg = 0.f, og = 0.f, cc = 0.f, cp = 0.f, dout = 0.f;
+  auto fetch = [&](int st) {   // saved values of recurrence step st (0 <= st < len)
+    const int t = dir == 0 ? st : len - 1 - st;
+    const float* r = res + (size_t)t * kResW * d;
+    ig = r[0]; jg = r[d]; fg = r[2 * d]; og = r[3 * d]; cc = r[4 * d];
+    cp = 0.f;
+    if (st > 0) cp = res[(size_t)(dir == 0 ? t - 1 : t + 1) * kResW * d + 4 * d];
+    dout = dout_p ? dout_p[(size_t)t * 2 * d] : 0.f;
+    if (d_last && st == len - 1) dout += d_last[(size_t)b * 2 * d + dir * d + e];
+  };
+  if (item && maxlen - 1 < len) fetch(maxlen - 1);
+
+  // ---- d h_prev product mapping: thread (quarter, e) ----
+  const int nq = (int)blockDim.x >= 4 * d ? 4 : ((int)blockDim.x >= 2 * d ? 2 : 1);
+  const bool prod = threadIdx.x < nq * d;
+  const int pq = threadIdx.x / d, pe = threadIdx.x - pq * d;
+  const int g0 = pq * (G / nq), g1 = g0 + G / nq;
+  const float* wr = w_s + (size_t)pe * wsd;
+
+  for (int step = maxlen - 1; step >= 0; --step) {
+    if (item) {
+      float dgi = 0.f, dgj = 0.f, dgf = 0.f, dgo = 0.f;
+      if (step < len) {
+        float dh = dout;
+        for (int q = 0; q < nq; ++q) dh += part_s[((size_t)q * d + e) * kSG + s];
+        const float tc = tanh_fast(cc);
+        const float dcv = fmaf(dh * og, 1.f - tc * tc, dc);
+        dgo = dh * tc * og * (1.f - og);
+        dgi = dcv * jg * ig * (1.f - ig);
+        dgj = dcv * ig * (1.f - jg * jg);
+        dgf = dcv * cp * fg * (1.f - fg);
+        dc = dcv * fg;
+        const int t = dir == 0 ? step : len - 1 - step;
+        float* o = dgd + (size_t)t * G;
+        o[0] = dgi; o[d] = dgj; o[2 * d] = dgf; o[3 * d] = dgo;
+      }
+      dgT[(size_t)e * kSG + s] = dgi;
+      dgT[(size_t)(d + e) * kSG + s] = dgj;
+      dgT[(size_t)(2 * d + e) * kSG + s] = dgf;
+      dgT[(size_t)(3 * d + e) * kSG + s] = dgo;
+      if (step >= 1 && step - 1 < len) fetch(step - 1);   // lands while the product below runs
+    }
+    __syncthreads();
+    if (prod) {
+      float2 a01 = make_float2(0.f, 0.f), a23 = a01, a45 = a01, a67 = a01;
+#pragma unroll 4
+      for (int g = g0; g < g1; ++g) {
+        const float w = wr[g];
+        const float2 w2 = make_float2(w, w);
+        const float4 x0 = *reinterpret_cast<const float4*>(dgT + (size_t)g * kSG);
+        const float4 x1 = *reinterpret_cast<const float4*>(dgT + (size_t)g * kSG + 4);
+        a01 = __ffma2_rn(w2, make_float2(x0.x, x0.y), a01);
+        a23 = __ffma2_rn(w2, make_float2(x0.z, x0.w), a23);
+        a45 = __ffma2_rn(w2, make_float2(x1.x, x1.y), a45);
+        a67 = __ffma2_rn(w2, make_float2(x1.z, x1.w), a67);
+      }
+      float4* dst = reinterpret_cast<float4*>(part_s + ((size_t)pq * d + pe) * kSG);
+      dst[0] = make_float4(a01.x, a01.y, a23.x, a23.y);
+      dst[1] = make_float4(a45.x, a45.y, a67.x, a67.y);
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void add_inplace4(size_t n4, float4* __restrict__ a, const float4* __restrict__ b) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) {
@@ -433,13 +545,25 @@ static int lstm_bwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x
   cudaError_t e = cudaMemsetAsync(dg, 0, (size_t)2 * NT * G * sizeof(float), st);
   if (e != cudaSuccess) { set_last_error("bilstm bwd memset", e); return FVTA_E_LAUNCH; }
   const LstmSmemPlan plan = lstm_smem_plan(L.d);
-  e = cudaFuncSetAttribute(bilstm_rec_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.bytes);
-  if (e != cudaSuccess) { set_last_error("bilstm_rec_bwd smem attr", e); return FVTA_E_LAUNCH; }
-  int threads = round_up((kSG * L.d) < 1024 ? (kSG * L.d) : 1024, 32);
   dim3 grid((L.B + kSG - 1) / kSG, 2);
-  bilstm_rec_bwd<<<grid, threads, plan.bytes, st>>>(L, A, lens, kernel_fw + (size_t)L.In * G,
-                                                   kernel_bw + (size_t)L.In * G, reserve, d_out, d_last, dg);
-  int rc = check_launch("bilstm_rec_bwd");
+  int rc;
+  const size_t item_smem = (round_up_sz((size_t)L.d * (G + 1), 4) + (size_t)2 * G * kSG) * sizeof(float);
+  if (kSG * L.d <= 1024 && item_smem <= 200 * 1024) {
+    const int threads = round_up(kSG * L.d, 32);
+    auto kern = threads <= 256 ? bilstm_rec_bwd_item<256> : (threads <= 416 ? bilstm_rec_bwd_item<416> : bilstm_rec_bwd_item<1024>);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)item_smem);
+    if (e != cudaSuccess) { set_last_error("bilstm_rec_bwd_item smem attr", e); return FVTA_E_LAUNCH; }
+    kern<<<grid, threads, item_smem, st>>>(L, A, lens, kernel_fw + (size_t)L.In * G, kernel_bw + (size_t)L.In * G,
+                                           reserve, d_out, d_last, dg);
+    rc = check_launch("bilstm_rec_bwd_item");
+  } else {
+    e = cudaFuncSetAttribute(bilstm_rec_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.bytes);
+    if (e != cudaSuccess) { set_last_error("bilstm_rec_bwd smem attr", e); return FVTA_E_LAUNCH; }
+    int threads = round_up((kSG * L.d) < 1024 ? (kSG * L.d) : 1024, 32);
+    bilstm_rec_bwd<<<grid, threads, plan.bytes, st>>>(L, A, lens, kernel_fw + (size_t)L.In * G,
+                                                     kernel_bw + (size_t)L.In * G, reserve, d_out, d_last, dg);
+    rc = check_launch("bilstm_rec_bwd");
+  }
   if (rc) return rc;
   const float* dgs[2] = {dg, dg + (size_t)NT * G};
   const float* ress[2] = {reserve, reserve + (size_t)NT * kResW * L.d};

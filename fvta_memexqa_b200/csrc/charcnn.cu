@@ -2,8 +2,9 @@
 // embedded characters, + bias, ReLU, max over positions) for the undropped case.
 //
 // The conv output at a position depends only on the `height` character IDS in its window:
-//   out[w,p,:] = bias + sum_h  char_emb[id[w,p+h]] @ filter[h]      = bias + sum_h table[h][id[w,p+h]][:]
-// with table[h] = char_emb @ filter[h]  ([VC,cdim] x [cdim,cw], a few MFLOP, done by the caller).
+//   out[w,p,:] = bias + sum_h  char_emb[id[w,p+h]] @ filter[h]      = bias + sum_h table[id[w,p+h]][h][:]
+// with table[:, h, :] = char_emb @ filter[h]  ([VC,cdim] x [cdim,cw], a few MFLOP, done by the caller
+// as ONE product char_emb @ [filter[0] | ... | filter[height-1]], hence the [VC, height, cw] layout).
 // So instead of a [words*positions, height*cdim] x [height*cdim, cw] GEMM (4 GFLOP per step at
 // the reference shape, the largest FLOP term of the whole model) the layer is a gather-add over
 // an L2-resident table: 5 loads per output.  Same function; only the fp32 summation order
@@ -41,7 +42,7 @@ __global__ void charcnn_fwd_kernel(int ntok, int W, int VC, int cw, int height, 
     for (int p = 0; p < npos; ++p) {
       float4 a = b4;
       for (int h = 0; h < height; ++h) {
-        const float4 t = *reinterpret_cast<const float4*>(table + ((size_t)h * VC + id_s[wl][p + h]) * cw + o4 * 4);
+        const float4 t = *reinterpret_cast<const float4*>(table + ((size_t)id_s[wl][p + h] * height + h) * cw + o4 * 4);
         a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
       }
       if (a.x > best.x) { best.x = a.x; bp0 = p; }
@@ -76,7 +77,7 @@ __global__ void charcnn_bwd_kernel(int ntok, int W, int VC, int cw, int height, 
     if (w < ntok && y[(size_t)w * ldy + o] > 0.f) {   // ReLU alive
       g = dy[(size_t)w * lddy + o];
       const int p = argpos[(size_t)w * cw + o];
-      for (int h = 0; h < height; ++h) atomicAdd(d_table + ((size_t)h * VC + id_s[wl][p + h]) * cw + o, g);
+      for (int h = 0; h < height; ++h) atomicAdd(d_table + ((size_t)id_s[wl][p + h] * height + h) * cw + o, g);
     }
     if (o < 128) db_s[wl][o] = g;
   }

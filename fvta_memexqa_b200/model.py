@@ -286,7 +286,9 @@ class Model:
             # a window's conv output depends only on its `height` char ids: tabulate
             # char_emb @ filter[h] once ([height,VC,cw], a few MFLOP) and gather-add (csrc/charcnn.cu);
             # the word vectors land next to it in the same buffer (csrc/embed.cu)
-            ctab = torch.matmul(v["emb/var/char_emb"].unsqueeze(0), filt[0]) if cfg.use_char else None
+            ctab = ops.CharTableFn.apply(v["emb/var/char_emb"], filt,
+                                         self._sink("emb/var/char_emb", "emb/conv/conv1d/filter")) \
+                if cfg.use_char else None
             return ops.TokenEmbedFn.apply(table, glove, ids, ctab, v["emb/conv/conv1d/bias"] if cfg.use_char else None,
                                           ids_c if cfg.use_char else None,
                                           self._sink("emb/word/var/word_emb_mat", "emb/conv/conv1d/bias"))
@@ -417,6 +419,17 @@ class Model:
         cfg = self.config
         losses = -(y.to(logits.dtype) * torch.log_softmax(logits, dim=-1)).sum(-1)
         return losses.mean() + self._wd_loss()
+
+    def release_graph(self):
+        """Drop every reference to the autograd graph of the last forward (call after backward).
+        Besides freeing the saved activations early this lets the leaves' AccumulateGrad nodes die
+        with the graph, so the next forward -- possibly under CUDA-graph capture, on another stream
+        -- creates fresh ones on ITS stream instead of inheriting nodes bound to a stale stream
+        (autograd would otherwise order the capture against that uncaptured stream and fail)."""
+        for name in ("loss", "g1_all", "gq"):
+            t = getattr(self, name, None)
+            if isinstance(t, torch.Tensor) and t.grad_fn is not None:
+                setattr(self, name, t.detach())
 
     def _ones_mask(self, N, device):
         """[N,1] all-true mask of the question attention's single 'question word' (cached)."""

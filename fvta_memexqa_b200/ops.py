@@ -427,6 +427,7 @@ class ReaderFn(torch.autograd.Function):
         ctx.save_for_backward(x_text, x_img, t_off, t_len, t_out, i_off, i_len, i_out, kt, ki, res_t, res_i)
         ctx.descs = (desc_t, desc_i)
         ctx.sinks = sinks       # (g kernel_t, g bias_t, g kernel_i, g bias_i) views of the flat gradient
+        ctx.set_materialize_grads(False)   # unused final states arrive as None, not as zero tensors
         return arena, last_t, last_i
 
     @staticmethod
@@ -467,9 +468,9 @@ class ReaderFn(torch.autograd.Function):
 # character CNN through the per-character table
 # ---------------------------------------------------------------------------------------------
 class CharCnnTableFn(torch.autograd.Function):
-    """y[w,:] = relu(max_p(bias + sum_h table[h][ids[w,p+h]]))  (fvta_charcnn_fwd/bwd).
-    table [height,VC,cw] = char_emb @ filter[h] is produced by the caller with ordinary (tiny)
-    matrix products, so autograd carries d table back to char_emb and the filter."""
+    """y[w,:] = relu(max_p(bias + sum_h table[ids[w,p+h]][h]))  (fvta_charcnn_fwd/bwd).
+    table [VC,height,cw] = char_emb @ filter[h] comes from CharTableFn (one small product), which
+    carries d table back to char_emb and the filter."""
 
     @staticmethod
     def forward(ctx, table, bias, ids, bias_sink=None):
@@ -478,7 +479,7 @@ class CharCnnTableFn(torch.autograd.Function):
         f32 = torch.float32
         table, bias = _req(table, f32, "table"), _req(bias, f32, "bias")
         ids = _req(ids, torch.int32, "char ids")
-        H, VC, cw = table.shape
+        VC, H, cw = table.shape
         ntok, W = ids.shape
         y = torch.empty(ntok, cw, dtype=f32, device=table.device)
         argpos = torch.empty(ntok, cw, dtype=torch.uint8, device=table.device)
@@ -497,13 +498,48 @@ class CharCnnTableFn(torch.autograd.Function):
         ids, y, argpos = ctx.saved_tensors
         H, VC, cw, ntok, W = ctx.shape
         dy = _req(dy, f32, "dy")
-        d_table = torch.zeros(H, VC, cw, dtype=f32, device=dy.device)
+        d_table = torch.zeros(VC, H, cw, dtype=f32, device=dy.device)
         sink = ctx.bias_sink
         d_bias = sink if sink is not None else torch.zeros(cw, dtype=f32, device=dy.device)
         rc = lib.fvta_charcnn_bwd(ntok, W, VC, cw, H, _ptr(ids), _ptr(y), cw, _ptr(argpos), _ptr(dy), cw,
                                   _ptr(d_table), _ptr(d_bias), _stream())
         check(rc, "fvta_charcnn_bwd")
         return d_table, (None if sink is not None else d_bias), None, None
+
+
+class CharTableFn(torch.autograd.Function):
+    """table[v,h,:] = char_emb[v,:] @ filter[0,h]  ([VC,height,cw]) as ONE product
+    char_emb @ F with F[c, h*cw + o] = filter[0,h,c,o]; the backward is two products and, with
+    sinks = (gradient view of char_emb, of the filter), no autograd plumbing."""
+
+    @staticmethod
+    def forward(ctx, char_emb, filt, sinks=None):
+        f32 = torch.float32
+        char_emb, filt = _req(char_emb, f32, "char_emb"), _req(filt, f32, "conv filter")
+        _, H, cdim, cw = filt.shape
+        F = filt[0].permute(1, 0, 2).reshape(cdim, H * cw).contiguous()
+        T2 = gemm(char_emb, F)
+        ctx.save_for_backward(char_emb, F)
+        ctx.dims = (H, cdim, cw)
+        ctx.sinks = sinks
+        return T2.view(char_emb.shape[0], H, cw)
+
+    @staticmethod
+    def backward(ctx, dT):
+        char_emb, F = ctx.saved_tensors
+        H, cdim, cw = ctx.dims
+        dT2 = _req(dT, torch.float32, "d table").reshape(char_emb.shape[0], H * cw)
+        g_emb, g_filt = ctx.sinks if ctx.sinks is not None else (None, None)
+        if g_emb is not None:
+            gemm(dT2, F, trans_b=True, out=g_emb, accumulate=True)
+            d_emb = None
+        else:
+            d_emb = gemm(dT2, F, trans_b=True)
+        d_filt = gemm(char_emb, dT2, trans_a=True).view(cdim, H, cw).permute(1, 0, 2).unsqueeze(0)
+        if g_filt is not None:
+            g_filt.add_(d_filt)
+            d_filt = None
+        return d_emb, d_filt, None
 
 
 class TokenEmbedFn(torch.autograd.Function):
@@ -528,7 +564,7 @@ class TokenEmbedFn(torch.autograd.Function):
         if char_table is not None:
             char_table, char_bias = _req(char_table, f32, "char table"), _req(char_bias, f32, "conv bias")
             ids_c = _req(ids_c, torch.int32, "char ids")
-            H, VC, _ = char_table.shape
+            VC, H, _ = char_table.shape
             W = ids_c.shape[1]
             argpos = torch.empty(ntok, cw, dtype=torch.uint8, device=out.device)
             rc = lib.fvta_charcnn_fwd(ntok, W, VC, cw, H, _ptr(ids_c), _ptr(char_table), _ptr(char_bias), _ptr(out),
@@ -554,7 +590,7 @@ class TokenEmbedFn(torch.autograd.Function):
         d_table = d_bias = None
         if cw:
             H, VC, _, W = ctx.cshape
-            d_table = torch.zeros(H, VC, cw, dtype=f32, device=dy.device)
+            d_table = torch.zeros(VC, H, cw, dtype=f32, device=dy.device)
             d_bias = g_bias if g_bias is not None else torch.zeros(cw, dtype=f32, device=dy.device)
             rc = lib.fvta_charcnn_bwd(ntok, W, VC, cw, H, _ptr(ids_c), _ptr(out), ld, _ptr(argpos), _ptr(dy), ld,
                                       _ptr(d_table), _ptr(d_bias), _stream())

@@ -31,6 +31,8 @@ class Trainer:
         ps.grad_flat.zero_()
         loss, _, _ = m.forward(dfeed, is_train=True)
         loss.backward()
+        loss = loss.detach()
+        m.release_graph()
         scale = 1.0
         if self.dp is not None:
             scale = self.dp.all_reduce_grads(ps.grad_flat)

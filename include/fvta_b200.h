@@ -208,8 +208,8 @@ int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int3
 /* ------------------------------------------------------------------------------------------
  * Character CNN (replaces conv1d, model_v2.py:52-70, when its input dropout is off): the conv
  * output of a window depends only on its `height` character ids, so with
- * table[h] = char_emb @ filter[h] (caller, [height,VC,cw]) the layer is
- *   y[w,:] = relu( max_p ( bias + sum_h table[h][ids[w,p+h]][:] ) ),  p in [0, W-height].
+ * table[:,h,:] = char_emb @ filter[h] (caller, [VC,height,cw]) the layer is
+ *   y[w,:] = relu( max_p ( bias + sum_h table[ids[w,p+h]][h][:] ) ),  p in [0, W-height].
  * argpos [ntok,cw] u8 records the arg-max position for the backward, which accumulates
  * d_table / d_bias (+=, caller zeroes them).  cw % 4 == 0, cw <= 128, W <= 64.
  * y and dy are addressed with row strides ldy / lddy (floats; ldy % 4 == 0, y 16-byte aligned) so

@@ -109,7 +109,7 @@ def test_charcnn_table_parity(cuda_device, shape):
     e = emb.to(dev).requires_grad_(True)
     f = filt.to(dev).requires_grad_(True)
     b = bias.to(dev).requires_grad_(True)
-    table = torch.matmul(e.unsqueeze(0), f[0])
+    table = ops.CharTableFn.apply(e, f)
     y = ops.CharCnnTableFn.apply(table, b, ids.to(torch.int32).to(dev))
     (y * dy.to(dev)).sum().backward()
     for name, a, r, r32 in zip(("y", "d_emb", "d_filter", "d_bias"), (y, e.grad, f.grad, b.grad), ref, ref32):
@@ -155,14 +155,16 @@ def test_token_embed_parity(cuda_device, use_char, sink):
     b = bias.to(dev).requires_grad_(True)
     g_new = torch.zeros(VW, wd, device=dev)
     g_bias = torch.zeros(cw, device=dev)
-    table = torch.matmul(e.unsqueeze(0), f[0]) if use_char else None
+    g_emb, g_filt = torch.zeros_like(e), torch.zeros_like(f)
+    table = ops.CharTableFn.apply(e, f, (g_emb, g_filt) if sink else None) if use_char else None
     out = ops.TokenEmbedFn.apply(n_, fixed.to(dev), ids.to(dev), table, b if use_char else None,
                                  ids_c.to(torch.int32).to(dev) if use_char else None,
                                  (g_new, g_bias if use_char else None) if sink else None)
     (out * dy.to(dev)).sum().backward()
-    got = (out, g_new if sink else n_.grad) + ((e.grad, f.grad, g_bias if sink else b.grad) if use_char else ())
+    got = (out, g_new if sink else n_.grad) + \
+        ((g_emb if sink else e.grad, g_filt if sink else f.grad, g_bias if sink else b.grad) if use_char else ())
     if sink:
-        assert n_.grad is None and b.grad is None
+        assert n_.grad is None and b.grad is None and e.grad is None and f.grad is None
     for name, a, r, r32 in zip(("out", "d_new", "d_emb", "d_filter", "d_bias"), got, ref, ref32):
         tol = max(TOL, 3 * rel_err(r32, r))
         assert rel_err(a, r) < tol, (name, rel_err(a, r))
