@@ -13,6 +13,7 @@
 // Backward = the mirrored recurrent kernel (BPTT) producing d gates, then GEMMs for d_x and
 // the weight gradients.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace fvta {
 
@@ -149,6 +150,139 @@ __global__ void __launch_bounds__(256) bilstm_rec_fwd_reg(FvtaLstmDesc L, SeqAdd
     if (b0 + s < L.B) last[(size_t)(b0 + s) * 2 * d + dir * d + e] = h_s[e][s];
   }
 }
+
+// Forward recurrence, two threads per gate column (d <= 64): thread (g, half) keeps HALF of column
+// g of W_h in registers and forms the partial gate pre-activation of the kSG sequences over its
+// half of the hidden units; the cell update then runs one (unit, sequence) item per thread (the
+// cell state never leaves its register) and sums the two partials.  Halves the dependent chain of
+// both phases of a step relative to bilstm_rec_fwd_reg, which this replaces when 8 d <= 1024.
+// Shared memory: h [HS][kSG] (transposed: the sequences of a unit contiguous), gate partials
+// [2][4d][kSG] (same orientation, so both its stores and its item-ordered loads are contiguous).
+// Optional per-step timeline of CTA (0,0) (build with -DFVTA_LSTM_TRACE, read with fvta_lstm_trace_read)
+#ifdef FVTA_LSTM_TRACE
+__device__ long long g_lstm_trace[32][8];
+#define LSTM_TRACE(step, ev) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (step) < 32) g_lstm_trace[step][ev] = clock64(); } while (0)
+#else
+#define LSTM_TRACE(step, ev) do {} while (0)
+#endif
+
+template <int HH>
+__global__ void __launch_bounds__(HH <= 25 ? 416 : 512, 2)
+bilstm_rec_fwd_split(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens, const float* __restrict__ xp_fw,
+                     const float* __restrict__ xp_bw, const float* __restrict__ wh_fw,
+                     const float* __restrict__ wh_bw, float* __restrict__ out, float* __restrict__ last,
+                     float* __restrict__ reserve) {
+  static_assert(kSG == 8, "item layout below assumes 8 sequences per CTA");
+  constexpr int HS = 2 * HH;
+  __shared__ __align__(16) float h_s[HS][kSG];
+  __shared__ __align__(16) float g_s[2][4 * HS][kSG];
+  __shared__ int len_s[kSG];
+  const int d = L.d, G = 4 * d;
+  const int dir = blockIdx.y;
+  const float* wh_g = dir == 0 ? wh_fw : wh_bw;
+  const float* xp = dir == 0 ? xp_fw : xp_bw;
+  const int b0 = blockIdx.x * kSG;
+  // ---- gate-phase role: (column g, half) ----
+  const bool gate = threadIdx.x < 2 * G;
+  const int half = threadIdx.x >= G ? 1 : 0;
+  const int g = threadIdx.x - half * G;
+  const int e0 = half * HH;
+  float w[HH];
+#pragma unroll
+  for (int i = 0; i < HH; ++i) w[i] = (gate && e0 + i < d) ? wh_g[(size_t)(e0 + i) * G + g] : 0.f;
+  for (int i = threadIdx.x; i < HS * kSG; i += blockDim.x) (&h_s[0][0])[i] = 0.f;
+  if (threadIdx.x < kSG) {
+    const int b = b0 + threadIdx.x;
+    len_s[threadIdx.x] = (b < L.B) ? min(lens[b], L.J) : 0;
+  }
+  __syncthreads();
+  int maxlen = 0;
+#pragma unroll
+  for (int q = 0; q < kSG; ++q) maxlen = max(maxlen, len_s[q]);
+  // ---- cell-phase role: item (unit e, sequence s), s fastest.  The item also adds the projected
+  // input of its four gates, fetched one step ahead straight into its own registers ----
+  const bool item = threadIdx.x < kSG * d;
+  const int ie = threadIdx.x / kSG, is = threadIdx.x % kSG;
+  const int ib = b0 + is;
+  const int ilen = item ? len_s[is] : 0;
+  const int itok = (item && ib < L.B) ? A.tok0(ib, L.J) : 0;
+  const long long iorow = (item && ib < L.B) ? A.out0(ib, L.J) : -1;
+  const float* xitem = xp + (size_t)itok * G + ie;
+  float c = 0.f;
+  float xg[4] = {0.f, 0.f, 0.f, 0.f};
+  auto fetch_x = [&](int step) {
+    if (step < ilen) {
+      const float* r = xitem + (size_t)(dir == 0 ? step : ilen - 1 - step) * G;
+      xg[0] = r[0]; xg[1] = r[d]; xg[2] = r[2 * d]; xg[3] = r[3 * d];
+    }
+  };
+  fetch_x(0);
+  const float* hrow = &h_s[e0][0];
+  float* gdst = &g_s[half][gate ? g : 0][0];
+  constexpr int kBatch = 3;   // hidden units whose broadcast h loads are issued before their FMAs
+
+  for (int step = 0; step < maxlen; ++step) {
+    LSTM_TRACE(step, 0);
+    if (gate) {
+      float2 a01 = make_float2(0.f, 0.f), a23 = a01, a45 = a01, a67 = a01;
+#pragma unroll
+      for (int i0 = 0; i0 < HH; i0 += kBatch) {
+        float4 x0[kBatch], x1[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+          if (i0 + u < HH) {
+            x0[u] = *reinterpret_cast<const float4*>(hrow + (i0 + u) * kSG);
+            x1[u] = *reinterpret_cast<const float4*>(hrow + (i0 + u) * kSG + 4);
+          }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+          if (i0 + u < HH) {
+            const float2 w2 = make_float2(w[i0 + u], w[i0 + u]);
+            a01 = __ffma2_rn(w2, make_float2(x0[u].x, x0[u].y), a01);
+            a23 = __ffma2_rn(w2, make_float2(x0[u].z, x0[u].w), a23);
+            a45 = __ffma2_rn(w2, make_float2(x1[u].x, x1[u].y), a45);
+            a67 = __ffma2_rn(w2, make_float2(x1[u].z, x1[u].w), a67);
+          }
+      }
+      reinterpret_cast<float4*>(gdst)[0] = make_float4(a01.x, a01.y, a23.x, a23.y);
+      reinterpret_cast<float4*>(gdst)[1] = make_float4(a45.x, a45.y, a67.x, a67.y);
+    }
+    LSTM_TRACE(step, 3);
+    __syncthreads();
+    LSTM_TRACE(step, 4);
+    if (item && step < ilen) {
+      const int t = dir == 0 ? step : ilen - 1 - step;
+      const float gi = g_s[0][ie][is] + g_s[1][ie][is] + xg[0];
+      const float gj = g_s[0][d + ie][is] + g_s[1][d + ie][is] + xg[1];
+      const float gf = g_s[0][2 * d + ie][is] + g_s[1][2 * d + ie][is] + xg[2];
+      const float go = g_s[0][3 * d + ie][is] + g_s[1][3 * d + ie][is] + xg[3];
+      fetch_x(step + 1);   // lands during the next gate phase
+      const float ig = sigmoid_fast(gi);
+      const float jg = tanh_fast(gj);
+      const float fg = sigmoid_fast(gf + 1.0f);  // forget_bias = 1.0 [TF]
+      const float og = sigmoid_fast(go);
+      const float hp = h_s[ie][is];
+      c = fmaf(c, fg, ig * jg);
+      const float h = tanh_fast(c) * og;
+      h_s[ie][is] = h;
+      if (iorow >= 0) out[((size_t)iorow + t) * 2 * d + dir * d + ie] = h;
+      float* r = reserve + ((size_t)dir * A.ntok + itok + t) * kResW * d + ie;
+      r[0] = ig; r[d] = jg; r[2 * d] = fg; r[3 * d] = og; r[4 * d] = c; r[5 * d] = hp;
+    }
+    LSTM_TRACE(step, 5);
+    __syncthreads();
+    LSTM_TRACE(step, 6);
+  }
+  if (item && ib < L.B) last[(size_t)ib * 2 * d + dir * d + ie] = h_s[ie][is];
+}
+
+#ifdef FVTA_LSTM_TRACE
+}  // namespace fvta
+extern "C" int fvta_lstm_trace_read(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, fvta::g_lstm_trace, sizeof(long long) * 32 * 8);
+}
+namespace fvta {
+#endif
 
 // grid (ceil(B/kSG), 2); block: multiple of 32
 __global__ void bilstm_rec_fwd(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
@@ -520,7 +654,21 @@ static int lstm_fwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x
   if (e != cudaSuccess) { set_last_error("bilstm_rec_fwd smem attr", e); return FVTA_E_LAUNCH; }
   int threads = round_up(G < 1024 ? G : 1024, 32);
   dim3 grid((L.B + kSG - 1) / kSG, 2);
-  if (L.d <= 64) {   // the reference's hidden sizes (50, 100 is the flag default): W_h column in registers
+  if (L.d <= 64) {   // the reference's hidden sizes (50; 100 is the flag default): W_h columns in registers
+    static const bool old_fwd = [] { const char* e2 = getenv("FVTA_LSTM_FWD_REG"); return e2 && e2[0] == '1'; }();
+    if (!old_fwd) {
+      const int th = round_up(8 * L.d, 32);
+      if (L.d <= 32)
+        bilstm_rec_fwd_split<16><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+                                                       kernel_bw + (size_t)L.In * G, out, last, reserve);
+      else if (L.d <= 50)
+        bilstm_rec_fwd_split<25><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+                                                       kernel_bw + (size_t)L.In * G, out, last, reserve);
+      else
+        bilstm_rec_fwd_split<32><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+                                                       kernel_bw + (size_t)L.In * G, out, last, reserve);
+      return check_launch("bilstm_rec_fwd_split");
+    }
     if (L.d <= 52)
       bilstm_rec_fwd_reg<13><<<grid, threads, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
                                                         kernel_bw + (size_t)L.In * G, out, last, reserve);
