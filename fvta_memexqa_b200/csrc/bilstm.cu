@@ -481,13 +481,17 @@ __global__ void bilstm_rec_bwd(FvtaLstmDesc L, SeqAddr A, const int32_t* __restr
 //   * the item's cell-state gradient lives in a register for the whole sequence;
 //   * the saved gates / cell states / incoming d out of the NEXT step to process are fetched while
 //     the d h_prev product of the current one runs (global latency off the per-step critical path);
-//   * d gates go to shared memory transposed, dgT[g][kSG] (conflict-free with this item order), the
-//     d h_prev product reads them as broadcast float4s against one W_h element per g (packed
-//     fp32x2 FMAs) and leaves per-gate-block partials part[q][e][kSG] that the next step's item
-//     threads add up -- two barriers per step.
-// Shared memory: W_h [d][4d+1] | dgT [4d][kSG] | part [4][d][kSG].
+//   * d gates go to shared memory transposed, dgT[g][kSG] (conflict-free with this item order).
+//     The d h_prev product is bound by how many bytes shared memory has to return to registers
+//     (every broadcast float4 costs a full 512-byte warp write-back), so a product thread owns TWO
+//     hidden units and one of kParts slices of the gate range: per gate it reads two W_h scalars
+//     and the two broadcast float4s of dgT[g] and issues eight packed FMAs.  The kParts partial
+//     sums part[p][e][kSG] are added up by the next step's item threads -- two barriers per step.
+// Shared memory: W_h [d][4d+1] | dgT [4d][kSG] | part [kParts][d][kSG].
+constexpr int kParts = 8;
+
 template <int BT>
-__global__ void __launch_bounds__(BT, BT <= 256 ? 4 : (BT <= 416 ? 3 : 1))
+__global__ void __launch_bounds__(BT, BT <= 256 ? 4 : (BT <= 416 ? 2 : 1))
 bilstm_rec_bwd_item(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
                                     const float* __restrict__ wh_fw, const float* __restrict__ wh_bw,
                                     const float* __restrict__ reserve, const float* __restrict__ d_out,
@@ -500,11 +504,11 @@ bilstm_rec_bwd_item(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
   const float* wh_g = dir == 0 ? wh_fw : wh_bw;
   float* w_s = sm;                                              // [d][4d+1]
   float* dgT = sm + round_up_sz((size_t)d * wsd, 4);            // [4d][kSG]
-  float* part_s = dgT + (size_t)G * kSG;                        // [4][d][kSG]
+  float* part_s = dgT + (size_t)G * kSG;                        // [kParts][d][kSG]
   __shared__ int len_s[kSG];
   const int b0 = blockIdx.x * kSG;
   for (int i = threadIdx.x; i < d * G; i += blockDim.x) w_s[(i / G) * wsd + (i % G)] = wh_g[i];
-  for (int i = threadIdx.x; i < 4 * d * kSG; i += blockDim.x) part_s[i] = 0.f;
+  for (int i = threadIdx.x; i < kParts * d * kSG; i += blockDim.x) part_s[i] = 0.f;
   if (threadIdx.x < kSG) {
     const int b = b0 + threadIdx.x;
     len_s[threadIdx.x] = (b < L.B) ? min(lens[b], L.J) : 0;
@@ -524,6 +528,7 @@ bilstm_rec_bwd_item(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
   const float* res = reserve + ((size_t)dir * A.ntok + tok0) * kResW * d + e;   // + t * kResW * d + slot * d
   const float* dout_p = (d_out && orow >= 0) ? d_out + (size_t)orow * 2 * d + dir * d + e : nullptr;
   float* dgd = dgates + ((size_t)dir * A.ntok + tok0) * G + e;
+  const float* part_i = part_s + (size_t)e * kSG + s;
   float dc = 0.f;
   float ig = 0.f, jg = 0.f, fg = 0.f, og = 0.f, cc = 0.f, cp = 0.f, dout = 0.f;
   auto fetch = [&](int st) {   // saved values of recurrence step st (0 <= st < len)
@@ -537,19 +542,23 @@ bilstm_rec_bwd_item(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
   };
   if (item && maxlen - 1 < len) fetch(maxlen - 1);
 
-  // ---- d h_prev product mapping: thread (quarter, e) ----
-  const int nq = (int)blockDim.x >= 4 * d ? 4 : ((int)blockDim.x >= 2 * d ? 2 : 1);
-  const bool prod = threadIdx.x < nq * d;
-  const int pq = threadIdx.x / d, pe = threadIdx.x - pq * d;
-  const int g0 = pq * (G / nq), g1 = g0 + G / nq;
-  const float* wr = w_s + (size_t)pe * wsd;
+  // ---- d h_prev product mapping: thread (part, unit pair) ----
+  const int dh2 = (d + 1) >> 1;                     // units pe and pe + dh2
+  const int gper = (G + kParts - 1) / kParts;
+  const bool prod = threadIdx.x < kParts * dh2;
+  const int pq = threadIdx.x / dh2, pe = threadIdx.x - pq * dh2;
+  const int pe1 = pe + dh2 < d ? pe + dh2 : pe;     // odd d: the last pair repeats a unit, its second sum is dropped
+  const int g0 = pq * gper, g1 = min(G, g0 + gper);
+  const float* wr0 = w_s + (size_t)pe * wsd;
+  const float* wr1 = w_s + (size_t)pe1 * wsd;
 
   for (int step = maxlen - 1; step >= 0; --step) {
     if (item) {
       float dgi = 0.f, dgj = 0.f, dgf = 0.f, dgo = 0.f;
       if (step < len) {
         float dh = dout;
-        for (int q = 0; q < nq; ++q) dh += part_s[((size_t)q * d + e) * kSG + s];
+#pragma unroll
+        for (int q = 0; q < kParts; ++q) dh += part_i[(size_t)q * d * kSG];
         const float tc = tanh_fast(cc);
         const float dcv = fmaf(dh * og, 1.f - tc * tc, dc);
         dgo = dh * tc * og * (1.f - og);
@@ -570,20 +579,30 @@ bilstm_rec_bwd_item(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
     __syncthreads();
     if (prod) {
       float2 a01 = make_float2(0.f, 0.f), a23 = a01, a45 = a01, a67 = a01;
-#pragma unroll 4
+      float2 c01 = a01, c23 = a01, c45 = a01, c67 = a01;
+#pragma unroll 5
       for (int g = g0; g < g1; ++g) {
-        const float w = wr[g];
-        const float2 w2 = make_float2(w, w);
+        const float w0 = wr0[g], w1 = wr1[g];
         const float4 x0 = *reinterpret_cast<const float4*>(dgT + (size_t)g * kSG);
         const float4 x1 = *reinterpret_cast<const float4*>(dgT + (size_t)g * kSG + 4);
-        a01 = __ffma2_rn(w2, make_float2(x0.x, x0.y), a01);
-        a23 = __ffma2_rn(w2, make_float2(x0.z, x0.w), a23);
-        a45 = __ffma2_rn(w2, make_float2(x1.x, x1.y), a45);
-        a67 = __ffma2_rn(w2, make_float2(x1.z, x1.w), a67);
+        const float2 u = make_float2(w0, w0), v = make_float2(w1, w1);
+        a01 = __ffma2_rn(u, make_float2(x0.x, x0.y), a01);
+        a23 = __ffma2_rn(u, make_float2(x0.z, x0.w), a23);
+        a45 = __ffma2_rn(u, make_float2(x1.x, x1.y), a45);
+        a67 = __ffma2_rn(u, make_float2(x1.z, x1.w), a67);
+        c01 = __ffma2_rn(v, make_float2(x0.x, x0.y), c01);
+        c23 = __ffma2_rn(v, make_float2(x0.z, x0.w), c23);
+        c45 = __ffma2_rn(v, make_float2(x1.x, x1.y), c45);
+        c67 = __ffma2_rn(v, make_float2(x1.z, x1.w), c67);
       }
       float4* dst = reinterpret_cast<float4*>(part_s + ((size_t)pq * d + pe) * kSG);
       dst[0] = make_float4(a01.x, a01.y, a23.x, a23.y);
       dst[1] = make_float4(a45.x, a45.y, a67.x, a67.y);
+      if (pe1 != pe) {
+        dst = reinterpret_cast<float4*>(part_s + ((size_t)pq * d + pe1) * kSG);
+        dst[0] = make_float4(c01.x, c01.y, c23.x, c23.y);
+        dst[1] = make_float4(c45.x, c45.y, c67.x, c67.y);
+      }
     }
     __syncthreads();
   }
@@ -695,7 +714,7 @@ static int lstm_bwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x
   const LstmSmemPlan plan = lstm_smem_plan(L.d);
   dim3 grid((L.B + kSG - 1) / kSG, 2);
   int rc;
-  const size_t item_smem = (round_up_sz((size_t)L.d * (G + 1), 4) + (size_t)2 * G * kSG) * sizeof(float);
+  const size_t item_smem = (round_up_sz((size_t)L.d * (G + 1), 4) + (size_t)G * kSG + (size_t)kParts * L.d * kSG) * sizeof(float);
   if (kSG * L.d <= 1024 && item_smem <= 200 * 1024) {
     const int threads = round_up(kSG * L.d, 32);
     auto kern = threads <= 256 ? bilstm_rec_bwd_item<256> : (threads <= 416 ? bilstm_rec_bwd_item<416> : bilstm_rec_bwd_item<1024>);
