@@ -151,13 +151,15 @@ __global__ void __launch_bounds__(256) bilstm_rec_fwd_reg(FvtaLstmDesc L, SeqAdd
   }
 }
 
-// Forward recurrence, two threads per gate column (d <= 64): thread (g, half) keeps HALF of column
-// g of W_h in registers and forms the partial gate pre-activation of the kSG sequences over its
-// half of the hidden units; the cell update then runs one (unit, sequence) item per thread (the
-// cell state never leaves its register) and sums the two partials.  Halves the dependent chain of
-// both phases of a step relative to bilstm_rec_fwd_reg, which this replaces when 8 d <= 1024.
-// Shared memory: h [HS][kSG] (transposed: the sequences of a unit contiguous), gate partials
-// [2][4d][kSG] (same orientation, so both its stores and its item-ordered loads are contiguous).
+// Forward recurrence for d <= 64.  What bounds a step is the number of bytes shared memory returns
+// to registers (a broadcast float4 of h costs a full 512-byte warp write-back), so a gate thread
+// owns TWO gate columns (g and g + 2d) and one quarter of the hidden units: per unit it reads the
+// two float4s h[e][0..7] once and issues eight packed FMAs against its 2 x HQ register-resident
+// W_h entries.  The cell update runs one (unit, sequence) item per thread -- the cell state and the
+// prefetched projected input of its four gates never leave its registers -- and adds the four
+// quarter partials.
+// Shared memory: h [4 HQ][kSG] (transposed: the sequences of a unit contiguous), gate partials
+// [4][4d][kSG] (same orientation: stores and item-ordered loads are both contiguous).
 // Optional per-step timeline of CTA (0,0) (build with -DFVTA_LSTM_TRACE, read with fvta_lstm_trace_read)
 #ifdef FVTA_LSTM_TRACE
 __device__ long long g_lstm_trace[32][8];
@@ -166,30 +168,34 @@ __device__ long long g_lstm_trace[32][8];
 #define LSTM_TRACE(step, ev) do {} while (0)
 #endif
 
-template <int HH>
-__global__ void __launch_bounds__(HH <= 25 ? 416 : 512, 2)
+template <int HQ>
+__global__ void __launch_bounds__(HQ <= 13 ? 416 : 512, 2)
 bilstm_rec_fwd_split(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens, const float* __restrict__ xp_fw,
                      const float* __restrict__ xp_bw, const float* __restrict__ wh_fw,
                      const float* __restrict__ wh_bw, float* __restrict__ out, float* __restrict__ last,
                      float* __restrict__ reserve) {
   static_assert(kSG == 8, "item layout below assumes 8 sequences per CTA");
-  constexpr int HS = 2 * HH;
+  constexpr int HS = 4 * HQ;
   __shared__ __align__(16) float h_s[HS][kSG];
-  __shared__ __align__(16) float g_s[2][4 * HS][kSG];
+  __shared__ __align__(16) float g_s[4][4 * HS][kSG];
   __shared__ int len_s[kSG];
-  const int d = L.d, G = 4 * d;
+  const int d = L.d, G = 4 * d, G2 = 2 * d;
   const int dir = blockIdx.y;
   const float* wh_g = dir == 0 ? wh_fw : wh_bw;
   const float* xp = dir == 0 ? xp_fw : xp_bw;
   const int b0 = blockIdx.x * kSG;
-  // ---- gate-phase role: (column g, half) ----
-  const bool gate = threadIdx.x < 2 * G;
-  const int half = threadIdx.x >= G ? 1 : 0;
-  const int g = threadIdx.x - half * G;
-  const int e0 = half * HH;
-  float w[HH];
+  // ---- gate-phase role: (column pair cp, quarter) ----
+  const bool gate = threadIdx.x < 4 * G2;
+  const int qtr = gate ? threadIdx.x / G2 : 0;
+  const int cp = threadIdx.x - qtr * G2;
+  const int e0 = qtr * HQ;
+  float w0[HQ], w1[HQ];
 #pragma unroll
-  for (int i = 0; i < HH; ++i) w[i] = (gate && e0 + i < d) ? wh_g[(size_t)(e0 + i) * G + g] : 0.f;
+  for (int i = 0; i < HQ; ++i) {
+    const bool ok = gate && e0 + i < d;
+    w0[i] = ok ? wh_g[(size_t)(e0 + i) * G + cp] : 0.f;
+    w1[i] = ok ? wh_g[(size_t)(e0 + i) * G + G2 + cp] : 0.f;
+  }
   for (int i = threadIdx.x; i < HS * kSG; i += blockDim.x) (&h_s[0][0])[i] = 0.f;
   if (threadIdx.x < kSG) {
     const int b = b0 + threadIdx.x;
@@ -199,8 +205,7 @@ bilstm_rec_fwd_split(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens
   int maxlen = 0;
 #pragma unroll
   for (int q = 0; q < kSG; ++q) maxlen = max(maxlen, len_s[q]);
-  // ---- cell-phase role: item (unit e, sequence s), s fastest.  The item also adds the projected
-  // input of its four gates, fetched one step ahead straight into its own registers ----
+  // ---- cell-phase role: item (unit e, sequence s), s fastest ----
   const bool item = threadIdx.x < kSG * d;
   const int ie = threadIdx.x / kSG, is = threadIdx.x % kSG;
   const int ib = b0 + is;
@@ -218,49 +223,51 @@ bilstm_rec_fwd_split(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens
   };
   fetch_x(0);
   const float* hrow = &h_s[e0][0];
-  float* gdst = &g_s[half][gate ? g : 0][0];
-  constexpr int kBatch = 3;   // hidden units whose broadcast h loads are issued before their FMAs
+  float* gdst0 = &g_s[qtr][gate ? cp : 0][0];
+  float* gdst1 = &g_s[qtr][gate ? G2 + cp : 0][0];
+  const float* gsrc = &g_s[0][item ? ie : 0][is];
+  constexpr int kQStride = 4 * HS * kSG;   // floats between quarter partials
 
   for (int step = 0; step < maxlen; ++step) {
     LSTM_TRACE(step, 0);
     if (gate) {
       float2 a01 = make_float2(0.f, 0.f), a23 = a01, a45 = a01, a67 = a01;
+      float2 c01 = a01, c23 = a01, c45 = a01, c67 = a01;
 #pragma unroll
-      for (int i0 = 0; i0 < HH; i0 += kBatch) {
-        float4 x0[kBatch], x1[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u)
-          if (i0 + u < HH) {
-            x0[u] = *reinterpret_cast<const float4*>(hrow + (i0 + u) * kSG);
-            x1[u] = *reinterpret_cast<const float4*>(hrow + (i0 + u) * kSG + 4);
-          }
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u)
-          if (i0 + u < HH) {
-            const float2 w2 = make_float2(w[i0 + u], w[i0 + u]);
-            a01 = __ffma2_rn(w2, make_float2(x0[u].x, x0[u].y), a01);
-            a23 = __ffma2_rn(w2, make_float2(x0[u].z, x0[u].w), a23);
-            a45 = __ffma2_rn(w2, make_float2(x1[u].x, x1[u].y), a45);
-            a67 = __ffma2_rn(w2, make_float2(x1[u].z, x1[u].w), a67);
-          }
+      for (int i = 0; i < HQ; ++i) {
+        const float4 x0 = *reinterpret_cast<const float4*>(hrow + i * kSG);
+        const float4 x1 = *reinterpret_cast<const float4*>(hrow + i * kSG + 4);
+        const float2 u = make_float2(w0[i], w0[i]), v = make_float2(w1[i], w1[i]);
+        a01 = __ffma2_rn(u, make_float2(x0.x, x0.y), a01);
+        a23 = __ffma2_rn(u, make_float2(x0.z, x0.w), a23);
+        a45 = __ffma2_rn(u, make_float2(x1.x, x1.y), a45);
+        a67 = __ffma2_rn(u, make_float2(x1.z, x1.w), a67);
+        c01 = __ffma2_rn(v, make_float2(x0.x, x0.y), c01);
+        c23 = __ffma2_rn(v, make_float2(x0.z, x0.w), c23);
+        c45 = __ffma2_rn(v, make_float2(x1.x, x1.y), c45);
+        c67 = __ffma2_rn(v, make_float2(x1.z, x1.w), c67);
       }
-      reinterpret_cast<float4*>(gdst)[0] = make_float4(a01.x, a01.y, a23.x, a23.y);
-      reinterpret_cast<float4*>(gdst)[1] = make_float4(a45.x, a45.y, a67.x, a67.y);
+      reinterpret_cast<float4*>(gdst0)[0] = make_float4(a01.x, a01.y, a23.x, a23.y);
+      reinterpret_cast<float4*>(gdst0)[1] = make_float4(a45.x, a45.y, a67.x, a67.y);
+      reinterpret_cast<float4*>(gdst1)[0] = make_float4(c01.x, c01.y, c23.x, c23.y);
+      reinterpret_cast<float4*>(gdst1)[1] = make_float4(c45.x, c45.y, c67.x, c67.y);
     }
     LSTM_TRACE(step, 3);
     __syncthreads();
     LSTM_TRACE(step, 4);
     if (item && step < ilen) {
       const int t = dir == 0 ? step : ilen - 1 - step;
-      const float gi = g_s[0][ie][is] + g_s[1][ie][is] + xg[0];
-      const float gj = g_s[0][d + ie][is] + g_s[1][d + ie][is] + xg[1];
-      const float gf = g_s[0][2 * d + ie][is] + g_s[1][2 * d + ie][is] + xg[2];
-      const float go = g_s[0][3 * d + ie][is] + g_s[1][3 * d + ie][is] + xg[3];
+      float gv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* p = gsrc + (size_t)k * d * kSG;
+        gv[k] = (p[0] + p[kQStride]) + (p[2 * kQStride] + p[3 * kQStride]) + xg[k];
+      }
       fetch_x(step + 1);   // lands during the next gate phase
-      const float ig = sigmoid_fast(gi);
-      const float jg = tanh_fast(gj);
-      const float fg = sigmoid_fast(gf + 1.0f);  // forget_bias = 1.0 [TF]
-      const float og = sigmoid_fast(go);
+      const float ig = sigmoid_fast(gv[0]);
+      const float jg = tanh_fast(gv[1]);
+      const float fg = sigmoid_fast(gv[2] + 1.0f);  // forget_bias = 1.0 [TF]
+      const float og = sigmoid_fast(gv[3]);
       const float hp = h_s[ie][is];
       c = fmaf(c, fg, ig * jg);
       const float h = tanh_fast(c) * og;
@@ -678,13 +685,13 @@ static int lstm_fwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x
     if (!old_fwd) {
       const int th = round_up(8 * L.d, 32);
       if (L.d <= 32)
-        bilstm_rec_fwd_split<16><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
-                                                       kernel_bw + (size_t)L.In * G, out, last, reserve);
-      else if (L.d <= 50)
-        bilstm_rec_fwd_split<25><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+        bilstm_rec_fwd_split<8><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+                                                      kernel_bw + (size_t)L.In * G, out, last, reserve);
+      else if (L.d <= 52)
+        bilstm_rec_fwd_split<13><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
                                                        kernel_bw + (size_t)L.In * G, out, last, reserve);
       else
-        bilstm_rec_fwd_split<32><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+        bilstm_rec_fwd_split<16><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
                                                        kernel_bw + (size_t)L.In * G, out, last, reserve);
       return check_launch("bilstm_rec_fwd_split");
     }
