@@ -8,7 +8,7 @@ tail -3 gpurun_out/pytest_gpu_$TAG.log
 timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 400 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; cat gpurun_out/bench_$TAG.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err; cat gpurun_out/bench_ref_$TAG.json
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 500 -c 700 --csv \
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 450 --csv \
   --log-file gpurun_out/launches_${TAG}_bench_eager.csv python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline \
   > gpurun_out/bench_ncu_$TAG.log 2>&1; echo "ncu list rc=$?"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:attn_fwd_tc -s 2 -c 1 -f \
