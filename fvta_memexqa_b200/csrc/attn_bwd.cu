@@ -463,6 +463,15 @@ static int launch_tile_bwd(const FvtaAttnDesc& d, const AttnLayout& L, const flo
 
 using namespace fvta;
 
+namespace fvta {
+bool fvta_force_ffma();
+bool attn_small_ok(const FvtaAttnDesc& d);
+size_t attn_small_ws_floats(const FvtaAttnDesc& d);
+int attn_small_bwd(const FvtaAttnDesc& d, const float* hall, const uint8_t* hall_mask, const float* hq,
+                   const uint8_t* hq_mask, const FvtaAttnParams& P, const float* dg1, float* d_hall, float* d_hq,
+                   const FvtaAttnGrads& G, float* ws, cudaStream_t st);
+}  // namespace fvta
+
 extern "C" int fvta_attn_bwd(const FvtaAttnDesc* desc, const float* hall, const uint8_t* hall_mask,
                              const float* hq, const uint8_t* hq_mask, const float* lq,
                              const FvtaAttnParams* params, const float* stats, const float* d_g1_all,
@@ -482,6 +491,9 @@ extern "C" int fvta_attn_bwd(const FvtaAttnDesc* desc, const float* hall, const 
   if (attn_tile_bwd_smem_bytes(d, L.JQP, L.Dp) > 227 * 1024) return FVTA_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
+  // question-attention shape: fused per-sample kernels (attn_small.cu), nothing taken from the forward
+  if (attn_small_ok(d) && !fvta_force_ffma() && workspace_bytes >= attn_small_ws_floats(d) * sizeof(float))
+    return attn_small_bwd(d, hall, hall_mask, hq, hq_mask, *params, d_g1_all, d_hall, d_hq, *grads, ws, st);
   // The folded operands are recomputed (cheap) so the workspace need not survive between
   // the forward and the backward call.
   if (!d.ws_from_fwd) {

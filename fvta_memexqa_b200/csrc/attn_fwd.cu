@@ -377,7 +377,7 @@ int attn_fwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hal
 int g_attn_stages = 7;
 
 // FVTA_FORCE_FFMA=1 pins the CUDA-core forward (A/B measurements, debugging)
-static bool fvta_force_ffma() {
+bool fvta_force_ffma() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("FVTA_FORCE_FFMA"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
@@ -397,6 +397,12 @@ extern "C" size_t fvta_attn_stats_floats(const FvtaAttnDesc* desc) {
   return (size_t)desc->N * desc->K * (kStatW + desc->D);
 }
 
+namespace fvta {
+bool attn_small_ok(const FvtaAttnDesc& d);
+int attn_small_fwd(const FvtaAttnDesc& d, const float* hall, const uint8_t* hall_mask, const float* hq,
+                   const uint8_t* hq_mask, const FvtaAttnParams& P, float* g1_all, float* a_logits, cudaStream_t st);
+}  // namespace fvta
+
 extern "C" int fvta_attn_fwd(const FvtaAttnDesc* desc, const float* hall, const uint8_t* hall_mask,
                              const float* hq, const uint8_t* hq_mask, const float* lq,
                              const FvtaAttnParams* params, float* g1_all, float* a_logits, float* c_col,
@@ -414,6 +420,9 @@ extern "C" int fvta_attn_fwd(const FvtaAttnDesc* desc, const float* hall, const 
   if (workspace_bytes < L.total * sizeof(float)) return FVTA_E_WORKSPACE;
   if (attn_tile_smem_bytes(d, L.JQP, L.Dp) > 227 * 1024) return FVTA_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
+  // question-attention shape (K = 1, JQ = 1, no time warp): one CTA per sample does everything
+  if (attn_small_ok(d) && warp_h == nullptr && c_col == nullptr && g_attn_stages == 7 && !fvta_force_ffma())
+    return attn_small_fwd(d, hall, hall_mask, hq, hq_mask, *params, g1_all, a_logits, st);
   float* ws = (float*)workspace;
   const int stages = g_attn_stages;
   if (stages & 1) {

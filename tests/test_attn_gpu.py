@@ -59,7 +59,10 @@ CASES = [
     (2, 6, 2, 6, 20, 5, 2, True, True, 1, False),      # warp type 1 (cnt = T; kept small: g^2 terms
                                                        # of O(T^2) make S ill-conditioned in fp32)
     (1, 6, 2, 40, 132, 8, 2, False, True, 2, False),   # chunked with a ragged last chunk
-    (2, 1, 1, 25, 100, 1, 2, True, False, 1, False),   # question-attention shape (K=1, JQ=1)
+    (2, 1, 1, 25, 100, 1, 2, True, False, 1, False),   # question-attention shape (K=1, JQ=1): attn_small.cu
+    (3, 1, 1, 25, 100, 1, 1, False, False, 1, False),  # question attention, simi 1, no tanh
+    (2, 1, 1, 30, 36, 1, 3, True, False, 1, False),    # question attention, simi 3
+    (2, 1, 1, 25, 100, 1, 4, True, False, 1, False),   # question attention, cosine
     (1, 6, 2, 64, 64, 64, 2, True, True, 5, False),    # JQ = 64 accumulators
 ]
 
@@ -95,6 +98,18 @@ def test_attn_fwd_fully_masked_and_zero(cuda_device):
     assert rel_err(out["g1_all"], ref["g1_all"]) < TOL or ref["g1_all"].abs().max() == 0
 
 
+def test_question_attention_fully_masked(cuda_device):
+    """K=1, JQ=1 path (attn_small.cu): a fully masked question gives the uniform softmax over all
+    T rows, exactly like tf.nn.softmax over a row of -1e30 (model_v2.py:23-48)."""
+    cfg, params, inp = attn_case(2, 1, 1, 25, 100, 1, 2, True, False, 1, False, seed=11)
+    inp["hall_mask"][1] = False
+    out, _ = run_gpu_fwd(cfg, params, inp, cuda_device, want_logits=True)
+    ref = oracle64(cfg, params, inp)
+    assert rel_err(out["g1_all"], ref["g1_all"]) < TOL
+    mean = inp["hall"][1].reshape(25, 100).double().mean(0)
+    assert rel_err(out["g1_all"][1], mean) < TOL
+
+
 def test_attn_fwd_single_valid_position(cuda_device):
     """Single valid position in one modality: r_k equals the gated row of that position."""
     cfg, params, inp = attn_case(1, 6, 1, 40, 100, 25, seed=5, density=1.0, q_density=1.0)
@@ -117,7 +132,10 @@ BWD_CASES = [
     (2, 5, 2, 33, 100, 32, 4, True, True, 5, False),   # cosine
     (2, 6, 2, 48, 100, 25, 2, True, False, 1, False),  # no time warp
     (2, 6, 2, 40, 256, 32, 2, True, True, 2, False),   # chunked D
-    (2, 1, 1, 25, 100, 1, 2, True, False, 1, False),   # question-attention shape
+    (2, 1, 1, 25, 100, 1, 2, True, False, 1, False),   # question-attention shape (attn_small.cu)
+    (3, 1, 1, 25, 100, 1, 1, False, False, 1, False),  # question attention, simi 1, no tanh
+    (2, 1, 1, 30, 36, 1, 3, True, False, 1, False),    # question attention, simi 3
+    (2, 1, 1, 25, 100, 1, 4, True, False, 1, False),   # question attention, cosine
     (2, 6, 2, 24, 100, 25, 2, False, True, 5, False),  # no tanh: maxima not saturated
 ]
 
