@@ -48,108 +48,12 @@ struct SeqAddr {
   __device__ __forceinline__ long long out0(int b, int J) const { return out_row ? out_row[b] : (long long)b * J; }
 };
 
-// Forward recurrence for d <= 64: thread g keeps column g of W_h in registers, h lives in shared
-// memory as float4 rows (one broadcast LDS.128 feeds four FMAs of each of the kSG sequences) and
-// the projected input of the NEXT step is fetched while the current step computes.
 // MUFU-based activations (ex2.approx / rcp.approx): |error| < 1e-6, an order of magnitude cheaper
 // than expf / tanhf, which dominated the cell update
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx_(1.f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.f - 2.f * rcp_approx_(1.f + ex2_approx(2.885390081777927f * x)); }
-
-template <int D4MAX>
-__global__ void __launch_bounds__(256) bilstm_rec_fwd_reg(FvtaLstmDesc L, SeqAddr A, const int32_t* __restrict__ lens,
-                                                          const float* __restrict__ xp_fw, const float* __restrict__ xp_bw,
-                                                          const float* __restrict__ wh_fw, const float* __restrict__ wh_bw,
-                                                          float* __restrict__ out, float* __restrict__ last,
-                                                          float* __restrict__ reserve) {
-  static_assert(kSG == 8, "the packed gate product below is written for 8 sequences per CTA");
-  constexpr int HS = 4 * D4MAX;                      // padded hidden size
-  __shared__ __align__(16) float h_s[HS][kSG];       // h transposed: the kSG sequences of one unit are contiguous
-  __shared__ float c_s[kSG][HS];
-  __shared__ float g_s[kSG][4 * HS];
-  __shared__ int len_s[kSG];
-  __shared__ int tok_s[kSG];
-  __shared__ long long orow_s[kSG];
-  const int d = L.d, G = 4 * d;
-  const int dir = blockIdx.y;
-  const float* wh_g = dir == 0 ? wh_fw : wh_bw;
-  const float* xp = dir == 0 ? xp_fw : xp_bw;
-  const int b0 = blockIdx.x * kSG;
-  const int g = threadIdx.x;
-  float w[HS];
-#pragma unroll
-  for (int e = 0; e < HS; ++e) w[e] = (g < G && e < d) ? wh_g[(size_t)e * G + g] : 0.f;
-  for (int i = threadIdx.x; i < kSG * HS; i += blockDim.x) { (&h_s[0][0])[i] = 0.f; (&c_s[0][0])[i] = 0.f; }
-  if (threadIdx.x < kSG) {
-    const int b = b0 + threadIdx.x;
-    len_s[threadIdx.x] = (b < L.B) ? min(lens[b], L.J) : 0;
-    tok_s[threadIdx.x] = (b < L.B) ? A.tok0(b, L.J) : 0;
-    orow_s[threadIdx.x] = (b < L.B) ? A.out0(b, L.J) : -1;
-  }
-  __syncthreads();
-  int maxlen = 0;
-#pragma unroll
-  for (int s = 0; s < kSG; ++s) maxlen = max(maxlen, len_s[s]);
-  auto fetch = [&](int step, float (&dst)[kSG]) {
-#pragma unroll
-    for (int s = 0; s < kSG; ++s) {
-      const int len = len_s[s];
-      const int t = dir == 0 ? step : len - 1 - step;
-      dst[s] = (g < G && step < len) ? xp[((size_t)tok_s[s] + t) * G + g] : 0.f;
-    }
-  };
-  float xnext[kSG];
-  fetch(0, xnext);
-  for (int step = 0; step < maxlen; ++step) {
-    // gate pre-activations of the 8 sequences as four packed fp32x2 accumulators:
-    // one broadcast LDS.128 pair + four FFMA2 per hidden unit
-    float2 acc01 = make_float2(xnext[0], xnext[1]), acc23 = make_float2(xnext[2], xnext[3]);
-    float2 acc45 = make_float2(xnext[4], xnext[5]), acc67 = make_float2(xnext[6], xnext[7]);
-    if (step + 1 < maxlen) fetch(step + 1, xnext);
-#pragma unroll
-    for (int e = 0; e < HS; ++e) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&h_s[e][0]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&h_s[e][4]);
-      const float2 w2 = make_float2(w[e], w[e]);
-      acc01 = __ffma2_rn(w2, make_float2(a0.x, a0.y), acc01);
-      acc23 = __ffma2_rn(w2, make_float2(a0.z, a0.w), acc23);
-      acc45 = __ffma2_rn(w2, make_float2(a1.x, a1.y), acc45);
-      acc67 = __ffma2_rn(w2, make_float2(a1.z, a1.w), acc67);
-    }
-    if (g < G) {
-      g_s[0][g] = acc01.x; g_s[1][g] = acc01.y; g_s[2][g] = acc23.x; g_s[3][g] = acc23.y;
-      g_s[4][g] = acc45.x; g_s[5][g] = acc45.y; g_s[6][g] = acc67.x; g_s[7][g] = acc67.y;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) {
-      const int s = i / d, e = i - s * d;
-      const int len = len_s[s];
-      if (step < len) {
-        const int t = dir == 0 ? step : len - 1 - step;
-        const float* gs = g_s[s];
-        const float ig = sigmoid_fast(gs[e]);
-        const float jg = tanh_fast(gs[d + e]);
-        const float fg = sigmoid_fast(gs[2 * d + e] + 1.0f);  // forget_bias = 1.0 [TF]
-        const float og = sigmoid_fast(gs[3 * d + e]);
-        const float hp = h_s[e][s];
-        const float c = fmaf(c_s[s][e], fg, ig * jg);
-        const float h = tanh_fast(c) * og;
-        c_s[s][e] = c;
-        h_s[e][s] = h;
-        if (orow_s[s] >= 0) out[((size_t)orow_s[s] + t) * 2 * d + dir * d + e] = h;
-        float* r = reserve + ((size_t)dir * A.ntok + tok_s[s] + t) * kResW * d;
-        r[e] = ig; r[d + e] = jg; r[2 * d + e] = fg; r[3 * d + e] = og; r[4 * d + e] = c; r[5 * d + e] = hp;
-      }
-    }
-    __syncthreads();
-  }
-  for (int i = threadIdx.x; i < kSG * d; i += blockDim.x) {
-    const int s = i / d, e = i - s * d;
-    if (b0 + s < L.B) last[(size_t)(b0 + s) * 2 * d + dir * d + e] = h_s[e][s];
-  }
-}
 
 // Forward recurrence for d <= 64.  What bounds a step is the number of bytes shared memory returns
 // to registers (a broadcast float4 of h costs a full 512-byte warp write-back), so a gate thread
@@ -681,27 +585,17 @@ static int lstm_fwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x
   int threads = round_up(G < 1024 ? G : 1024, 32);
   dim3 grid((L.B + kSG - 1) / kSG, 2);
   if (L.d <= 64) {   // the reference's hidden sizes (50; 100 is the flag default): W_h columns in registers
-    static const bool old_fwd = [] { const char* e2 = getenv("FVTA_LSTM_FWD_REG"); return e2 && e2[0] == '1'; }();
-    if (!old_fwd) {
-      const int th = round_up(8 * L.d, 32);
-      if (L.d <= 32)
-        bilstm_rec_fwd_split<8><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
-                                                      kernel_bw + (size_t)L.In * G, out, last, reserve);
-      else if (L.d <= 52)
-        bilstm_rec_fwd_split<13><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
-                                                       kernel_bw + (size_t)L.In * G, out, last, reserve);
-      else
-        bilstm_rec_fwd_split<16><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
-                                                       kernel_bw + (size_t)L.In * G, out, last, reserve);
-      return check_launch("bilstm_rec_fwd_split");
-    }
-    if (L.d <= 52)
-      bilstm_rec_fwd_reg<13><<<grid, threads, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
-                                                        kernel_bw + (size_t)L.In * G, out, last, reserve);
+    const int th = round_up(8 * L.d, 32);
+    if (L.d <= 32)
+      bilstm_rec_fwd_split<8><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+                                                    kernel_bw + (size_t)L.In * G, out, last, reserve);
+    else if (L.d <= 52)
+      bilstm_rec_fwd_split<13><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+                                                     kernel_bw + (size_t)L.In * G, out, last, reserve);
     else
-      bilstm_rec_fwd_reg<16><<<grid, threads, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
-                                                        kernel_bw + (size_t)L.In * G, out, last, reserve);
-    return check_launch("bilstm_rec_fwd_reg");
+      bilstm_rec_fwd_split<16><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
+                                                     kernel_bw + (size_t)L.In * G, out, last, reserve);
+    return check_launch("bilstm_rec_fwd_split");
   }
   bilstm_rec_fwd<<<grid, threads, plan.bytes, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
                                                    kernel_bw + (size_t)L.In * G, out, last, reserve);
