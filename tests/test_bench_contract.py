@@ -67,3 +67,17 @@ def test_committed_bench_line_is_complete():
     assert line["gpu_launches"] > 0 and line["e2e"]["h2d_bytes_per_step"] > 0
     assert line["e2e"]["value"] <= line["value"] * 1.02      # host copies can only cost time
     assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_committed_launch_list_summarises():
+    """profiles/launches_r1_bench_eager.csv parses into one complete step whose time is dominated by
+    this library's kernels (the evidence that the step is not a torch fallback)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"),
+                          os.path.join(ROOT, "profiles", "launches_r1_bench_eager.csv")],
+                         capture_output=True, text=True, cwd=ROOT, timeout=120)
+    assert out.returncode == 0, out.stderr[-1000:]
+    head = out.stdout.splitlines()[0]
+    assert head.startswith("step:") and "fvta:: kernels" in head
+    pct = int(head.rsplit("(", 1)[1].split("%")[0])
+    assert pct >= 75, head
+    assert "fvta::attn_fwd_tc" in out.stdout and "fvta::gemm_mma_kernel" in out.stdout
