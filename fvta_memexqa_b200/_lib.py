@@ -16,7 +16,7 @@ c_i32_p = ctypes.c_void_p
 class FvtaAttnDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "N", "K", "T", "D", "JQ", "simi", "add_tanh", "use_time_warp", "warp_type", "window",
-        "time_warp_att", "has_mask", "ws_from_fwd")]
+        "time_warp_att", "has_mask", "ws_from_fwd", "path")]
 
 
 class FvtaAttnParams(ctypes.Structure):
@@ -35,6 +35,9 @@ class FvtaReaderDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("B", "ntok", "In", "d", "Jmax")]
 
 
+PATH_AUTO, PATH_SMALL, PATH_FFMA, PATH_TC = 0, 1, 2, 3
+PATH_NAMES = {1: "attn_small", 2: "attn_tile_fwd (FFMA)", 3: "attn_fwd_tc (tcgen05)"}
+
 ERRORS = {0: "FVTA_OK", -1: "FVTA_E_BADARG", -2: "FVTA_E_UNSUPPORTED", -3: "FVTA_E_WORKSPACE",
           -4: "FVTA_E_LAUNCH", -5: "FVTA_E_SHAPE"}
 
@@ -43,7 +46,7 @@ SYMBOLS = {
     "fvta_version": (ctypes.c_int, []),
     "fvta_last_error": (ctypes.c_char_p, []),
     "fvta_launch_count": (ctypes.c_ulonglong, []),
-    "fvta_attn_fwd_set_stages": (None, [ctypes.c_int]),
+    "fvta_attn_fwd_path": (ctypes.c_int, [ctypes.POINTER(FvtaAttnDesc), ctypes.c_int, ctypes.c_int]),
     "fvta_attn_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(FvtaAttnDesc)]),
     "fvta_attn_stats_floats": (ctypes.c_size_t, [ctypes.POINTER(FvtaAttnDesc)]),
     "fvta_attn_fwd": (ctypes.c_int, [ctypes.POINTER(FvtaAttnDesc), c_float_p, c_u8_p, c_float_p, c_u8_p,

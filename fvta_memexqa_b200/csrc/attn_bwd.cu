@@ -16,7 +16,7 @@
 namespace fvta {
 
 int attn_prep_launch(const FvtaAttnDesc& d, const AttnLayout& L, const FvtaAttnParams& p, const float* hq,
-                     const float* lq, float* ws, cudaStream_t st);
+                     const float* lq, float* ws, cudaStream_t st, bool tc_images);
 
 // drow[n][k] = { ds_k, beta_k * (r_k . ghat), beta_k, 0 }
 __global__ void attn_bwd_prep(FvtaAttnDesc d, const float* __restrict__ stats, const float* __restrict__ dg1,
@@ -464,7 +464,6 @@ static int launch_tile_bwd(const FvtaAttnDesc& d, const AttnLayout& L, const flo
 using namespace fvta;
 
 namespace fvta {
-bool fvta_force_ffma();
 bool attn_small_ok(const FvtaAttnDesc& d);
 size_t attn_small_ws_floats(const FvtaAttnDesc& d);
 int attn_small_bwd(const FvtaAttnDesc& d, const float* hall, const uint8_t* hall_mask, const float* hq,
@@ -492,12 +491,12 @@ extern "C" int fvta_attn_bwd(const FvtaAttnDesc* desc, const float* hall, const 
   cudaStream_t st = (cudaStream_t)stream;
   float* ws = (float*)workspace;
   // question-attention shape: fused per-sample kernels (attn_small.cu), nothing taken from the forward
-  if (attn_small_ok(d) && !fvta_force_ffma() && workspace_bytes >= attn_small_ws_floats(d) * sizeof(float))
+  if (attn_small_ok(d) && d.path != FVTA_PATH_FFMA && workspace_bytes >= attn_small_ws_floats(d) * sizeof(float))
     return attn_small_bwd(d, hall, hall_mask, hq, hq_mask, *params, d_g1_all, d_hall, d_hq, *grads, ws, st);
   // The folded operands are recomputed (cheap) so the workspace need not survive between
   // the forward and the backward call.
   if (!d.ws_from_fwd) {
-    rc = attn_prep_launch(d, L, *params, hq, lq, ws, st);
+    rc = attn_prep_launch(d, L, *params, hq, lq, ws, st, false);
     if (rc) return rc;
   }
   cudaError_t e = cudaMemsetAsync(ws + L.dqeffT, 0, (L.drow - L.dqeffT) * sizeof(float), st);

@@ -19,7 +19,6 @@
 //   s_k     = max_{t,j} a;  beta = softmax_k s;  g1_all = sum_k beta_k r_k
 #include "common.cuh"
 #include "attn_tile.cuh"
-#include <stdlib.h>
 
 namespace fvta {
 
@@ -353,8 +352,14 @@ static int launch_tile_fwd(const FvtaAttnDesc& d, const AttnLayout& L, const flo
   return check_launch("attn_tile_fwd");
 }
 
+// tensor-core B images + per-sample CTA counters (attn_fwd_tc.cu)
+int attn_tc_prep_images_launch(const FvtaAttnDesc& d, const AttnLayout& L, float* ws, cudaStream_t st);
+bool attn_tc_covers(const FvtaAttnDesc& d);
+
+// Operand folding: coefficient vectors, per-sample question operand / column term / gate constant,
+// and (tc_images) what only the tensor-core kernel reads.
 int attn_prep_launch(const FvtaAttnDesc& d, const AttnLayout& L, const FvtaAttnParams& p, const float* hq,
-                     const float* lq, float* ws, cudaStream_t st) {
+                     const float* lq, float* ws, cudaStream_t st, bool tc_images) {
   {
     int threads = 256;
     int blocks = (L.Dp * 32 + threads - 1) / threads;
@@ -364,23 +369,24 @@ int attn_prep_launch(const FvtaAttnDesc& d, const AttnLayout& L, const FvtaAttnP
   }
   attn_prep_q<<<dim3(d.N, L.JQP < 8 ? L.JQP : 8), 128, L.JQP * sizeof(float), st>>>(d, p, hq, lq, ws + L.qeffT, ws + L.col,
                                                          ws + L.zconst, L.Dp, L.JQP);
-  return check_launch("attn_prep_q");
+  int rc = check_launch("attn_prep_q");
+  if (rc || !tc_images) return rc;
+  return attn_tc_prep_images_launch(d, L, ws, st);
 }
 
-int attn_fwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hall, const uint8_t* hall_mask,
-                    const uint8_t* hq_mask, float* ws, float* g1_all, float* a_logits, float* c_col, float* stats,
-                    cudaStream_t st);
+int attn_fwd_tc_launch(const FvtaAttnDesc& d, const AttnLayout& L, const float* hall, const uint8_t* hall_mask,
+                       const uint8_t* hq_mask, float* ws, float* g1_all, float* a_logits, float* c_col, float* stats,
+                       cudaStream_t st);
+bool attn_small_ok(const FvtaAttnDesc& d);
 
-// Diagnostic: which stages fvta_attn_fwd launches (bit 0 operand folding, bit 1 the tile kernel,
-// bit 2 the combine).  bench.py times the dominant kernel alone with stages = 2 after one full
-// call has filled the workspace.  Default 7; not for production use.
-int g_attn_stages = 7;
-
-// FVTA_FORCE_FFMA=1 pins the CUDA-core forward (A/B measurements, debugging)
-bool fvta_force_ffma() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FVTA_FORCE_FFMA"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
+// The one place that decides which forward kernel serves a descriptor (fvta_attn_fwd and the
+// fvta_attn_fwd_path query both call it).
+int attn_pick_path(const FvtaAttnDesc& d, bool want_c_col, bool want_warp_h) {
+  if (d.path != FVTA_PATH_AUTO && d.path != FVTA_PATH_FFMA) return FVTA_E_BADARG;
+  if (d.path == FVTA_PATH_FFMA) return FVTA_PATH_FFMA;
+  if (attn_small_ok(d) && !want_warp_h && !want_c_col) return FVTA_PATH_SMALL;
+  if (!want_warp_h && attn_tc_covers(d)) return FVTA_PATH_TC;
+  return FVTA_PATH_FFMA;
 }
 
 }  // namespace fvta
@@ -398,10 +404,15 @@ extern "C" size_t fvta_attn_stats_floats(const FvtaAttnDesc* desc) {
 }
 
 namespace fvta {
-bool attn_small_ok(const FvtaAttnDesc& d);
 int attn_small_fwd(const FvtaAttnDesc& d, const float* hall, const uint8_t* hall_mask, const float* hq,
                    const uint8_t* hq_mask, const FvtaAttnParams& P, float* g1_all, float* a_logits, cudaStream_t st);
 }  // namespace fvta
+
+extern "C" int fvta_attn_fwd_path(const FvtaAttnDesc* desc, int want_c_col, int want_warp_h) {
+  int rc = attn_validate(desc);
+  if (rc) return rc;
+  return attn_pick_path(*desc, want_c_col != 0, want_warp_h != 0);
+}
 
 extern "C" int fvta_attn_fwd(const FvtaAttnDesc* desc, const float* hall, const uint8_t* hall_mask,
                              const float* hq, const uint8_t* hq_mask, const float* lq,
@@ -420,21 +431,18 @@ extern "C" int fvta_attn_fwd(const FvtaAttnDesc* desc, const float* hall, const 
   if (workspace_bytes < L.total * sizeof(float)) return FVTA_E_WORKSPACE;
   if (attn_tile_smem_bytes(d, L.JQP, L.Dp) > 227 * 1024) return FVTA_E_SHAPE;
   cudaStream_t st = (cudaStream_t)stream;
+  const int path = attn_pick_path(d, c_col != nullptr, warp_h != nullptr);
+  if (path < 0) return path;
   // question-attention shape (K = 1, JQ = 1, no time warp): one CTA per sample does everything
-  if (attn_small_ok(d) && warp_h == nullptr && c_col == nullptr && g_attn_stages == 7 && !fvta_force_ffma())
-    return attn_small_fwd(d, hall, hall_mask, hq, hq_mask, *params, g1_all, a_logits, st);
+  if (path == FVTA_PATH_SMALL) return attn_small_fwd(d, hall, hall_mask, hq, hq_mask, *params, g1_all, a_logits, st);
   float* ws = (float*)workspace;
-  const int stages = g_attn_stages;
-  if (stages & 1) {
-    rc = attn_prep_launch(d, L, *params, hq, lq, ws, st);
+  if (!d.ws_from_fwd) {
+    rc = attn_prep_launch(d, L, *params, hq, lq, ws, st, path == FVTA_PATH_TC);
     if (rc) return rc;
   }
-  if (warp_h == nullptr && !fvta_force_ffma()) {
-    // tensor-core path (attn_fwd_tc.cu) when the shape/flags are covered; 1 = not covered
-    rc = attn_fwd_tc_try(d, L, hall, hall_mask, hq_mask, ws, g1_all, a_logits, c_col, stats, st);
-    if (rc <= 0) return rc;
-  }
-  if (stages & 2) switch (L.JQP) {
+  if (path == FVTA_PATH_TC)
+    return attn_fwd_tc_launch(d, L, hall, hall_mask, hq_mask, ws, g1_all, a_logits, c_col, stats, st);
+  switch (L.JQP) {
     case 4: rc = launch_tile_fwd<1>(d, L, hall, hall_mask, hq_mask, ws, a_logits, c_col, warp_h, st); break;
     case 8: rc = launch_tile_fwd<2>(d, L, hall, hall_mask, hq_mask, ws, a_logits, c_col, warp_h, st); break;
     case 16: rc = launch_tile_fwd<4>(d, L, hall, hall_mask, hq_mask, ws, a_logits, c_col, warp_h, st); break;
@@ -444,8 +452,5 @@ extern "C" int fvta_attn_fwd(const FvtaAttnDesc* desc, const float* hall, const 
     default: return FVTA_E_SHAPE;
   }
   if (rc) return rc;
-  if (!(stages & 4)) return FVTA_OK;
   return attn_combine_launch(d, ws + L.part_stat, ws + L.part_o, g1_all, stats, L.nt, L.Dp, st);
 }
-
-extern "C" void fvta_attn_fwd_set_stages(int mask) { fvta::g_attn_stages = mask & 7; }

@@ -1,26 +1,34 @@
 // Focal visual-text attention forward on the 5th-generation tensor cores (sm_100a only).
 //
-// Same math, same outputs and the same tile-partial / combine protocol as attn_fwd.cu, but the
-// question x context contraction P[t,j] = h[t,:] . qeff[j,:] -- the part that makes the FFMA
-// version compute-bound at JQ/2 = 16 flop/B -- runs as tcgen05.mma tiles with the accumulator
-// in TMEM, and the context tile arrives by TMA.  One pass over hall:
+// Same math and outputs as attn_fwd.cu (model_v2.py:953-1009 time warp, :301-341 window, :210-298
+// attention_3d, :23-48 softmax/softsel, utils.py:210-213 exp_mask), ONE pass over hall, ONE launch
+// after the operand folding (the combine of the per-CTA partials runs in the last CTA of each sample).
 //
-//   TMA warp      : 3-stage ring of fp32 context tiles  [K modalities x TB positions x D]
-//                   (cp.async.bulk.tensor.3d, mbarrier complete_tx)
-//   4 math warps  : one thread per context row.  pass 1: gate / row statistics and the split of
-//                   the row into fp16 (hi, lo*2^11) operands written in the 128B-swizzled K-major
-//                   layout UMMA reads;   epilogue: TMEM -> registers, logits, mask, row max,
-//                   softmax weight;   pass 2: weighted sum of the (still resident) fp32 tile
-//   MMA warp      : one elected thread issues, per 16-wide k-step,
-//                     D[:, 0:64] += A_hi . [B_hi ; B_lo]^T   and   D[:,64:96] += A_lo . B_hi^T
-//                   so P = D0 + (D1 + D2) * 2^-11 carries ~22 mantissa bits (fp32 accumulate):
-//                   the 1e-4 parity bar holds where single-pass tf32/bf16 would not.
+// The question x context contraction P[t,j] = h[t,:] . qeff[j,:] -- what makes a CUDA-core version
+// compute-bound at JQ/2 = 16 flop/B -- runs as tcgen05.mma with BOTH the accumulator and the A
+// operand (the context rows) in tensor memory:
 //
-// The softmax over T needs no online rescaling here: this kernel is used when the logits are
-// bounded by 1 (tanh or cosine), so exp(m - 1) cannot overflow and every tile uses the fixed
-// reference maximum 1.  Masked rows get the weight 2^-100 instead of exp(-1e30 - 1) = 0: it is
-// absorbed exactly by any unmasked weight and reproduces TF's uniform softmax over a fully
-// masked sequence.
+//   A_hi = the fp32 row as it is: kind::tf32 reads the upper 19 bits (no conversion work at all)
+//   A_lo = fp16(x - tf32(x))      the 13 bits the tensor core drops, as a second operand
+//   P    = A_hi.B_hi + A_hi.B_lo   (kind::tf32, N = 64: [B_hi ; B_lo] = tf32(q), q - tf32(q))
+//        + A_lo.B_hi16             (kind::f16,  N = 32, accumulated into the B_lo columns)
+//   ~21 mantissa bits per product, fp32 accumulation: the 1e-4 parity bar holds where single-pass
+//   tf32 / bf16 would not (S = g.P + ... with |g| up to 7).
+//
+// Pipeline (one persistent CTA per SM, 18 warps, every hand-over is an mbarrier):
+//   warp 16      TMA      ring of fp32 context tiles [K modalities x TB positions x D]
+//                         (cp.async.bulk.tensor.3d, complete_tx; rows past T are zero-filled)
+//   warps 0-7    split    two threads per context row: row statistics (u.h^2, w_quad.h^2, w_lin.h),
+//                         A_lo, and tcgen05.st of both operands into TMEM (lane = row)
+//   warp 17      MMA      one thread: 13 tf32 + 7 f16 k-steps per tile at D = 100, commit -> acc_full
+//   warps 8-11   softmax  one thread per row: gate, tcgen05.ld of its 2 x 32 accumulator columns,
+//                         logits (MUFU tanh), exp_mask as a min with a per-column cap, row max,
+//                         softmax weight (fixed reference maximum 1: the logits are bounded)
+//   warps 12-15  wsum     weighted sum  o[k,:] += w.g.h  over the still resident fp32 tile, then
+//                         the stage goes back to the TMA warp
+// The softmax over T needs no online rescaling: this kernel is used when the logits are bounded by
+// 1 (tanh or cosine).  Masked rows get the weight 2^-100 instead of exp(-1e30 - 1) = 0: absorbed
+// exactly by any unmasked weight, and it reproduces TF's uniform softmax over a fully masked row.
 #include "common.cuh"
 #include "attn_tile.cuh"
 #include <cuda.h>
@@ -28,68 +36,88 @@
 
 namespace fvta {
 
-// Optional per-role timeline (build with -DFVTA_TC_TRACE, run tools/tc_trace.py): CTA (0,0) stores
-// the SM clock at each pipeline event of its first kTraceTiles tiles into g_tc_trace.
 #ifdef FVTA_TC_TRACE
 constexpr int kTraceTiles = 24;
-__device__ long long g_tc_trace[4][kTraceTiles][8];
+__device__ long long g_tc_trace[5][kTraceTiles][8];
 #define TC_TRACE(role, i, ev)                                                                     \
-  do { if (blockIdx.x == 0 && blockIdx.y == 0 && (i) < kTraceTiles && (threadIdx.x == 0 || threadIdx.x == 256 || threadIdx.x == 512 || threadIdx.x == 544)) \
+  do { if (blockIdx.x == 0 && blockIdx.y == 0 && (i) < kTraceTiles && (threadIdx.x & 127) == 0)   \
          g_tc_trace[role][i][ev] = clock64(); } while (0)
 #else
 #define TC_TRACE(role, i, ev) do {} while (0)
 #endif
 
-int attn_combine_launch(const FvtaAttnDesc& d, const float* part_stat, const float* part_o, float* g1_all,
-                        float* stats, int nt, int Dp, cudaStream_t st);
-extern int g_attn_stages;
-
-constexpr int kTcThreads = 576;  // warps 0-7 split, 8-15 softmax, warp 16 TMA, warp 17 MMA
-constexpr int kTcStages = 3;
-constexpr int kTcJQP = 32;       // question positions per tile (N of the MMA = 64 + 32)
-constexpr int kTcTmemCols = 256; // 2 accumulator buffers x 128 columns (96 used)
+constexpr int kTcThreads = 576;   // warps 0-7 split, 8-11 softmax, 12-15 wsum, 16 TMA, 17 MMA
+constexpr int kTcJQP = 32;        // question positions per tile (N of the MMAs: 64 and 32)
+constexpr int kTcTmemCols = 512;
+constexpr int kTcMaxStages = 6;
 constexpr float kMaskedWeight = 7.888609052210118e-31f;  // 2^-100
+#ifndef FVTA_TC_MIN_STAGES
+#define FVTA_TC_MIN_STAGES 4
+#endif
 
 struct TcPlan {
   int TB;           // context positions per tile
   int rows;         // K * TB <= 128
-  int KC;           // 64-wide fp16 K chunks (128-byte swizzle lines) = ceil(D / 64)
-  int ksteps;       // 16-wide MMA k-steps = ceil(D / 16)
+  int K32;          // tf32 k-steps (8 features)  = ceil(D / 8)
+  int K16;          // f16 k-steps (16 features)  = ceil(D / 16)
+  int C32;          // 32-feature (128-byte) chunks of the tf32 B image
+  int C16;          // 64-feature (128-byte) chunks of the f16 B image
+  int stages;       // fp32 ring depth
   int stage_bytes;  // fp32 tile, rounded to 128 B
   int tiles;        // tiles per sample
   int slabs;        // CTAs per sample
-  size_t smem;      // dynamic shared memory
+  int col_ahi, w_ahi, col_alo, w_alo;   // TMEM columns of the two A buffers (buffer b at col + b * w)
+  size_t smem;
 };
 
-__host__ __device__ inline size_t tc_smem_bytes(int KC, int stage_bytes, int Dp) {
-  size_t b = 0;
-  b += (size_t)2 * KC * 16384;                      // A_hi, A_lo
-  b += (size_t)KC * 8192;                           // [B_hi ; B_lo]
-  b += (size_t)kTcStages * stage_bytes;             // fp32 ring
-  b += (size_t)(3 * Dp + 2 * kTcJQP + 256 + 512 + 2 * 256 + 4 * 512) * sizeof(float);  // coef, col, cap, wg, mx, st, zq/red
-  b += 256;                                         // barriers, tmem pointer
-  return b;
+__host__ __device__ inline size_t tc_fixed_smem(const TcPlan& p, int Dp) {
+  return (size_t)p.C32 * 8192 + (size_t)p.C16 * 4096 + (size_t)(3 * Dp + 2 * kTcJQP) * 4 + 8192 /*zq*/ +
+         6144 /*stg*/ + 2560 /*red*/ + 1024 /*combine scratch*/ + 256 /*barriers*/;
 }
 
 static bool tc_make_plan(const FvtaAttnDesc& d, TcPlan& p) {
   if ((d.D & 3) != 0 || d.D > 128 || d.D < 8 || d.JQ > kTcJQP || d.K > 8) return false;
   const bool bounded = (d.simi == 4) || d.add_tanh;
   if (!bounded || d.time_warp_att) return false;
-  p.KC = (d.D + 63) / 64;
-  p.ksteps = (d.D + 15) / 16;
-  for (int TB = 128 / d.K; TB >= 4; --TB) {
-    p.TB = TB;
-    p.rows = d.K * TB;
-    p.stage_bytes = round_up(p.rows * d.D * 4, 128);
-    p.smem = tc_smem_bytes(p.KC, p.stage_bytes, round_up(d.D, 4));
-    if (p.smem <= 227 * 1024) break;
-    p.TB = 0;
+  p.K32 = (d.D + 7) / 8;
+  p.K16 = (d.D + 15) / 16;
+  p.C32 = (d.D + 31) / 32;
+  p.C16 = (d.D + 63) / 64;
+  p.w_ahi = 8 * p.K32;
+  p.w_alo = 8 * p.K16;
+  p.col_ahi = 128;
+  p.col_alo = p.col_ahi + 2 * p.w_ahi;
+  if (p.col_alo + 2 * p.w_alo > kTcTmemCols) return false;
+  const size_t fixed = tc_fixed_smem(p, round_up(d.D, 4));
+  const size_t budget = 227 * 1024;
+  int best_tb = 0, best_st = 0;
+#ifdef FVTA_TC_TB
+  const int tb_max = FVTA_TC_TB;
+#else
+  const int tb_max = 128 / d.K;
+#endif
+  for (int TB = tb_max; TB >= 2; --TB) {
+    const int sb = round_up(d.K * TB * d.D * 4, 128);
+    int st = (int)((budget - fixed) / (size_t)(sb + 512));
+    if (st > kTcMaxStages) st = kTcMaxStages;
+    if (st >= FVTA_TC_MIN_STAGES) { best_tb = TB; best_st = st; break; }
+    if (st >= 2 && best_tb == 0) { best_tb = TB; best_st = st; }   // deepest ring is not reachable: take the widest tile
   }
-  if (p.TB == 0) return false;
+  if (best_tb == 0) return false;
+  p.TB = best_tb;
+  p.stages = best_st;
+  p.rows = d.K * p.TB;
+  p.stage_bytes = round_up(p.rows * d.D * 4, 128);
+  p.smem = fixed + (size_t)p.stages * (p.stage_bytes + 512);
   p.tiles = (d.T + p.TB - 1) / p.TB;
-  int want = (148 + d.N - 1) / d.N;  // one CTA per SM
+  const int want = (148 + d.N - 1) / d.N;  // one CTA per SM
   p.slabs = want < 1 ? 1 : (want > p.tiles ? p.tiles : want);
   return true;
+}
+
+bool attn_tc_covers(const FvtaAttnDesc& d) {
+  TcPlan p;
+  return tc_make_plan(d, p);
 }
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -103,18 +131,27 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Waiting warps must not compete for issue slots with the warps they wait for (the scheduler
-// favours high warp ids, and a try_wait spin loop is always ready): back off between polls.
+// try_wait suspends the warp in hardware until the phase completes or the time hint passes, so
+// waiting warps do not compete for issue slots.  A wait that lasts two seconds is a pipeline bug:
+// trap (the launch fails with an error) instead of hanging the device.
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x4000;\n\t"
       "selp.u32 %0, 1, 0, P1;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned sleep_ns = 40) {
-  while (!mbar_try(bar, parity)) __nanosleep(sleep_ns);
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try(bar, parity)) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
@@ -127,32 +164,22 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] . B[smem]^T, M = 128
+__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// issue only; pair with tmem_ld_wait() before the registers are read
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -162,80 +189,111 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
 
 // K-major, 128B-swizzled operand: 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16, A/B = fp16 K-major, D = fp32, M = 128
-__device__ __forceinline__ uint32_t umma_idesc_f16(int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | (8u << 24); }
+// D = fp32, M = 128, A and B K-major; fmt 0 = fp16, 2 = tf32
+__device__ __forceinline__ uint32_t umma_idesc(int fmt, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
+}
 
 // MUFU.EX2 / MUFU.RCP; tanh(x) = 1 - 2 / (1 + 2^{2 log2(e) x}) built from them has |error| < 1e-6
 // and never exceeds 1 in magnitude
 __device__ __forceinline__ float exp2f_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// ---- B operand: [B_hi ; B_lo] as fp16, pre-swizzled, one image per sample ----------------------
-__global__ void attn_prep_qb(FvtaAttnDesc d, const float* __restrict__ qeffT, __half* __restrict__ qB, int Dp,
-                             int JQP, int KC) {
+// what kind::tf32 keeps of an fp32 operand (tools/umma_probe.cu: the tensor core truncates)
+__device__ __forceinline__ float tf32_part(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// ---- B operands, pre-swizzled, one image per sample (built by attn_prep_all, attn_fwd.cu) --------
+//   qB32: C32 chunks x 64 rows x 128 B: rows 0-31 tf32(qeff[j]), rows 32-63 qeff[j] - tf32(qeff[j])
+//   qB16: C16 chunks x 32 rows x 128 B: fp16(qeff[j])
+// 16-byte unit u of row n sits at unit (u ^ (n & 7)) of its 128-byte line.
+__global__ void attn_prep_images(FvtaAttnDesc d, const float* __restrict__ qeffT, uint8_t* __restrict__ qB32,
+                                 uint8_t* __restrict__ qB16, int* __restrict__ counters, int Dp, int JQP) {
   const int n = blockIdx.x;
-  const float* q = qeffT + (size_t)n * Dp * JQP;
-  uint8_t* out = reinterpret_cast<uint8_t*>(qB) + (size_t)n * KC * 8192;
-  for (int i = threadIdx.x; i < KC * 64 * 8; i += blockDim.x) {
-    const int c = i & 7, row = (i >> 3) & 63, kc = i >> 9;
+  const int C32 = (d.D + 31) / 32, C16 = (d.D + 63) / 64;
+  const float* qeffT_n = qeffT + (size_t)n * Dp * JQP;
+  uint8_t* qB32_n = qB32 + (size_t)n * C32 * 8192;
+  uint8_t* qB16_n = qB16 + (size_t)n * C16 * 4096;
+  if (threadIdx.x == 0) counters[n] = 0;
+  for (int i = threadIdx.x; i < C32 * 64 * 8; i += blockDim.x) {
+    const int u = i & 7, row = (i >> 3) & 63, c = i >> 9;
     const int j = row & 31;
     const bool lo = row >= 32;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int dd = c * 32 + u * 4 + e;
+      const float x = (dd < d.D && j < d.JQ) ? qeffT_n[(size_t)dd * JQP + j] : 0.f;
+      // round to nearest on the question side: the low 13 bits of `hi` are zero, so the tensor
+      // core's own truncation leaves it alone, and x - hi is exact in fp32
+      const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+      v[e] = lo ? x - hi : hi;
+    }
+    *reinterpret_cast<float4*>(qB32_n + c * 8192 + row * 128 + ((u ^ (row & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  for (int i = threadIdx.x; i < C16 * 32 * 8; i += blockDim.x) {
+    const int u = i & 7, row = (i >> 3) & 31, c = i >> 8;
     __half v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int dd = kc * 64 + c * 8 + e;
-      const float x = (dd < d.D && j < d.JQ) ? q[(size_t)dd * JQP + j] : 0.f;
-      const __half hi = __float2half_rn(x);
-      v[e] = lo ? __float2half_rn(x - __half2float(hi)) : hi;
+      const int dd = c * 64 + u * 8 + e;
+      v[e] = __float2half_rn((dd < d.D && row < d.JQ) ? qeffT_n[(size_t)dd * JQP + row] : 0.f);
     }
-    *reinterpret_cast<uint4*>(out + kc * 8192 + row * 128 + ((c ^ (row & 7)) << 4)) = *reinterpret_cast<uint4*>(v);
+    *reinterpret_cast<uint4*>(qB16_n + c * 4096 + row * 128 + ((u ^ (row & 7)) << 4)) = *reinterpret_cast<uint4*>(v);
   }
 }
 
 // ---- the fused kernel: grid (slabs, N) ----------------------------------------------------------
-// 18 warps.  Two threads share one context row so that each scheduler has four math warps to
-// interleave (the per-tile work is ~2.5k dependent-ish instructions per row):
-//   warps 0-7   "split"   : pass 1 of tile i+1 -- thread (r, h) converts the 16-byte chunks c = h, h+2, ...
-//                           of row r into the fp16 hi/lo operands and accumulates the row statistics
-//   warps 8-15  "softmax" : epilogue + pass 2 of tile i -- thread (r, h) owns accumulator columns
-//                           [16h, 16h+16) of TMEM lane r (warp & 3 selects the lane quadrant)
-//   warp 16 TMA producer,  warp 17 MMA issuer (+ TMEM allocation)
 template <bool HAS_LIN>
 __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     const __grid_constant__ CUtensorMap tmap, FvtaAttnDesc d, TcPlan pl, const uint8_t* __restrict__ hall_mask,
-    const uint8_t* __restrict__ hq_mask, const float* __restrict__ coef, const __half* __restrict__ qB,
-    const float* __restrict__ col, const float* __restrict__ zconst, float* __restrict__ a_logits,
-    float* __restrict__ c_col, float* __restrict__ part_stat, float* __restrict__ part_o, int Dp, int JQPg) {
-  // 1024-byte alignment is what the 128B swizzle pattern is defined against; keeping the pointers
-  // derived from the __shared__ symbol (no integer round-trip) lets ptxas emit LDS/STS, not LD/ST
+    const uint8_t* __restrict__ hq_mask, const float* __restrict__ coef, const uint8_t* __restrict__ qB32,
+    const uint8_t* __restrict__ qB16, const float* __restrict__ col, const float* __restrict__ zconst,
+    float* __restrict__ a_logits, float* __restrict__ c_col, float* __restrict__ part_stat,
+    float* __restrict__ part_o, int* __restrict__ counters, float* __restrict__ g1_all, float* __restrict__ stats,
+    int Dp, int JQPg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* a_hi = smem;
-  uint8_t* a_lo = a_hi + pl.KC * 16384;
-  uint8_t* b_s = a_lo + pl.KC * 16384;
-  uint8_t* ring = b_s + pl.KC * 8192;
-  float* coef_s = reinterpret_cast<float*>(ring + kTcStages * pl.stage_bytes);  // [3][Dp]
-  float* col_s = coef_s + 3 * Dp;      // [32]   per-question-word term + bias
-  float* cap_s = col_s + kTcJQP;       // [32]   +inf for a valid question word, -1e30 masked, -inf padding
-  float* wg_s = cap_s + kTcJQP;        // [2][128]     softmax weight * gate
-  float* mx_s = wg_s + 256;            // [2][2][128]  half-row maxima
-  float2* st_s = reinterpret_cast<float2*>(mx_s + 512);  // [2][128]  (c1, second coefficient) per row
-  float4* zq_s = reinterpret_cast<float4*>(st_s + 256);  // [2][2][128] half-row (zdot, quad, lin, -)
-  float* red_s = reinterpret_cast<float*>(zq_s);         // [5][256], aliases zq_s after the last tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(zq_s + 512);
-  uint64_t* full = bars;               // [3]  TMA -> split, softmax
-  uint64_t* empty = bars + 3;          // [3]  softmax -> TMA
-  uint64_t* a_ready = bars + 6;        // [2]  split -> MMA, one per 64-feature operand chunk
-  uint64_t* a_free = bars + 8;         // [2]  MMA -> split: the chunk's MMAs have read the operand
-  uint64_t* acc_full = bars + 10;      // [2]  MMA -> softmax (accumulator ready)
-  uint64_t* st_ready = bars + 12;      // [2]  split -> softmax (row coefficients)
-  uint64_t* ep_done = bars + 14;       // [2]  softmax -> split (accumulator + coefficient buffer free)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  const int S = pl.stages;
+  uint8_t* b32_s = smem;                                   // tf32 [B_hi ; B_lo], swizzled
+  uint8_t* b16_s = b32_s + pl.C32 * 8192;                  // f16 B_hi, swizzled
+  uint8_t* ring = b16_s + pl.C16 * 4096;                   // fp32 tiles
+  float* coef_s = reinterpret_cast<float*>(ring + (size_t)S * pl.stage_bytes);  // [3][Dp]
+  float* col_s = coef_s + 3 * Dp;        // [32]  per-question-word term + bias
+  float* cap_s = col_s + kTcJQP;         // [32]  +inf for a valid question word, -1e30 masked, -inf padding
+  float4* zq_s = reinterpret_cast<float4*>(cap_s + kTcJQP);   // [2][2][128] half-row (zdot, quad, lin, -)
+  float4* stg_s = zq_s + 512;            // [128][3] weighted-sum partials of the slab
+  float* red_s = reinterpret_cast<float*>(stg_s + 384);      // [5][128]
+  float* cmb_s = red_s + 640;            // [256] combine scratch
+  float* wg_s = cmb_s + 256;             // [S][128]  softmax weight * gate
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wg_s + S * 128);
+  uint64_t* full = bars;                              // [S]  TMA -> split
+  uint64_t* empty = bars + kTcMaxStages;              // [S]  wsum -> TMA
+  uint64_t* wg_ready = bars + 2 * kTcMaxStages;       // [S]  softmax -> wsum
+  uint64_t* a_ready = bars + 3 * kTcMaxStages;        // [2]  split -> MMA, softmax
+  uint64_t* acc_full = a_ready + 2;                   // [2]  MMA -> softmax
+  uint64_t* ep_done = a_ready + 4;                    // [2]  softmax -> split (TMEM buffers + zq free)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_ready + 6);
+  int* last_flag = reinterpret_cast<int*>(tmem_ptr + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slab = blockIdx.x, n = blockIdx.y;
@@ -245,8 +303,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   const int D = d.D, TB = pl.TB, rows = pl.rows;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 256); }
-    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(&a_ready[b2], 256); mbar_init(&a_free[b2], 1); mbar_init(&acc_full[b2], 1); mbar_init(&st_ready[b2], 256); mbar_init(&ep_done[b2], 256); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 128); mbar_init(&wg_ready[s], 128); }
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(&a_ready[b2], 256); mbar_init(&acc_full[b2], 1); mbar_init(&ep_done[b2], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 17) {
@@ -256,9 +314,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   }
   // per-sample constants
   {
-    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(qB) + (size_t)n * pl.KC * 8192);
-    uint4* dst = reinterpret_cast<uint4*>(b_s);
-    for (int i = threadIdx.x; i < pl.KC * 512; i += blockDim.x) dst[i] = src[i];
+    const uint4* s32 = reinterpret_cast<const uint4*>(qB32 + (size_t)n * pl.C32 * 8192);
+    const uint4* s16 = reinterpret_cast<const uint4*>(qB16 + (size_t)n * pl.C16 * 4096);
+    uint4* d32 = reinterpret_cast<uint4*>(b32_s);
+    uint4* d16 = reinterpret_cast<uint4*>(b16_s);
+    for (int i = threadIdx.x; i < pl.C32 * 512; i += blockDim.x) d32[i] = s32[i];
+    for (int i = threadIdx.x; i < pl.C16 * 256; i += blockDim.x) d16[i] = s16[i];
     for (int i = threadIdx.x; i < 3 * Dp; i += blockDim.x) coef_s[i] = coef[i];
     for (int j = threadIdx.x; j < kTcJQP; j += blockDim.x) {
       col_s[j] = j < JQPg ? col[(size_t)n * JQPg + j] : 0.f;
@@ -276,82 +337,55 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     // ===== TMA producer =====
     if (lane == 0) {
       for (int i = 0; i < ntile; ++i) {
-        const int s = i % kTcStages;
-        mbar_wait(&empty[s], ((i / kTcStages) & 1) ^ 1, 200);
+        const int s = i % S;
+        if (i >= S) mbar_wait(&empty[s], ((i / S) - 1) & 1);
         TC_TRACE(0, i, 0);
         mbar_expect_tx(&full[s], (uint32_t)(rows * D * 4));
-        tma_load_3d(ring + s * pl.stage_bytes, &tmap, &full[s], 0, (tile_begin + i) * TB, n * d.K);
+        tma_load_3d(ring + (size_t)s * pl.stage_bytes, &tmap, &full[s], 0, (tile_begin + i) * TB, n * d.K);
       }
     }
   } else if (warp == 17) {
     // ===== MMA issuer =====
-    // per k-step:  D[:, 0:64] += A_hi . [B_hi ; B_lo]^T   and   D[:, 32:64] += A_lo . B_hi^T
-    // so the epilogue adds two 32-column groups: P = D[:, 0:32] + D[:, 32:64]
+    //   acc[:, 0:64]  = A_hi . [B_hi ; B_lo]^T   (kind::tf32)
+    //   acc[:, 32:64] += A_lo . B_hi16^T          (kind::f16)       P = acc[:, 0:32] + acc[:, 32:64]
     if (lane == 0) {
-      const uint32_t idesc64 = umma_idesc_f16(64), idesc32 = umma_idesc_f16(32);
-      const uint32_t a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo), b_u = smem_u32(b_s);
+      const uint32_t id32 = umma_idesc(2, 64), id16 = umma_idesc(0, 32);
+      const uint32_t b32_u = smem_u32(b32_s), b16_u = smem_u32(b16_s);
       for (int i = 0; i < ntile; ++i) {
-        const uint32_t acc = tmem_base + (uint32_t)((i & 1) * 128);
-        for (int kc = 0; kc < pl.KC; ++kc) {
-          mbar_wait(&a_ready[kc], i & 1, 60);
-          TC_TRACE(1, i, kc);
-          tc_fence_after();
-          const int ks_end = min(pl.ksteps, kc * 4 + 4);
-          for (int ks = kc * 4; ks < ks_end; ++ks) {
-            const uint32_t off = (uint32_t)(kc * 16384 + (ks & 3) * 32);
-            const uint32_t boff = (uint32_t)(kc * 8192 + (ks & 3) * 32);
-            umma_f16(acc, umma_desc_sw128(a_hi_u + off), umma_desc_sw128(b_u + boff), idesc64, ks > 0);
-            umma_f16(acc + 32, umma_desc_sw128(a_lo_u + off), umma_desc_sw128(b_u + boff), idesc32, 1u);
-          }
-          umma_commit(&a_free[kc]);   // the split warps may overwrite this chunk for the next tile
-        }
-        umma_commit(&acc_full[i & 1]);
-        TC_TRACE(1, i, 2);
+        const int b2 = i & 1;
+        const uint32_t acc = tmem_base + (uint32_t)(b2 * 64);
+        const uint32_t a_hi = tmem_base + (uint32_t)(pl.col_ahi + b2 * pl.w_ahi);
+        const uint32_t a_lo = tmem_base + (uint32_t)(pl.col_alo + b2 * pl.w_alo);
+        mbar_wait(&a_ready[b2], (i >> 1) & 1);
+        TC_TRACE(1, i, 0);
+        tc_fence_after();
+        for (int ks = 0; ks < pl.K32; ++ks)
+          umma_ts_tf32(acc, a_hi + 8 * ks, umma_desc_sw128(b32_u + (uint32_t)((ks >> 2) * 8192 + (ks & 3) * 32)), id32, ks > 0);
+        for (int ks = 0; ks < pl.K16; ++ks)
+          umma_ts_f16(acc + 32, a_lo + 8 * ks, umma_desc_sw128(b16_u + (uint32_t)((ks >> 2) * 4096 + (ks & 3) * 32)), id16, 1u);
+        umma_commit(&acc_full[b2]);
+        TC_TRACE(1, i, 1);
       }
     }
   } else if (warp < 8) {
     // ===== split warps: threads (r, 0) and (r, 1) share context row r = k*TB + tt =====
     const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
-    const bool active = r < rows;
-    const int k = active ? r / TB : 0, tt = active ? r - k * TB : 0;
-    const int nch = pl.ksteps * 2;   // 16-byte (8 x fp16) chunks the MMA reads
-    const int nfull = D >> 3;        // chunks holding 8 real features
-    uint8_t* ahi_row = a_hi + r * 128;
-    uint8_t* alo_row = a_lo + r * 128;
-    const float zc = d.use_time_warp ? zconst[n] : 0.f;
-    uint32_t sw[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) sw[j] = (uint32_t)(((h + 2 * j) ^ (r & 7)) << 4);
+    const int roff = (r < rows ? r : 0) * D;        // idle lanes read row 0: their TMEM rows are never used
+    const int OT = 2 * pl.K16;                      // 8-feature groups ("octs") covering both operands
+    const int o_begin = h ? OT / 2 : 0, o_end = h ? OT : OT / 2;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = 0; i < ntile; ++i) {
-      const int s = i % kTcStages, b2 = i & 1;
+      const int s = i % S, b2 = i & 1;
       TC_TRACE(2, i, 0);
-      mbar_wait(&full[s], (i / kTcStages) & 1);
-      if (i >= 2) mbar_wait(&ep_done[b2], ((i - 2) >> 1) & 1);             // softmax(i-2) released buffers b2
+      mbar_wait(&full[s], (i / S) & 1);
+      if (i >= 2) mbar_wait(&ep_done[b2], ((i - 2) >> 1) & 1);   // softmax(i-2) has drained buffers b2
       TC_TRACE(2, i, 1);
+      const float* hrow = reinterpret_cast<const float*>(ring + (size_t)s * pl.stage_bytes) + roff;
+      const uint32_t colA = lane_base + (uint32_t)(pl.col_ahi + b2 * pl.w_ahi);
+      const uint32_t colL = lane_base + (uint32_t)(pl.col_alo + b2 * pl.w_alo);
       // packed fp32x2 arithmetic (FFMA2/FMUL2); two accumulator sets keep the dependent chains short
-      float2 zdA = make_float2(0.f, 0.f), qdA = make_float2(0.f, 0.f), lnA = make_float2(0.f, 0.f);
-      float2 zdB = make_float2(0.f, 0.f), qdB = make_float2(0.f, 0.f), lnB = make_float2(0.f, 0.f);
-      const float* hrow = reinterpret_cast<const float*>(ring + s * pl.stage_bytes) + (size_t)r * D;
-      const float2 neg1 = make_float2(-1.f, -1.f);
-      auto split_store = [&](uint32_t off, const float4& v0, const float4& v1) {
-        const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w);
-        const __half2 h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
-        // residual x - fp16(x) is exact in fp32; below 2^-14 it lands on fp16 subnormals whose
-        // 2^-25 absolute rounding is under the fp32 rounding of the operand itself
-        const float2 r0 = __ffma2_rn(__half22float2(h0), neg1, make_float2(v0.x, v0.y));
-        const float2 r1 = __ffma2_rn(__half22float2(h1), neg1, make_float2(v0.z, v0.w));
-        const float2 r2 = __ffma2_rn(__half22float2(h2), neg1, make_float2(v1.x, v1.y));
-        const float2 r3 = __ffma2_rn(__half22float2(h3), neg1, make_float2(v1.z, v1.w));
-        const __half2 l0 = __floats2half2_rn(r0.x, r0.y), l1 = __floats2half2_rn(r1.x, r1.y);
-        const __half2 l2 = __floats2half2_rn(r2.x, r2.y), l3 = __floats2half2_rn(r3.x, r3.y);
-        uint4 ph, plo;
-        ph.x = *reinterpret_cast<const uint32_t*>(&h0); ph.y = *reinterpret_cast<const uint32_t*>(&h1);
-        ph.z = *reinterpret_cast<const uint32_t*>(&h2); ph.w = *reinterpret_cast<const uint32_t*>(&h3);
-        plo.x = *reinterpret_cast<const uint32_t*>(&l0); plo.y = *reinterpret_cast<const uint32_t*>(&l1);
-        plo.z = *reinterpret_cast<const uint32_t*>(&l2); plo.w = *reinterpret_cast<const uint32_t*>(&l3);
-        *reinterpret_cast<uint4*>(ahi_row + off) = ph;
-        *reinterpret_cast<uint4*>(alo_row + off) = plo;
-      };
+      float2 zdA = make_float2(0.f, 0.f), qdA = zdA, lnA = zdA, zdB = zdA, qdB = zdA, lnB = zdA;
       auto stats4 = [&](int d0, const float4& v, float2& zd, float2& qd, float2& ln) {
         const float4 cu = *reinterpret_cast<const float4*>(coef_s + d0);
         const float4 cq = *reinterpret_cast<const float4*>(coef_s + 2 * Dp + d0);
@@ -367,164 +401,135 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
           ln = __ffma2_rn(make_float2(cl.z, cl.w), a23, ln);
         }
       };
-      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int kc = 0; kc < pl.KC; ++kc) {
-        if (i >= 1) mbar_wait(&a_free[kc], (i - 1) & 1);   // MMA(i-1) has read this operand chunk
-        TC_TRACE(2, i, 2 + 2 * kc);
-        if (active) {
-          const int c_end = min(nch, kc * 8 + 8);
-          // this thread's chunks of the 64-feature group: c = 8 kc + h + 2 j, swizzled 16-byte slot sw[j]
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c = kc * 8 + h + 2 * j;
-            if (c < c_end) {
-              const uint32_t off = (uint32_t)(kc * 16384) + sw[j];
-              if (c < nfull) {
-                const float4 v0 = *reinterpret_cast<const float4*>(hrow + c * 8);
-                const float4 v1 = *reinterpret_cast<const float4*>(hrow + c * 8 + 4);
-                stats4(c * 8, v0, zdA, qdA, lnA);
-                stats4(c * 8 + 4, v1, zdB, qdB, lnB);
-                split_store(off, v0, v1);
-              } else {  // D % 8 == 4 leaves a half chunk; the rest is zero padding up to the k-step
-                float4 v0 = zero4;
-                if (c * 8 < D) { v0 = *reinterpret_cast<const float4*>(hrow + c * 8); stats4(c * 8, v0, zdA, qdA, lnA); }
-                split_store(off, v0, zero4);
-              }
-            }
-          }
-        }
-        TC_TRACE(2, i, 3 + 2 * kc);
-        fence_async_smem();   // written through the generic proxy; UMMA reads via the async proxy
-        mbar_arrive(&a_ready[kc]);
+      // residual the tensor core drops, as two packed fp16: exact subtraction, fp16 rounding 2^-11 of it
+      auto lo2 = [&](float a, float b) -> uint32_t {
+        const float2 rr = __ffma2_rn(make_float2(tf32_part(a), tf32_part(b)), make_float2(-1.f, -1.f), make_float2(a, b));
+        const __half2 p = __floats2half2_rn(rr.x, rr.y);
+        return *reinterpret_cast<const uint32_t*>(&p);
+      };
+      auto load4 = [&](int d0) -> float4 { return d0 < D ? *reinterpret_cast<const float4*>(hrow + d0) : zero4; };
+#pragma unroll 1
+      for (int o = o_begin; o < o_end; o += 2) {
+        const bool two = o + 1 < o_end;
+        const int d0 = o * 8;
+        const float4 v0 = load4(d0), v1 = load4(d0 + 4);
+        const float4 v2 = two ? load4(d0 + 8) : zero4, v3 = two ? load4(d0 + 12) : zero4;
+        if (d0 < D) stats4(d0, v0, zdA, qdA, lnA);
+        if (d0 + 4 < D) stats4(d0 + 4, v1, zdB, qdB, lnB);
+        if (two && d0 + 8 < D) stats4(d0 + 8, v2, zdA, qdA, lnA);
+        if (two && d0 + 12 < D) stats4(d0 + 12, v3, zdB, qdB, lnB);
+        uint32_t hi[16], lo[8];
+        hi[0] = __float_as_uint(v0.x); hi[1] = __float_as_uint(v0.y); hi[2] = __float_as_uint(v0.z); hi[3] = __float_as_uint(v0.w);
+        hi[4] = __float_as_uint(v1.x); hi[5] = __float_as_uint(v1.y); hi[6] = __float_as_uint(v1.z); hi[7] = __float_as_uint(v1.w);
+        hi[8] = __float_as_uint(v2.x); hi[9] = __float_as_uint(v2.y); hi[10] = __float_as_uint(v2.z); hi[11] = __float_as_uint(v2.w);
+        hi[12] = __float_as_uint(v3.x); hi[13] = __float_as_uint(v3.y); hi[14] = __float_as_uint(v3.z); hi[15] = __float_as_uint(v3.w);
+        lo[0] = lo2(v0.x, v0.y); lo[1] = lo2(v0.z, v0.w); lo[2] = lo2(v1.x, v1.y); lo[3] = lo2(v1.z, v1.w);
+        lo[4] = lo2(v2.x, v2.y); lo[5] = lo2(v2.z, v2.w); lo[6] = lo2(v3.x, v3.y); lo[7] = lo2(v3.z, v3.w);
+        // all conditions below are warp-uniform (o and h are): the stores are warp-collective
+        if (two && o + 1 < pl.K32) tmem_st16(colA + 8 * o, hi);
+        else if (o < pl.K32) tmem_st8(colA + 8 * o, hi);
+        if (two) tmem_st8(colL + 4 * o, lo);
+        else tmem_st4(colL + 4 * o, lo);
       }
       const float2 zd2 = __fadd2_rn(zdA, zdB), qd2 = __fadd2_rn(qdA, qdB), ln2 = __fadd2_rn(lnA, lnB);
-      const float zdot = zd2.x + zd2.y, quad = qd2.x + qd2.y, lin = ln2.x + ln2.y;
-      zq_s[(b2 * 2 + h) * 128 + r] = make_float4(zdot, quad, lin, 0.f);
-      named_bar_sync(1, 256);
-      TC_TRACE(2, i, 6);
-      if (h == 0 && active) {
-        const float4* zq0 = zq_s + (b2 * 2) * 128;
-        const float4* zq1 = zq0 + 128;
-        const float4 p0 = zq0[r], p1 = zq1[r];
-        const int t = (tile_begin + i) * TB + tt;
-        float g = 1.f;
-        if (d.use_time_warp) {
-          float z = zc;
-          for (int kk = 0; kk < d.K; ++kk) z += zq0[kk * TB + tt].x + zq1[kk * TB + tt].x;
-          const int tc = t < d.T ? t : d.T - 1;
-          const float tz = 1.f - 2.f * rcp_approx(exp2f_approx(z * 2.885390081777927f) + 1.f);   // tanh(z)
-          g = tz * window_count(tc, d.T, d.warp_type, d.window);
-          if (c_col != nullptr && k == 0 && t < d.T) c_col[(size_t)n * d.T + t] = tz;
-        }
-        float c1, c0v;
-        row_coefs(d, g, p0.z + p1.z, p0.y + p1.y, c1, c0v);
-        // simi 1-3: c1 == g, second slot carries c0;  cosine: c0 == 0, second slot carries g
-        st_s[b2 * 128 + r] = make_float2(c1, d.simi == 4 ? g : c0v);
-      }
-      mbar_arrive(&st_ready[b2]);
-      TC_TRACE(2, i, 7);
+      zq_s[(b2 * 2 + h) * 128 + r] = make_float4(zd2.x + zd2.y, qd2.x + qd2.y, ln2.x + ln2.y, 0.f);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&a_ready[b2]);
+      TC_TRACE(2, i, 2);
     }
-  } else {
-    // ===== softmax warps: thread (r, h) owns columns [16h, 16h+16) of accumulator row r =====
-    const int tid = threadIdx.x - 256;
-    const int r = tid & 127, h = tid >> 7;
-    const int wq = warp & 3;
+  } else if (warp < 12) {
+    // ===== softmax warps: thread r owns accumulator row r (TMEM lane r) =====
+    const int r = threadIdx.x - 256;
     const bool active = r < rows;
     const int k = active ? r / TB : 0, tt = active ? r - k * TB : 0;
     const bool tanh_on = d.add_tanh && d.simi != 4;
     const bool cosine = d.simi == 4;
-    // pass 2 mapping: thread u = part * D4 + d4 owns the float4 feature group d4 over the tile rows
-    // [wr0, wr1) (rows are k-major: r = k * TB + tt).  A range never spans more than two modalities
-    // (its length <= TB because K <= 256 / D4), hence two accumulators.
-    const int D4 = D >> 2;
-    const int nparts = 256 / D4;
-    const bool ws_on = tid < nparts * D4;
-    const int ws_d4 = tid % D4, ws_part = tid / D4;
-    const int wr0 = ws_on ? (ws_part * rows) / nparts : 0;
-    const int wr1 = ws_on ? ((ws_part + 1) * rows) / nparts : 0;
-    const int ws_kb = (wr0 / TB + 1) * TB;                 // first row of the next modality
-    const int ws_n0 = max(min(wr1, ws_kb) - wr0, 0);       // rows accumulated into o_acc[0]
-    const int ws_n1 = (wr1 - wr0) - ws_n0;                 //                      into o_acc[1]
-    const int ws_off = wr0 * D + ws_d4 * 4;
-    float4 o_acc[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) o_acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float zc = d.use_time_warp ? zconst[n] : 0.f;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     float l_acc = 0.f, smax = -INFINITY, ties = 0.f, am_t = 3.0e38f, am_j = 0.f;
-    const float4* col4 = reinterpret_cast<const float4*>(col_s + 16 * h);
-    const float4* cap4 = reinterpret_cast<const float4*>(cap_s + 16 * h);
-
+    const float4* col4 = reinterpret_cast<const float4*>(col_s);
+    const float4* cap4 = reinterpret_cast<const float4*>(cap_s);
     for (int i = 0; i < ntile; ++i) {
-      const int s = i % kTcStages, b2 = i & 1;
+      const int s = i % S, b2 = i & 1;
       const int t = (tile_begin + i) * TB + tt;
       const bool in_range = active && t < d.T;
-      // issue the mask load before blocking on the barriers
       uint8_t mh_u = 1;
       if (in_range && d.has_mask) mh_u = hall_mask[((size_t)n * d.K + k) * d.T + t];
       TC_TRACE(3, i, 0);
-      mbar_wait(&st_ready[b2], (i >> 1) & 1);
+      mbar_wait(&a_ready[b2], (i >> 1) & 1);     // the split warps' row statistics are visible
+      const float4* zq0 = zq_s + (b2 * 2) * 128;
+      const float4* zq1 = zq0 + 128;
+      const float4 p0 = zq0[active ? r : 0], p1 = zq1[active ? r : 0];
+      float g = 1.f;
+      if (d.use_time_warp) {
+        float z = zc;
+        for (int kk = 0; kk < d.K; ++kk) z += zq0[kk * TB + tt].x + zq1[kk * TB + tt].x;
+        const int tc = t < d.T ? t : d.T - 1;
+        const float tz = 1.f - 2.f * rcp_approx(exp2f_approx(z * 2.885390081777927f) + 1.f);   // tanh(z)
+        g = tz * window_count(tc, d.T, d.warp_type, d.window);
+        if (c_col != nullptr && k == 0 && in_range) c_col[(size_t)n * d.T + t] = tz;
+      }
+      float c1, c0v;
+      row_coefs(d, g, p0.z + p1.z, p0.y + p1.y, c1, c0v);
+      const float p_c0 = cosine ? 0.f : c0v;
+      const bool mh = in_range && mh_u != 0;
       mbar_wait(&acc_full[b2], (i >> 1) & 1);
       TC_TRACE(3, i, 1);
       tc_fence_after();
-      const float2 st = st_s[b2 * 128 + r];
-      const float p_c1 = st.x, p_c0 = cosine ? 0.f : st.y, p_g = cosine ? st.y : st.x;
-      const float* tile = reinterpret_cast<const float*>(ring + s * pl.stage_bytes);
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(b2 * 128 + 16 * h);
-      float P[16];
-      {
-        uint32_t x0[16], x1[16];
-        tmem_ld16_issue(taddr, x0);
-        tmem_ld16_issue(taddr + 32, x1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) P[j] = __uint_as_float(x0[j]) + __uint_as_float(x1[j]);
-      }
-      tc_fence_before();
-      TC_TRACE(3, i, 2);
-      const bool mh = in_range && mh_u != 0;
-      // branch-free logits: P[] is overwritten by the masked logits a[].  |th| <= 1 here, so
-      // th + (-1e30) == -1e30 exactly: exp_mask is a min with the per-column cap
+      const uint32_t taddr = lane_base + (uint32_t)(b2 * 64);
+      float a[32];
       float m = -INFINITY;
-      const float2 c1c1 = make_float2(p_c1, p_c1), c0c0 = make_float2(p_c0, p_c0);
+      const float2 c1c1 = make_float2(c1, c1), c0c0 = make_float2(p_c0, p_c0);
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const float4 cq = col4[j >> 2], kq = cap4[j >> 2];
-        const float colr0 = (j & 2) ? cq.z : cq.x, colr1 = (j & 2) ? cq.w : cq.y;
-        const float capr0 = (j & 2) ? kq.z : kq.x, capr1 = (j & 2) ? kq.w : kq.y;
-        float2 S = __fadd2_rn(__ffma2_rn(c1c1, make_float2(P[j], P[j + 1]), c0c0), make_float2(colr0, colr1));
-        if (tanh_on) {  // tanh(x) = 1 - 2 / (1 + e^{2x}), packed
-          const float2 e2 = __fmul2_rn(S, make_float2(2.885390081777927f, 2.885390081777927f));  // 2*log2(e)
-          const float2 den = __fadd2_rn(make_float2(exp2f_approx(e2.x), exp2f_approx(e2.y)), make_float2(1.f, 1.f));
-          S = __ffma2_rn(make_float2(rcp_approx(den.x), rcp_approx(den.y)), make_float2(-2.f, -2.f), make_float2(1.f, 1.f));
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t x0[16], x1[16];
+        tmem_ld16_issue(taddr + 16 * hh, x0);
+        tmem_ld16_issue(taddr + 32 + 16 * hh, x1);
+        tmem_ld_wait();
+        if (hh == 1) {           // both accumulator halves are in registers: the buffers can be refilled
+          tc_fence_before();
+          mbar_arrive(&ep_done[b2]);
         }
-        const float a0 = fminf(S.x, capr0);
-        const float a1 = fminf(S.y, capr1);
-        P[j] = a0; P[j + 1] = a1;
-        m = fmaxf(m, fmaxf(a0, a1));
+        // branch-free logits.  |tanh| <= 1, so th + (-1e30) == -1e30 exactly: exp_mask is a min
+        // with the per-column cap
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const float4 cq = col4[(16 * hh + j) >> 2], kq = cap4[(16 * hh + j) >> 2];
+          const float colr0 = (j & 2) ? cq.z : cq.x, colr1 = (j & 2) ? cq.w : cq.y;
+          const float capr0 = (j & 2) ? kq.z : kq.x, capr1 = (j & 2) ? kq.w : kq.y;
+          const float2 P = __fadd2_rn(make_float2(__uint_as_float(x0[j]), __uint_as_float(x0[j + 1])),
+                                      make_float2(__uint_as_float(x1[j]), __uint_as_float(x1[j + 1])));
+          float2 Sv = __fadd2_rn(__ffma2_rn(c1c1, P, c0c0), make_float2(colr0, colr1));
+          if (tanh_on) {  // tanh(x) = 1 - 2 / (1 + e^{2x}), packed
+            const float2 e2 = __fmul2_rn(Sv, make_float2(2.885390081777927f, 2.885390081777927f));  // 2*log2(e)
+            const float2 den = __fadd2_rn(make_float2(exp2f_approx(e2.x), exp2f_approx(e2.y)), make_float2(1.f, 1.f));
+            Sv = __ffma2_rn(make_float2(rcp_approx(den.x), rcp_approx(den.y)), make_float2(-2.f, -2.f), make_float2(1.f, 1.f));
+          }
+          const float a0 = fminf(Sv.x, capr0), a1 = fminf(Sv.y, capr1);
+          a[16 * hh + j] = a0; a[16 * hh + j + 1] = a1;
+          m = fmaxf(m, fmaxf(a0, a1));
+        }
       }
       if (__any_sync(0xffffffffu, !mh) && !mh) {   // masked context row: every logit is -1e30 (padding columns stay -inf)
         m = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { P[j] = fminf(cap_s[16 * h + j], FVTA_VERY_NEGATIVE); m = fmaxf(m, P[j]); }
+        for (int j = 0; j < 32; ++j) { a[j] = fminf(cap_s[j], FVTA_VERY_NEGATIVE); m = fmaxf(m, a[j]); }
       }
-      TC_TRACE(3, i, 3);
-      mx_s[(b2 * 2 + h) * 128 + r] = m;
+      TC_TRACE(3, i, 2);
       if (a_logits != nullptr && in_range) {
-        float* arow = a_logits + (((size_t)n * d.K + k) * d.T + t) * d.JQ + 16 * h;
+        float* arow = a_logits + (((size_t)n * d.K + k) * d.T + t) * d.JQ;
         if ((d.JQ & 3) == 0) {
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            if (16 * h + j4 * 4 < d.JQ)
-              *reinterpret_cast<float4*>(arow + j4 * 4) = make_float4(P[j4 * 4], P[j4 * 4 + 1], P[j4 * 4 + 2], P[j4 * 4 + 3]);
+          for (int j4 = 0; j4 < 8; ++j4)
+            if (j4 * 4 < d.JQ)
+              *reinterpret_cast<float4*>(arow + j4 * 4) = make_float4(a[j4 * 4], a[j4 * 4 + 1], a[j4 * 4 + 2], a[j4 * 4 + 3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (16 * h + j < d.JQ) arow[j] = P[j];
+          for (int j = 0; j < 32; ++j)
+            if (j < d.JQ) arow[j] = a[j];
         }
       }
-      named_bar_sync(2, 256);
-      TC_TRACE(3, i, 4);
-      m = fmaxf(m, mx_s[(b2 * 2 + (h ^ 1)) * 128 + r]);   // full-row maximum
-      float w = 0.f;
       // a new (or tied) running maximum is rare after the first tiles: keep the bookkeeping behind a
       // warp-uniform branch so it costs nothing when no lane needs it
       const bool newmax = in_range && m >= smax;
@@ -533,27 +538,68 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
           if (m > smax) { smax = m; ties = 0.f; am_t = 3.0e38f; }
           int cnt = 0, jm = -1;
 #pragma unroll
-          for (int j = 15; j >= 0; --j) {
-            const bool hit = P[j] == m;
+          for (int j = 31; j >= 0; --j) {
+            const bool hit = a[j] == m;
             cnt += hit ? 1 : 0;
             jm = hit ? j : jm;
           }
           ties += (float)cnt;
-          if (jm >= 0 && (float)t < am_t) { am_t = (float)t; am_j = (float)(16 * h + jm); }
+          if (jm >= 0 && (float)t < am_t) { am_t = (float)t; am_j = (float)jm; }
         }
       }
+      float w = 0.f;
       if (in_range) {
         w = (m <= -1e29f) ? kMaskedWeight : expf(m - 1.f);
-        if (h == 0) l_acc += w;
+        l_acc += w;
       }
-      float* wg = wg_s + b2 * 128;
-      if (h == 0) wg[r] = w * p_g;
-      named_bar_sync(3, 256);
-      TC_TRACE(3, i, 5);
-      // pass 2: o[k][d4] += sum_rows (w*g) * h over this thread's row range, four rows per batch
+      wg_s[s * 128 + r] = w * g;
+      mbar_arrive(&wg_ready[s]);
+      TC_TRACE(3, i, 3);
+    }
+    // ---- slab statistics: per-modality reductions over the TB threads owning its rows ----
+    red_s[r] = l_acc; red_s[128 + r] = smax; red_s[256 + r] = ties; red_s[384 + r] = am_t; red_s[512 + r] = am_j;
+    named_bar_sync(1, 128);
+    if (r < d.K) {
+      float l = 0.f, sm = -INFINITY, ti = 0.f, at = 3.0e38f, aj = 0.f;
+      for (int t2 = 0; t2 < TB; ++t2) {
+        const int rr = r * TB + t2;
+        l += red_s[rr];
+        const float v = red_s[128 + rr];
+        if (v > sm) { sm = v; ti = 0.f; at = 3.0e38f; }
+        if (v == sm) {
+          ti += red_s[256 + rr];
+          if (red_s[384 + rr] < at) { at = red_s[384 + rr]; aj = red_s[512 + rr]; }
+        }
+      }
+      float* ps = part_stat + (((size_t)n * pl.slabs + slab) * d.K + r) * kPartW;
+      ps[0] = 1.f; ps[1] = l; ps[2] = sm; ps[3] = ti; ps[4] = at; ps[5] = aj; ps[6] = 0.f; ps[7] = 0.f;
+      __threadfence();
+    }
+  } else {
+    // ===== wsum warps: o[k][d4] += sum_rows (w*g) * h; thread u = part * D4 + d4 owns the float4 feature
+    // group d4 over the tile rows [wr0, wr1), which span at most three modalities =====
+    const int u = threadIdx.x - 384;
+    const int D4 = D >> 2;
+    const int nparts = 128 / D4;
+    const bool ws_on = u < nparts * D4;
+    const int ws_d4 = u % D4, ws_part = u / D4;
+    const int wr0 = ws_on ? (ws_part * rows) / nparts : 0;
+    const int wr1 = ws_on ? ((ws_part + 1) * rows) / nparts : 0;
+    const int kb1 = (wr0 / TB + 1) * TB;                      // first row of the next modality
+    const int e0 = min(wr1, kb1), e1 = min(wr1, kb1 + TB);
+    const int ws_n0 = max(e0 - wr0, 0), ws_n1 = max(e1 - e0, 0), ws_n2 = max(wr1 - e1, 0);
+    const int ws_off = wr0 * D + ws_d4 * 4;
+    float4 o_acc[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) o_acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < ntile; ++i) {
+      const int s = i % S;
+      TC_TRACE(4, i, 0);
+      mbar_wait(&wg_ready[s], (i / S) & 1);
+      TC_TRACE(4, i, 1);
       if (ws_on) {
-        const float* hp = tile + ws_off;
-        const float* wp = wg + wr0;
+        const float* hp = reinterpret_cast<const float*>(ring + (size_t)s * pl.stage_bytes) + ws_off;
+        const float* wp = wg_s + s * 128 + wr0;
         auto wsum = [&](int nrow, float4& acc) {
           float2 oa = make_float2(acc.x, acc.y), ob = make_float2(acc.z, acc.w);
           int t2 = 0;
@@ -585,68 +631,116 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
           acc = make_float4(oa.x, oa.y, ob.x, ob.y);
         };
         wsum(ws_n0, o_acc[0]);
-        TC_TRACE(3, i, 6);
         wsum(ws_n1, o_acc[1]);
+        wsum(ws_n2, o_acc[2]);
       }
       mbar_arrive(&empty[s]);
-      mbar_arrive(&ep_done[b2]);
-      TC_TRACE(3, i, 7);
+      TC_TRACE(4, i, 2);
     }
-    // ---- slab partials: per-modality reductions over the 2*TB threads owning its rows ----
-    // (red_s aliases zq_s: the split warps finished their last tile before st_ready of that tile)
-    red_s[tid] = l_acc; red_s[256 + tid] = smax; red_s[512 + tid] = ties; red_s[768 + tid] = am_t; red_s[1024 + tid] = am_j;
-    named_bar_sync(2, 256);
-    if (tid < d.K) {
-      float l = 0.f, sm = -INFINITY, ti = 0.f, at = 3.0e38f, aj = 0.f;
-      for (int hh = 0; hh < 2; ++hh)
-        for (int t2 = 0; t2 < TB; ++t2) {
-          const int rr = hh * 128 + tid * TB + t2;
-          l += red_s[rr];
-          const float v = red_s[256 + rr];
-          if (v > sm) { sm = v; ti = 0.f; at = 3.0e38f; }
-          if (v == sm) {
-            ti += red_s[512 + rr];
-            if (red_s[768 + rr] < at) { at = red_s[768 + rr]; aj = red_s[1024 + rr]; }
-          }
-        }
-      float* ps = part_stat + (((size_t)n * pl.slabs + slab) * d.K + tid) * kPartW;
-      ps[0] = 1.f; ps[1] = l; ps[2] = sm; ps[3] = ti; ps[4] = at; ps[5] = aj; ps[6] = 0.f; ps[7] = 0.f;
-    }
-    // the row ranges of one feature group live on nparts threads: stage every thread's two partial
-    // sums in shared memory (over red_s, once the statistics above are out) and add them per
-    // (modality, feature group) in a fixed order, so the result does not depend on scheduling
-    named_bar_sync(2, 256);
-    float4* stg = reinterpret_cast<float4*>(red_s);   // [256][2]
-    if (ws_on) { stg[tid * 2] = o_acc[0]; stg[tid * 2 + 1] = o_acc[1]; }
-    named_bar_sync(2, 256);
-    for (int idx = tid; idx < d.K * D4; idx += 256) {
+    // the row ranges of one feature group live on nparts threads: stage every thread's partial
+    // sums and add them per (modality, feature group) in a fixed order (deterministic)
+    if (ws_on) { stg_s[u * 3] = o_acc[0]; stg_s[u * 3 + 1] = o_acc[1]; stg_s[u * 3 + 2] = o_acc[2]; }
+    named_bar_sync(2, 128);
+    for (int idx = u; idx < d.K * D4; idx += 128) {
       const int k2 = idx / D4, d4 = idx - k2 * D4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int pp = 0; pp < nparts; ++pp) {
         const int q0 = (pp * rows) / nparts, q1 = ((pp + 1) * rows) / nparts;
         if (q1 <= q0) continue;
         const int klo = q0 / TB;
-        int slot = -1;
-        if (klo == k2) slot = 0;
-        else if (klo + 1 == k2 && q1 > (klo + 1) * TB) slot = 1;
-        if (slot >= 0) {
-          const float4 o = stg[(pp * D4 + d4) * 2 + slot];
+        const int slot = k2 - klo;
+        if (slot >= 0 && slot < 3 && (slot == 0 || q1 > (klo + slot) * TB)) {
+          const float4 o = stg_s[(pp * D4 + d4) * 3 + slot];
           v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
         }
       }
       *reinterpret_cast<float4*>(part_o + (((size_t)n * pl.slabs + slab) * d.K + k2) * Dp + d4 * 4) = v;
     }
+    __threadfence();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 17) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
   }
+
+  // ===== combine: the last CTA of sample n merges the slab partials (model_v2.py:266-278:
+  // softmax over T from the partial sums, softmax over the K modalities, g1_all) =====
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int ticket = atomicAdd(&counters[n], 1);
+    *last_flag = (ticket == pl.slabs - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (*last_flag == 0) return;
+  __threadfence();
+  {
+    const int K = d.K, nsl = pl.slabs;
+    float* L_s = cmb_s;          // [8]
+    float* s_s = cmb_s + 8;      // [8]
+    float* beta_s = cmb_s + 16;  // [8]
+    const float* ps = part_stat + (size_t)n * nsl * K * kPartW;
+    if (warp < K) {
+      const int k = warp;
+      float L = 0.f, sm = -INFINITY;
+      for (int i = lane; i < nsl; i += 32) {
+        const float* e = ps + ((size_t)i * K + k) * kPartW;
+        L += __ldcg(e + 1);
+        sm = fmaxf(sm, __ldcg(e + 2));
+      }
+      // fixed-order tree: the same value on every run
+      L = warp_sum(L);
+      sm = warp_max(sm);
+      float ti = 0.f;
+      int first = 0x7fffffff;
+      for (int i = lane; i < nsl; i += 32) {
+        const float* e = ps + ((size_t)i * K + k) * kPartW;
+        if (__ldcg(e + 2) == sm) { ti += __ldcg(e + 3); first = min(first, i); }
+      }
+      ti = warp_sum(ti);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+      if (lane == 0) {
+        const float* ef = ps + ((size_t)(first < nsl ? first : 0) * K + k) * kPartW;
+        float* st = stats + ((size_t)n * K + k) * kStatW;
+        st[0] = 1.f; st[1] = L; st[2] = sm; st[3] = ti; st[5] = __ldcg(ef + 4); st[6] = __ldcg(ef + 5); st[7] = 0.f;
+        L_s[k] = L; s_s[k] = sm;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+      float smax = -INFINITY, den = 0.f;
+      for (int kk = 0; kk < K; ++kk) smax = fmaxf(smax, s_s[kk]);
+      for (int kk = 0; kk < K; ++kk) den += expf(s_s[kk] - smax);
+      const float beta = expf(s_s[threadIdx.x] - smax) / den;
+      beta_s[threadIdx.x] = beta;
+      stats[((size_t)n * K + threadIdx.x) * kStatW + 4] = beta;
+    }
+    __syncthreads();
+    // r_k = sum_slabs o / L_k; staged over the (now idle) ring so that g1_all adds K terms in order
+    float* r_s = reinterpret_cast<float*>(ring);     // [K][Dp]
+    const float* po = part_o + (size_t)n * nsl * K * Dp;
+    for (int idx = threadIdx.x; idx < K * D; idx += blockDim.x) {
+      const int k = idx / D, c = idx - k * D;
+      float o = 0.f;
+      for (int i = 0; i < nsl; ++i) o += __ldcg(po + ((size_t)i * K + k) * Dp + c);
+      const float rv = o / L_s[k];
+      r_s[k * Dp + c] = rv;
+      stats[attn_stats_r_offset(d) + ((size_t)n * K + k) * D + c] = rv;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float gsum = 0.f;
+      for (int k = 0; k < K; ++k) gsum = fmaf(beta_s[k], r_s[k * Dp + c], gsum);
+      g1_all[(size_t)n * D + c] = gsum;
+    }
+    if (threadIdx.x == 0) counters[n] = 0;   // ready for the next call over this workspace
+  }
 }
 
 #ifdef FVTA_TC_TRACE
 extern "C" int fvta_tc_trace_read(long long* out) {
-  return (int)cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 4 * kTraceTiles * 8);
+  return (int)cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(long long) * 5 * kTraceTiles * 8);
 }
 #endif
 
@@ -656,7 +750,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
+  static EncodeTiledFn fn = nullptr;   // resolved once; the same pointer for every caller
   if (fn) return fn;
   void* p = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -665,16 +759,22 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// Returns FVTA_OK if it ran, 1 if this shape/flag combination is not covered (caller uses the
-// FFMA kernel), or a negative error.
-int attn_fwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hall, const uint8_t* hall_mask,
-                    const uint8_t* hq_mask, float* ws, float* g1_all, float* a_logits, float* c_col, float* stats,
-                    cudaStream_t st) {
+int attn_tc_prep_images_launch(const FvtaAttnDesc& d, const AttnLayout& L, float* ws, cudaStream_t st) {
+  attn_prep_images<<<d.N, 256, 0, st>>>(d, ws + L.qeffT, reinterpret_cast<uint8_t*>(ws + L.qB32),
+                                        reinterpret_cast<uint8_t*>(ws + L.qB16), reinterpret_cast<int*>(ws + L.counter),
+                                        L.Dp, L.JQP);
+  return check_launch("attn_prep_images");
+}
+
+// Runs the tile kernel (+ fused combine) over a workspace whose folded operands are in place.
+int attn_fwd_tc_launch(const FvtaAttnDesc& d, const AttnLayout& L, const float* hall, const uint8_t* hall_mask,
+                       const uint8_t* hq_mask, float* ws, float* g1_all, float* a_logits, float* c_col, float* stats,
+                       cudaStream_t st) {
   TcPlan pl;
-  if (!tc_make_plan(d, pl)) return 1;
-  if (pl.slabs > L.nt) return 1;  // partial buffers are sized for ceil(T/32) tiles per sample
+  if (!tc_make_plan(d, pl)) return FVTA_E_SHAPE;
+  if (pl.slabs > L.npart) return FVTA_E_SHAPE;
   EncodeTiledFn encode = get_encode_fn();
-  if (!encode) return 1;
+  if (!encode) { set_last_error("cuTensorMapEncodeTiled not found", cudaErrorUnknown); return FVTA_E_LAUNCH; }
   CUtensorMap tmap;
   cuuint64_t gdim[3] = {(cuuint64_t)d.D, (cuuint64_t)d.T, (cuuint64_t)d.N * d.K};
   cuuint64_t gstr[2] = {(cuuint64_t)d.D * 4, (cuuint64_t)d.T * d.D * 4};
@@ -683,27 +783,18 @@ int attn_fwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hal
   CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(hall), gdim, gstr, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) return 1;
-  __half* qB = reinterpret_cast<__half*>(ws + L.qB);
-  int rc = FVTA_OK;
-  if (g_attn_stages & 1) {
-    attn_prep_qb<<<d.N, 256, 0, st>>>(d, ws + L.qeffT, qB, L.Dp, L.JQP, pl.KC);
-    rc = check_launch("attn_prep_qb");
-    if (rc) return rc;
-  }
-  if (!(g_attn_stages & 2)) return (g_attn_stages & 4) ? attn_combine_launch(d, ws + L.part_stat, ws + L.part_o, g1_all, stats, pl.slabs, L.Dp, st) : FVTA_OK;
+  if (cr != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed", cudaErrorInvalidValue); return FVTA_E_LAUNCH; }
   const bool has_lin = (d.simi == 1 || d.simi == 3);   // w_lin is identically zero otherwise
   auto kern = has_lin ? attn_fwd_tc<true> : attn_fwd_tc<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) { set_last_error("attn_fwd_tc smem attr", e); return FVTA_E_LAUNCH; }
   dim3 grid(pl.slabs, d.N);
-  kern<<<grid, kTcThreads, pl.smem, st>>>(tmap, d, pl, hall_mask, hq_mask, ws + L.coef, qB, ws + L.col,
-                                          ws + L.zconst, a_logits, c_col, ws + L.part_stat, ws + L.part_o, L.Dp,
-                                          L.JQP);
-  rc = check_launch("attn_fwd_tc");
-  if (rc) return rc;
-  if (!(g_attn_stages & 4)) return FVTA_OK;
-  return attn_combine_launch(d, ws + L.part_stat, ws + L.part_o, g1_all, stats, pl.slabs, L.Dp, st);
+  kern<<<grid, kTcThreads, pl.smem, st>>>(tmap, d, pl, hall_mask, hq_mask, ws + L.coef,
+                                          reinterpret_cast<const uint8_t*>(ws + L.qB32),
+                                          reinterpret_cast<const uint8_t*>(ws + L.qB16), ws + L.col, ws + L.zconst,
+                                          a_logits, c_col, ws + L.part_stat, ws + L.part_o,
+                                          reinterpret_cast<int*>(ws + L.counter), g1_all, stats, L.Dp, L.JQP);
+  return check_launch("attn_fwd_tc");
 }
 
 }  // namespace fvta

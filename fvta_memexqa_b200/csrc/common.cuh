@@ -77,6 +77,7 @@ constexpr int kPartW = 8;        // floats per tile partial: M, l, s, ties, argm
 
 struct AttnLayout {
   int nt;    // tiles per sample = ceil(T / kAttnTT)
+  int npart; // partial slots per sample the workspace holds: max(nt, CTAs per sample of the tcgen05 kernel)
   int JQP;   // JQ padded to the accumulator width the kernel is instantiated for
   int Dp;    // D padded to 4
   // forward scratch
@@ -84,8 +85,8 @@ struct AttnLayout {
   size_t qeffT;      // [N][Dp][JQP] effective question operand, transposed (d-major)
   size_t col;        // [N][JQP]     per-question-word term + bias
   size_t zconst;     // [N]          K*((b_WH+lq).W_WC + b_WC)
-  size_t part_stat;  // [N][nt][K][kPartW] tile partials: M, l, smax, ties, argmax (t, j)
-  size_t part_o;     // [N][nt][K][Dp] tile partial weighted sums
+  size_t part_stat;  // [N][npart][K][kPartW] tile partials: M, l, smax, ties, argmax (t, j)
+  size_t part_o;     // [N][npart][K][Dp] tile partial weighted sums
   // backward scratch
   size_t dqeffT;     // [N][Dp][JQP]
   size_t dcol;       // [N][JQP]
@@ -94,7 +95,9 @@ struct AttnLayout {
   size_t drow;       // [N][K][4]    per-(n,k) scalars the backward needs (ds, rdotdr, ...)
   size_t du;         // [Dp]         d u summed over samples
   size_t scal;       // [4]          sum_n dzc, d att_b
-  size_t qB;         // [N][ceil(D/64)][64][64] fp16: tensor-core B operand image (8 KB per chunk)
+  size_t qB32;       // [N][ceil(D/32)][64 rows][128 B]: tf32 [B_hi ; B_lo] image of the tensor-core kernel
+  size_t qB16;       // [N][ceil(D/64)][32 rows][128 B]: fp16 B_hi image
+  size_t counter;    // [N] int: CTAs of the sample that have delivered their partials (self-resetting)
   size_t total;      // floats
 };
 
@@ -112,6 +115,11 @@ __host__ __device__ inline int attn_jqp(int JQ) {
 __host__ __device__ inline AttnLayout attn_layout(const FvtaAttnDesc& d) {
   AttnLayout L;
   L.nt = (d.T + kAttnTT - 1) / kAttnTT;
+  {  // the tensor-core kernel runs min(tiles, ceil(148 / N)) CTAs per sample with tiles <= ceil(T / 4)
+    const int per_sample = (148 + d.N - 1) / d.N, max_tiles = (d.T + 3) / 4;
+    const int slabs = per_sample < max_tiles ? per_sample : max_tiles;
+    L.npart = L.nt > slabs ? L.nt : slabs;
+  }
   L.JQP = attn_jqp(d.JQ);
   L.Dp = round_up(d.D, 4);
   size_t o = 0;
@@ -120,8 +128,8 @@ __host__ __device__ inline AttnLayout attn_layout(const FvtaAttnDesc& d) {
   L.qeffT = take((size_t)d.N * L.Dp * L.JQP);
   L.col = take((size_t)d.N * L.JQP);
   L.zconst = take((size_t)d.N);
-  L.part_stat = take((size_t)d.N * L.nt * d.K * kPartW);
-  L.part_o = take((size_t)d.N * L.nt * d.K * L.Dp);
+  L.part_stat = take((size_t)d.N * L.npart * d.K * kPartW);
+  L.part_o = take((size_t)d.N * L.npart * d.K * L.Dp);
   L.dqeffT = take((size_t)d.N * L.Dp * L.JQP);
   L.dcol = take((size_t)d.N * L.JQP);
   L.dcoef = take((size_t)d.N * 3 * L.Dp);
@@ -129,7 +137,9 @@ __host__ __device__ inline AttnLayout attn_layout(const FvtaAttnDesc& d) {
   L.drow = take((size_t)d.N * d.K * 4);
   L.du = take((size_t)L.Dp);
   L.scal = take(4);
-  L.qB = take((size_t)d.N * ((d.D + 63) / 64) * 2048);
+  L.qB32 = take((size_t)d.N * ((d.D + 31) / 32) * 2048);
+  L.qB16 = take((size_t)d.N * ((d.D + 63) / 64) * 1024);
+  L.counter = take((size_t)d.N);
   L.total = o;
   return L;
 }

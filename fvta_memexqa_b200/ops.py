@@ -54,11 +54,11 @@ class AttnConfig:
         self.window = int(math.ceil(float(window_t)))  # model_v2.py:335 ceil -> int64
         self.time_warp_att = bool(time_warp_att)
 
-    def desc(self, N, K, T, D, JQ, has_mask):
+    def desc(self, N, K, T, D, JQ, has_mask, path=0):
         return FvtaAttnDesc(N=N, K=K, T=T, D=D, JQ=JQ, simi=self.simiMatrix, add_tanh=int(self.add_tanh),
                             use_time_warp=int(self.use_time_warp), warp_type=self.warp_type,
                             window=self.window, time_warp_att=int(self.time_warp_att),
-                            has_mask=int(has_mask), ws_from_fwd=0)
+                            has_mask=int(has_mask), ws_from_fwd=0, path=int(path))
 
 
 def _attn_params(W, b, WH_W, WH_b, WC_W, WC_b):
@@ -67,8 +67,11 @@ def _attn_params(W, b, WH_W, WH_b, WC_W, WC_b):
 
 
 def attn_forward(cfg, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=None,
-                 want_logits=False, want_c=False, want_warp_h=False, reuse=None):
-    """fvta_attn_fwd.  hall [N,K,T,D], hq [N,JQ,D] -> dict(g1_all, a_logits, c_col, warp_h, stats)."""
+                 want_logits=False, want_c=False, want_warp_h=False, reuse=None, path=0, folded=False):
+    """fvta_attn_fwd.  hall [N,K,T,D], hq [N,JQ,D] -> dict(g1_all, a_logits, c_col, warp_h, stats, path).
+    path: _lib.PATH_AUTO, or _lib.PATH_FFMA to pin the CUDA-core tile kernel (A/B parity checks).
+    folded=True (with reuse=): the workspace of the earlier call still holds the folded question
+    operands for the same hq / lq / parameters (FvtaAttnDesc.ws_from_fwd), only the context is new."""
     lib = _lib.load()
     f32 = torch.float32
     hall = _req(hall, f32, "hall")
@@ -81,7 +84,7 @@ def attn_forward(cfg, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W=None, WH_b=No
     has_mask = hall_mask is not None and hq_mask is not None  # model_v2.py:232, :263
     hm = _mask_u8(hall_mask, "hall_mask") if has_mask else None
     qm = _mask_u8(hq_mask, "hq_mask") if has_mask else None
-    desc = cfg.desc(N, K, T, D, JQ, has_mask)
+    desc = cfg.desc(N, K, T, D, JQ, has_mask, path)
     dev = hall.device
     ws_bytes = lib.fvta_attn_workspace_bytes(ctypes.byref(desc))
     if ws_bytes == 0:
@@ -97,12 +100,18 @@ def attn_forward(cfg, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W=None, WH_b=No
     c_col = torch.empty(N, T, dtype=f32, device=dev) if (want_c and cfg.use_time_warp) else None
     warp_h = torch.empty(N, K, T, D, dtype=f32, device=dev) if (want_warp_h and cfg.use_time_warp) else None
     params = _attn_params(W, b, WH_W, WH_b, WC_W, WC_b)
+    ran = lib.fvta_attn_fwd_path(ctypes.byref(desc), int(c_col is not None), int(warp_h is not None))
+    if folded:
+        if reuse is None:
+            raise _lib.FvtaError("folded=True needs the buffers of the earlier call (reuse=)")
+        desc.ws_from_fwd = 1
     rc = lib.fvta_attn_fwd(ctypes.byref(desc), _ptr(hall), _ptr(hm), _ptr(hq), _ptr(qm), _ptr(lq),
                            ctypes.byref(params), _ptr(g1_all), _ptr(a_logits), _ptr(c_col), _ptr(warp_h),
                            _ptr(stats), _ptr(ws), ws_bytes, _stream())
     check(rc, "fvta_attn_fwd")
+    desc.ws_from_fwd = 0
     return dict(g1_all=g1_all, a_logits=a_logits, c_col=c_col, warp_h=warp_h, stats=stats, ws=ws,
-                desc=desc, saved=(hall, hm, hq, qm, lq))
+                desc=desc, saved=(hall, hm, hq, qm, lq), path=ran)
 
 
 def attn_backward(fwd, d_g1_all, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=None, sinks=None,

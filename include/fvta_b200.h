@@ -13,7 +13,8 @@
  *   - the caller owns every buffer; nothing here allocates, frees or synchronises;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
  *   - return value: FVTA_OK (0) or a negative FVTA_E_* code; never throws;
- *   - re-entrant across streams and devices; no global state.
+ *   - re-entrant across streams and devices; no global state (fvta_last_error is per thread,
+ *     fvta_launch_count a monotonic diagnostic counter).
  */
 #ifndef FVTA_B200_H
 #define FVTA_B200_H
@@ -57,9 +58,18 @@ typedef struct {
   int32_t window;        /* ceil(window_t) for warp_type 5 (model_v2.py:333-337); 3 */
   int32_t time_warp_att; /* --use_time_warp_att (model_v2.py:269-275) */
   int32_t has_mask;      /* 0: hinfo_mask/hq_mask are None (exp_mask skipped, model_v2.py:263) */
-  int32_t ws_from_fwd;   /* fvta_attn_bwd only: 1 = `workspace` still holds what fvta_attn_fwd left
-                            there for these inputs, so the operand folding is not redone */
+  int32_t ws_from_fwd;   /* 1 = `workspace` still holds what an earlier fvta_attn_fwd call left there for
+                            the same hq / hq_mask / lq / parameters, so the operand folding is not redone
+                            (fvta_attn_bwd after its forward; fvta_attn_fwd over a new context with the
+                            same question, e.g. repeated inference) */
+  int32_t path;          /* forward kernel selection: FVTA_PATH_AUTO, or FVTA_PATH_FFMA to pin the
+                            CUDA-core tile kernel (A/B parity checks).  Per call, not process state */
 } FvtaAttnDesc;
+
+#define FVTA_PATH_AUTO 0
+#define FVTA_PATH_SMALL 1 /* one fused CTA per sample (question attention: K = 1, JQ = 1, no time warp) */
+#define FVTA_PATH_FFMA 2  /* CUDA-core tile kernel + combine kernels */
+#define FVTA_PATH_TC 3    /* tcgen05 / TMEM / TMA tile kernel with the combine fused in */
 
 typedef struct {
   const float* att_W; /* att_logits/W [rows,1], rows = 3D,2D,4D,0 for simi 1..4 */
@@ -79,9 +89,10 @@ typedef struct {      /* gradients, same shapes as FvtaAttnParams; each is OVERW
   float* WC_b;
 } FvtaAttnGrads;
 
-/* Diagnostic knob for benchmarks: which stages fvta_attn_fwd launches -- bit 0 operand folding,
- * bit 1 the tile kernel, bit 2 the combine (default 7).  Process-wide; leave at 7 in production. */
-void fvta_attn_fwd_set_stages(int mask);
+/* Which kernel fvta_attn_fwd runs for this descriptor (a pure function of its arguments): one of
+ * FVTA_PATH_SMALL / FVTA_PATH_FFMA / FVTA_PATH_TC, or a negative FVTA_E_* code.  want_c_col /
+ * want_warp_h: whether those optional outputs will be requested. */
+int fvta_attn_fwd_path(const FvtaAttnDesc* desc, int want_c_col, int want_warp_h);
 
 /* Bytes of scratch the fwd/bwd calls need, and floats of `stats` fwd saves for bwd. */
 size_t fvta_attn_workspace_bytes(const FvtaAttnDesc* desc);

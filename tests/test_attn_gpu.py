@@ -40,11 +40,14 @@ def oracle32(cfg, params, inp):
                                     params, cfg)
 
 
-def case_tol(ref32, ref64, key, mask=None):
-    """1e-4 relative, widened only where fp32 itself cannot do better: wide windows (warp types
-    1/3/4 give gates up to T) make S = g*P + g^2*r_h + ... cancel catastrophically, and the fp32
-    CPU oracle then differs from the fp64 one by more than 1e-4 too."""
-    return max(TOL, 6.0 * rel_err(ref32[key], ref64[key], mask))
+# Fixed bounds.  1e-4 everywhere except the cases listed here, whose pre-activations
+# S = g*P + g^2*r_h + ... carry gates of O(T) (window types 1/3/4: cnt = T, t+1, T-t) with no tanh to
+# squash them: the logits themselves are O(1e3..1e5) and fp32 rounding of the g^2 term alone is
+# ~1e-3 relative to the largest logit (the fp32 CPU oracle is no closer to the fp64 one).
+CASE_BOUND = {
+    (2, 6, 3, 17, 100, 25, 1, False, True, 3, False): 2e-3,
+    (2, 6, 2, 40, 36, 13, 3, True, True, 4, True): 1e-3,
+}
 
 
 CASES = [
@@ -71,18 +74,26 @@ CASES = [
 def test_attn_fwd_parity(cuda_device, case):
     N, K, M, JMAX, D, JQ, simi, tanh, warp, wtype, twa = case
     cfg, params, inp = attn_case(N, K, M, JMAX, D, JQ, simi, tanh, warp, wtype, twa, seed=N + D)
-    out, _ = run_gpu_fwd(cfg, params, inp, cuda_device, want_logits=True, want_c=True, want_warp_h=True)
+    # the production call (no warp_h: whichever kernel the dispatcher picks for this shape) ...
+    out, _ = run_gpu_fwd(cfg, params, inp, cuda_device, want_logits=True, want_c=True)
     ref = oracle64(cfg, params, inp)
-    ref32 = oracle32(cfg, params, inp)
     valid = (ref["att_logits"] > -1e29).double()
-    assert rel_err(out["g1_all"], ref["g1_all"]) < case_tol(ref32, ref, "g1_all")
-    assert rel_err(out["a_logits"], ref["att_logits"], valid) < case_tol(ref32, ref, "att_logits", valid)
+    bound = CASE_BOUND.get(tuple(case), TOL)
+    from fvta_memexqa_b200 import _lib
+    e_g, e_a = rel_err(out["g1_all"], ref["g1_all"]), rel_err(out["a_logits"], ref["att_logits"], valid)
+    print("[attn fwd] %s ran %s: g1_all %.2e logits %.2e (bound %.0e)" % (case, _lib.PATH_NAMES[out["path"]], e_g, e_a, bound))
+    assert e_g < bound and e_a < bound
     # masked entries are exactly float32(-1e30), as exp_mask leaves them
     a = out["a_logits"].cpu()
     assert torch.all(a[valid == 0] == torch.tensor(-1e30, dtype=torch.float32))
     if warp:
         assert rel_err(out["c_col"], ref["c"]) < TOL
-        assert rel_err(out["warp_h"].reshape(ref["warp_h"].shape), ref["warp_h"]) < TOL
+        # ... and a separate call for model.warp_h (visualisation), which only the CUDA-core kernel writes
+        vis, _ = run_gpu_fwd(cfg, params, inp, cuda_device, want_logits=True, want_warp_h=True)
+        assert vis["path"] == _lib.PATH_FFMA
+        assert rel_err(vis["warp_h"].reshape(ref["warp_h"].shape), ref["warp_h"]) < TOL
+        assert rel_err(vis["g1_all"], ref["g1_all"]) < bound
+        assert rel_err(vis["a_logits"], ref["att_logits"], valid) < bound
 
 
 def test_attn_fwd_fully_masked_and_zero(cuda_device):
