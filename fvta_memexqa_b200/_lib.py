@@ -92,7 +92,7 @@ SYMBOLS = {
     "fvta_output_loss": (ctypes.c_int, [ctypes.c_int32] * 3 + [c_float_p] * 5 + [c_u8_p] + [c_float_p] * 8 +
                          [ctypes.c_void_p]),
     "fvta_adadelta": (ctypes.c_int, [ctypes.c_int64, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
-                                     ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                     c_i32_p, c_float_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                      ctypes.c_void_p]),
 }
 

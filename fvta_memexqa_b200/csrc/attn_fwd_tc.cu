@@ -15,17 +15,21 @@
 //   ~21 mantissa bits per product, fp32 accumulation: the 1e-4 parity bar holds where single-pass
 //   tf32 / bf16 would not (S = g.P + ... with |g| up to 7).
 //
-// Pipeline (one persistent CTA per SM, 18 warps, every hand-over is an mbarrier):
-//   warp 16      TMA      ring of fp32 context tiles [K modalities x TB positions x D]
-//                         (cp.async.bulk.tensor.3d, complete_tx; rows past T are zero-filled)
-//   warps 0-7    split    two threads per context row: row statistics (u.h^2, w_quad.h^2, w_lin.h),
-//                         A_lo, and tcgen05.st of both operands into TMEM (lane = row)
-//   warp 17      MMA      one thread: 13 tf32 + 7 f16 k-steps per tile at D = 100, commit -> acc_full
-//   warps 8-11   softmax  one thread per row: gate, tcgen05.ld of its 2 x 32 accumulator columns,
-//                         logits (MUFU tanh), exp_mask as a min with a per-column cap, row max,
-//                         softmax weight (fixed reference maximum 1: the logits are bounded)
-//   warps 12-15  wsum     weighted sum  o[k,:] += w.g.h  over the still resident fp32 tile, then
-//                         the stage goes back to the TMA warp
+// Pipeline (one persistent CTA per SM, 7 warpgroups, every hand-over is an mbarrier; each role is
+// bound by its own dependent-instruction latency, so every role gets as many warps as it takes to
+// keep its time per tile under the HBM time of the tile; registers are moved between the roles
+// with setmaxnreg):
+//   warp 24       TMA      ring of fp32 context tiles [K modalities x TB positions x D]
+//                          (cp.async.bulk.tensor.3d, complete_tx; rows past T are zero-filled)
+//   warps 0-7     split    two threads per context row: row statistics (u.h^2, w_quad.h^2, w_lin.h),
+//                          A_lo, and tcgen05.st of both operands into TMEM (lane = row)
+//   warp 25       MMA      one elected lane: 13 tf32 + 7 f16 k-steps per tile at D = 100
+//   warps 8-11,   softmax  two warpgroups on alternate tiles, one thread per row: gate, tcgen05.ld of
+//         12-15            its 2 x 32 accumulator columns, logits (MUFU tanh), exp_mask as a min
+//                          with a per-column cap, row max, softmax weight (fixed reference maximum
+//                          1: the logits are bounded)
+//   warps 16-23   wsum     weighted sum  o[k,:] += w.g.h  over the still resident fp32 tile (thread =
+//                          one modality x one float4 of features), then the stage goes back to TMA
 // The softmax over T needs no online rescaling: this kernel is used when the logits are bounded by
 // 1 (tanh or cosine).  Masked rows get the weight 2^-100 instead of exp(-1e30 - 1) = 0: absorbed
 // exactly by any unmasked weight, and it reproduces TF's uniform softmax over a fully masked row.
@@ -38,19 +42,38 @@ namespace fvta {
 
 #ifdef FVTA_TC_TRACE
 constexpr int kTraceTiles = 24;
+#ifndef FVTA_TC_TRACE_T0
+#define FVTA_TC_TRACE_T0 0
+#endif
 __device__ long long g_tc_trace[5][kTraceTiles][8];
 #define TC_TRACE(role, i, ev)                                                                     \
-  do { if (blockIdx.x == 0 && blockIdx.y == 0 && (i) < kTraceTiles && (threadIdx.x & 127) == 0)   \
-         g_tc_trace[role][i][ev] = clock64(); } while (0)
+  do { if (blockIdx.x == 0 && blockIdx.y == 0 && (i) >= FVTA_TC_TRACE_T0 && (i) < FVTA_TC_TRACE_T0 + kTraceTiles - 1 && \
+           (threadIdx.x == 0 || threadIdx.x == 32 || threadIdx.x == 128 || threadIdx.x == kWarpSplit0 * 32 || threadIdx.x == kWarpSoft0 * 32 || threadIdx.x == kWarpSoft0 * 32 + 128)) \
+         g_tc_trace[role][(i) - FVTA_TC_TRACE_T0][ev] = clock64(); } while (0)
+__device__ __forceinline__ long long tc_globaltimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// kernel-level stamps of CTA (0,0), thread 0: slot 0 entry, 1 pipeline start, 2 pipeline end, 3 exit (cycles; +4: ns)
+#define TC_STAMP(slot)                                                                            \
+  do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == kWarpSplit0 * 32) {                \
+         g_tc_trace[0][kTraceTiles - 1][slot] = clock64(); g_tc_trace[0][kTraceTiles - 1][4 + (slot)] = tc_globaltimer(); } } while (0)
 #else
 #define TC_TRACE(role, i, ev) do {} while (0)
+#define TC_STAMP(slot) do {} while (0)
 #endif
 
-constexpr int kTcThreads = 576;   // warps 0-7 split, 8-11 softmax, 12-15 wsum, 16 TMA, 17 MMA
+// warp 0 TMA, 1 MMA, 2-3 idle, 4-11 wsum, 12-19 softmax (2 x 4), 20-27 split.  The scheduler favours high warp
+// ids: the split warps, which set the pace, come last.
+constexpr int kTcThreads = 896;
+#ifdef FVTA_TC_SPLIT_TOP
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpWsum0 = 4, kWarpSoft0 = 12, kWarpSplit0 = 20;
+#else
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpWsum0 = 4, kWarpSplit0 = 12, kWarpSoft0 = 20;
+#endif
+constexpr int kRegSoftmax = 104, kRegWsum = 56, kRegIssue = 40;   // split keeps the launch value (72)
 constexpr int kTcJQP = 32;        // question positions per tile (N of the MMAs: 64 and 32)
 constexpr int kTcTmemCols = 512;
 constexpr int kTcMaxStages = 6;
 constexpr float kMaskedWeight = 7.888609052210118e-31f;  // 2^-100
+constexpr int kTcStageExtra = 512 + 3 * 1024;   // per ring stage: wg [128] + row statistics [3][2][128]
 #ifndef FVTA_TC_MIN_STAGES
 #define FVTA_TC_MIN_STAGES 4
 #endif
@@ -71,8 +94,8 @@ struct TcPlan {
 };
 
 __host__ __device__ inline size_t tc_fixed_smem(const TcPlan& p, int Dp) {
-  return (size_t)p.C32 * 8192 + (size_t)p.C16 * 4096 + (size_t)(3 * Dp + 2 * kTcJQP) * 4 + 8192 /*zq*/ +
-         6144 /*stg*/ + 2560 /*red*/ + 1024 /*combine scratch*/ + 256 /*barriers*/;
+  return (size_t)p.C32 * 8192 + (size_t)p.C16 * 4096 + (size_t)(3 * Dp + 2 * kTcJQP) * 4 + 5120 /*red*/ +
+         1024 /*combine scratch*/ + 256 /*barriers*/;
 }
 
 static bool tc_make_plan(const FvtaAttnDesc& d, TcPlan& p) {
@@ -98,7 +121,7 @@ static bool tc_make_plan(const FvtaAttnDesc& d, TcPlan& p) {
 #endif
   for (int TB = tb_max; TB >= 2; --TB) {
     const int sb = round_up(d.K * TB * d.D * 4, 128);
-    int st = (int)((budget - fixed) / (size_t)(sb + 512));
+    int st = (int)((budget - fixed) / (size_t)(sb + kTcStageExtra));
     if (st > kTcMaxStages) st = kTcMaxStages;
     if (st >= FVTA_TC_MIN_STAGES) { best_tb = TB; best_st = st; break; }
     if (st >= 2 && best_tb == 0) { best_tb = TB; best_st = st; }   // deepest ring is not reachable: take the widest tile
@@ -108,7 +131,7 @@ static bool tc_make_plan(const FvtaAttnDesc& d, TcPlan& p) {
   p.stages = best_st;
   p.rows = d.K * p.TB;
   p.stage_bytes = round_up(p.rows * d.D * 4, 128);
-  p.smem = fixed + (size_t)p.stages * (p.stage_bytes + 512);
+  p.smem = fixed + (size_t)p.stages * (p.stage_bytes + kTcStageExtra);
   p.tiles = (d.T + p.TB - 1) / p.TB;
   const int want = (148 + d.N - 1) / d.N;  // one CTA per SM
   p.slabs = want < 1 ? 1 : (want > p.tiles ? p.tiles : want);
@@ -131,27 +154,33 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// try_wait suspends the warp in hardware until the phase completes or the time hint passes, so
-// waiting warps do not compete for issue slots.  A wait that lasts two seconds is a pipeline bug:
-// trap (the launch fails with an error) instead of hanging the device.
+// try_wait suspends the warp in hardware until the phase completes or an implementation time limit
+// passes, so the loop around it rarely iterates and waiting warps do not compete for issue slots.
+// (A suspend-time hint makes ptxas emit a NANOSLEEP.SYNCS loop that wakes on every barrier event of
+// the CTA: measured 33 % of all issued instructions.)  Far more iterations than any real wait can
+// need mean a pipeline bug: trap (the launch fails with an error) instead of hanging the device.
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x4000;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, P1;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
-  unsigned long long t0, t1;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  while (!mbar_try(bar, parity)) {
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 2000000000ull) __trap();
-  }
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity))
+    if (++spins > (1u << 24)) __trap();
+}
+// for the roles with slack (everything but the split warps, which set the pace): sleep between polls so
+// that waiting warps leave the issue slots to the working ones (plain polling was 45 % of all issued
+// instructions); the wake-up delay only adds pipeline latency, which the ring absorbs
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 22)) __trap();
+  }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
@@ -162,6 +191,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one lane of a converged warp; the branch it guards keeps warp-uniform values in uniform registers
+// (a `lane == 0` branch makes ptxas re-broadcast every tcgen05.mma operand through an R2UR loop:
+// ~110 cycles per MMA instead of ~10, tools/umma_probe.cu)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // D[tmem] (+)= A[tmem] . B[smem]^T, M = 128
@@ -192,17 +232,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]) : "memory");
+               "r"(r[2]), "r"(r[3]));
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
 }
 
 // K-major, 128B-swizzled operand: 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100)
@@ -263,7 +303,76 @@ __global__ void attn_prep_images(FvtaAttnDesc d, const float* __restrict__ qeffT
 }
 
 // ---- the fused kernel: grid (slabs, N) ----------------------------------------------------------
-template <bool HAS_LIN>
+template <int NREG> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NREG)); }
+template <int NREG> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NREG)); }
+
+// One split thread's share of a tile row: `NO` 8-feature groups starting at group o0 (compile-time when
+// DT > 0: straight-line code, every bound folded).  Loads first, then statistics, residuals and the
+// two TMEM stores per pair of groups.
+template <bool HAS_LIN, int DT>
+__device__ __forceinline__ void split_row(const float* __restrict__ hrow, const float* __restrict__ coef_s, int Dp,
+                                          int D, int o_begin, int o_end, int K32, uint32_t colA, uint32_t colL,
+                                          float& zdot, float& quad, float& lin) {
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 zdA = make_float2(0.f, 0.f), qdA = zdA, lnA = zdA, zdB = zdA, qdB = zdA, lnB = zdA;
+  auto stats4 = [&](int d0, const float4& v, float2& zd, float2& qd, float2& ln) {
+    const float4 cu = *reinterpret_cast<const float4*>(coef_s + d0);
+    const float4 cq = *reinterpret_cast<const float4*>(coef_s + 2 * Dp + d0);
+    const float2 a01 = make_float2(v.x, v.y), a23 = make_float2(v.z, v.w);
+    const float2 s01 = __fmul2_rn(a01, a01), s23 = __fmul2_rn(a23, a23);
+    zd = __ffma2_rn(make_float2(cu.x, cu.y), s01, zd);
+    zd = __ffma2_rn(make_float2(cu.z, cu.w), s23, zd);
+    qd = __ffma2_rn(make_float2(cq.x, cq.y), s01, qd);
+    qd = __ffma2_rn(make_float2(cq.z, cq.w), s23, qd);
+    if (HAS_LIN) {
+      const float4 cl = *reinterpret_cast<const float4*>(coef_s + Dp + d0);
+      ln = __ffma2_rn(make_float2(cl.x, cl.y), a01, ln);
+      ln = __ffma2_rn(make_float2(cl.z, cl.w), a23, ln);
+    }
+  };
+  // residual the tensor core drops, as two packed fp16: exact subtraction, fp16 rounding 2^-11 of it
+  auto lo2 = [&](float a, float b) -> uint32_t {
+    const float2 rr = __ffma2_rn(make_float2(tf32_part(a), tf32_part(b)), make_float2(-1.f, -1.f), make_float2(a, b));
+    const __half2 p = __floats2half2_rn(rr.x, rr.y);
+    return *reinterpret_cast<const uint32_t*>(&p);
+  };
+  auto pair = [&](int o, bool two) {
+    const int d0 = o * 8;
+    const float4 v0 = d0 < D ? *reinterpret_cast<const float4*>(hrow + d0) : zero4;
+    const float4 v1 = d0 + 4 < D ? *reinterpret_cast<const float4*>(hrow + d0 + 4) : zero4;
+    const float4 v2 = (two && d0 + 8 < D) ? *reinterpret_cast<const float4*>(hrow + d0 + 8) : zero4;
+    const float4 v3 = (two && d0 + 12 < D) ? *reinterpret_cast<const float4*>(hrow + d0 + 12) : zero4;
+    if (d0 < D) stats4(d0, v0, zdA, qdA, lnA);
+    if (d0 + 4 < D) stats4(d0 + 4, v1, zdB, qdB, lnB);
+    if (two && d0 + 8 < D) stats4(d0 + 8, v2, zdA, qdA, lnA);
+    if (two && d0 + 12 < D) stats4(d0 + 12, v3, zdB, qdB, lnB);
+    uint32_t hi[16], lo[8];
+    hi[0] = __float_as_uint(v0.x); hi[1] = __float_as_uint(v0.y); hi[2] = __float_as_uint(v0.z); hi[3] = __float_as_uint(v0.w);
+    hi[4] = __float_as_uint(v1.x); hi[5] = __float_as_uint(v1.y); hi[6] = __float_as_uint(v1.z); hi[7] = __float_as_uint(v1.w);
+    hi[8] = __float_as_uint(v2.x); hi[9] = __float_as_uint(v2.y); hi[10] = __float_as_uint(v2.z); hi[11] = __float_as_uint(v2.w);
+    hi[12] = __float_as_uint(v3.x); hi[13] = __float_as_uint(v3.y); hi[14] = __float_as_uint(v3.z); hi[15] = __float_as_uint(v3.w);
+    lo[0] = lo2(v0.x, v0.y); lo[1] = lo2(v0.z, v0.w); lo[2] = lo2(v1.x, v1.y); lo[3] = lo2(v1.z, v1.w);
+    lo[4] = lo2(v2.x, v2.y); lo[5] = lo2(v2.z, v2.w); lo[6] = lo2(v3.x, v3.y); lo[7] = lo2(v3.z, v3.w);
+    // every condition below is warp-uniform (o and the half are): the stores are warp-collective
+    if (two && o + 1 < K32) tmem_st16(colA + 8 * o, hi);
+    else if (o < K32) tmem_st8(colA + 8 * o, hi);
+    if (two) tmem_st8(colL + 4 * o, lo);
+    else tmem_st4(colL + 4 * o, lo);
+  };
+  if (DT > 0) {
+    constexpr int kOT = 2 * ((DT + 15) / 16), kHalf = kOT / 2;     // groups per thread half
+#pragma unroll
+    for (int j = 0; j < kHalf; j += 2) pair(o_begin + j, j + 1 < kHalf);
+  } else {
+#pragma unroll 1
+    for (int o = o_begin; o < o_end; o += 2) pair(o, o + 1 < o_end);
+  }
+  const float2 zd2 = __fadd2_rn(zdA, zdB), qd2 = __fadd2_rn(qdA, qdB), ln2 = __fadd2_rn(lnA, lnB);
+  zdot = zd2.x + zd2.y; quad = qd2.x + qd2.y; lin = ln2.x + ln2.y;
+}
+
+// DT: compile-time D (100, the reference hidden size 50) or 0 = any supported D at run time.
+template <bool HAS_LIN, int DT>
 __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     const __grid_constant__ CUtensorMap tmap, FvtaAttnDesc d, TcPlan pl, const uint8_t* __restrict__ hall_mask,
     const uint8_t* __restrict__ hq_mask, const float* __restrict__ coef, const uint8_t* __restrict__ qB32,
@@ -273,25 +382,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     int Dp, int JQPg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+  TC_STAMP(0);
   const int S = pl.stages;
+  const int D = DT > 0 ? DT : d.D;
   uint8_t* b32_s = smem;                                   // tf32 [B_hi ; B_lo], swizzled
   uint8_t* b16_s = b32_s + pl.C32 * 8192;                  // f16 B_hi, swizzled
   uint8_t* ring = b16_s + pl.C16 * 4096;                   // fp32 tiles
   float* coef_s = reinterpret_cast<float*>(ring + (size_t)S * pl.stage_bytes);  // [3][Dp]
   float* col_s = coef_s + 3 * Dp;        // [32]  per-question-word term + bias
   float* cap_s = col_s + kTcJQP;         // [32]  +inf for a valid question word, -1e30 masked, -inf padding
-  float4* zq_s = reinterpret_cast<float4*>(cap_s + kTcJQP);   // [2][2][128] half-row (zdot, quad, lin, -)
-  float4* stg_s = zq_s + 512;            // [128][3] weighted-sum partials of the slab
-  float* red_s = reinterpret_cast<float*>(stg_s + 384);      // [5][128]
-  float* cmb_s = red_s + 640;            // [256] combine scratch
-  float* wg_s = cmb_s + 256;             // [S][128]  softmax weight * gate
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wg_s + S * 128);
+  float* red_s = cap_s + kTcJQP;         // [2][5][128] slab statistics of the two softmax warpgroups
+  float* cmb_s = red_s + 1280;           // [256] combine scratch
+  float* wg_s = cmb_s + 256;             // [S][128]     softmax weight * gate
+  float* zq_s = wg_s + S * 128;          // [S][3][2][128] half-row statistics: zdot, quad, lin
+  uint64_t* bars = reinterpret_cast<uint64_t*>(zq_s + S * 768);
   uint64_t* full = bars;                              // [S]  TMA -> split
   uint64_t* empty = bars + kTcMaxStages;              // [S]  wsum -> TMA
   uint64_t* wg_ready = bars + 2 * kTcMaxStages;       // [S]  softmax -> wsum
-  uint64_t* a_ready = bars + 3 * kTcMaxStages;        // [2]  split -> MMA, softmax
-  uint64_t* acc_full = a_ready + 2;                   // [2]  MMA -> softmax
-  uint64_t* ep_done = a_ready + 4;                    // [2]  softmax -> split (TMEM buffers + zq free)
+  uint64_t* a_ready = bars + 3 * kTcMaxStages;        // [2]  split -> MMA (operands), softmax (row statistics)
+  uint64_t* acc_full = a_ready + 2;                   // [2]  MMA -> softmax (accumulator), split (A buffers free)
+  uint64_t* ep_done = a_ready + 4;                    // [2]  softmax -> MMA (accumulator drained)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_ready + 6);
   int* last_flag = reinterpret_cast<int*>(tmem_ptr + 1);
 
@@ -300,14 +410,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   const int tile_begin = (int)(((long long)slab * pl.tiles) / pl.slabs);
   const int tile_end = (int)(((long long)(slab + 1) * pl.tiles) / pl.slabs);
   const int ntile = tile_end - tile_begin;
-  const int D = d.D, TB = pl.TB, rows = pl.rows;
+  const int TB = pl.TB, rows = pl.rows;
+  const int K32 = DT > 0 ? (DT + 7) / 8 : pl.K32, K16 = DT > 0 ? (DT + 15) / 16 : pl.K16;
+  const int ws_warps = (d.K * (D >> 2) + 31) >> 5;      // weighted-sum warps with work (<= 8)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 128); mbar_init(&wg_ready[s], 128); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ws_warps * 32); mbar_init(&wg_ready[s], 128); }
     for (int b2 = 0; b2 < 2; ++b2) { mbar_init(&a_ready[b2], 256); mbar_init(&acc_full[b2], 1); mbar_init(&ep_done[b2], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 17) {
+  if (warp == kWarpMma) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                  "r"(kTcTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -332,23 +444,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  TC_STAMP(1);
 
-  if (warp == 16) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+  if (warp < kWarpWsum0) {
+    reg_dec<kRegIssue>();
+    if (warp == kWarpTma) {
+      // ===== TMA producer (whole warp loops, one elected lane issues) =====
       for (int i = 0; i < ntile; ++i) {
         const int s = i % S;
-        if (i >= S) mbar_wait(&empty[s], ((i / S) - 1) & 1);
+        if (i >= S) mbar_wait_relaxed(&empty[s], ((i / S) - 1) & 1);
         TC_TRACE(0, i, 0);
-        mbar_expect_tx(&full[s], (uint32_t)(rows * D * 4));
-        tma_load_3d(ring + (size_t)s * pl.stage_bytes, &tmap, &full[s], 0, (tile_begin + i) * TB, n * d.K);
+        if (elect_one()) {
+          mbar_expect_tx(&full[s], (uint32_t)(rows * D * 4));
+          tma_load_3d(ring + (size_t)s * pl.stage_bytes, &tmap, &full[s], 0, (tile_begin + i) * TB, n * d.K);
+        }
+        __syncwarp();
       }
-    }
-  } else if (warp == 17) {
-    // ===== MMA issuer =====
-    //   acc[:, 0:64]  = A_hi . [B_hi ; B_lo]^T   (kind::tf32)
-    //   acc[:, 32:64] += A_lo . B_hi16^T          (kind::f16)       P = acc[:, 0:32] + acc[:, 32:64]
-    if (lane == 0) {
+    } else if (warp == kWarpMma) {
+      // ===== MMA issuer =====
+      //   acc[:, 0:64]  = A_hi . [B_hi ; B_lo]^T   (kind::tf32)
+      //   acc[:, 32:64] += A_lo . B_hi16^T          (kind::f16)       P = acc[:, 0:32] + acc[:, 32:64]
+      // The whole warp runs the loop (uniform control flow keeps every operand in uniform registers:
+      // a `lane == 0` branch costs ~110 cycles per MMA in R2UR broadcast loops); one elected lane issues.
       const uint32_t id32 = umma_idesc(2, 64), id16 = umma_idesc(0, 32);
       const uint32_t b32_u = smem_u32(b32_s), b16_u = smem_u32(b16_s);
       for (int i = 0; i < ntile; ++i) {
@@ -356,128 +473,114 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         const uint32_t acc = tmem_base + (uint32_t)(b2 * 64);
         const uint32_t a_hi = tmem_base + (uint32_t)(pl.col_ahi + b2 * pl.w_ahi);
         const uint32_t a_lo = tmem_base + (uint32_t)(pl.col_alo + b2 * pl.w_alo);
-        mbar_wait(&a_ready[b2], (i >> 1) & 1);
+        mbar_wait_relaxed(&a_ready[b2], (i >> 1) & 1);
+        if (i >= 2) mbar_wait_relaxed(&ep_done[b2], ((i - 2) >> 1) & 1);   // softmax(i-2) has drained accumulator b2
         TC_TRACE(1, i, 0);
         tc_fence_after();
-        for (int ks = 0; ks < pl.K32; ++ks)
-          umma_ts_tf32(acc, a_hi + 8 * ks, umma_desc_sw128(b32_u + (uint32_t)((ks >> 2) * 8192 + (ks & 3) * 32)), id32, ks > 0);
-        for (int ks = 0; ks < pl.K16; ++ks)
-          umma_ts_f16(acc + 32, a_lo + 8 * ks, umma_desc_sw128(b16_u + (uint32_t)((ks >> 2) * 4096 + (ks & 3) * 32)), id16, 1u);
-        umma_commit(&acc_full[b2]);
+        if (elect_one()) {
+          if (DT > 0) {
+#pragma unroll
+            for (int ks = 0; ks < (DT + 7) / 8; ++ks)
+              umma_ts_tf32(acc, a_hi + 8 * ks, umma_desc_sw128(b32_u + (uint32_t)((ks >> 2) * 8192 + (ks & 3) * 32)), id32, ks > 0);
+#pragma unroll
+            for (int ks = 0; ks < (DT + 15) / 16; ++ks)
+              umma_ts_f16(acc + 32, a_lo + 8 * ks, umma_desc_sw128(b16_u + (uint32_t)((ks >> 2) * 4096 + (ks & 3) * 32)), id16, 1u);
+          } else {
+#pragma unroll 4
+            for (int ks = 0; ks < K32; ++ks)
+              umma_ts_tf32(acc, a_hi + 8 * ks, umma_desc_sw128(b32_u + (uint32_t)((ks >> 2) * 8192 + (ks & 3) * 32)), id32, ks > 0);
+#pragma unroll 4
+            for (int ks = 0; ks < K16; ++ks)
+              umma_ts_f16(acc + 32, a_lo + 8 * ks, umma_desc_sw128(b16_u + (uint32_t)((ks >> 2) * 4096 + (ks & 3) * 32)), id16, 1u);
+          }
+          umma_commit(&acc_full[b2]);
+        }
+        __syncwarp();
         TC_TRACE(1, i, 1);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp >= kWarpSplit0 && warp < kWarpSplit0 + 8) {
     // ===== split warps: threads (r, 0) and (r, 1) share context row r = k*TB + tt =====
-    const int r = threadIdx.x & 127, h = threadIdx.x >> 7;
+    const int r = (threadIdx.x - kWarpSplit0 * 32) & 127, h = (threadIdx.x - kWarpSplit0 * 32) >> 7;
     const int roff = (r < rows ? r : 0) * D;        // idle lanes read row 0: their TMEM rows are never used
-    const int OT = 2 * pl.K16;                      // 8-feature groups ("octs") covering both operands
+    const int OT = 2 * K16;                         // 8-feature groups ("octs") covering both operands
     const int o_begin = h ? OT / 2 : 0, o_end = h ? OT : OT / 2;
     const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = 0; i < ntile; ++i) {
       const int s = i % S, b2 = i & 1;
       TC_TRACE(2, i, 0);
       mbar_wait(&full[s], (i / S) & 1);
-      if (i >= 2) mbar_wait(&ep_done[b2], ((i - 2) >> 1) & 1);   // softmax(i-2) has drained buffers b2
+      if (i >= 2) {                                   // MMA(i-2) has consumed the A buffers b2
+        mbar_wait(&acc_full[b2], ((i - 2) >> 1) & 1);
+        tc_fence_after();
+      }
       TC_TRACE(2, i, 1);
       const float* hrow = reinterpret_cast<const float*>(ring + (size_t)s * pl.stage_bytes) + roff;
       const uint32_t colA = lane_base + (uint32_t)(pl.col_ahi + b2 * pl.w_ahi);
       const uint32_t colL = lane_base + (uint32_t)(pl.col_alo + b2 * pl.w_alo);
-      // packed fp32x2 arithmetic (FFMA2/FMUL2); two accumulator sets keep the dependent chains short
-      float2 zdA = make_float2(0.f, 0.f), qdA = zdA, lnA = zdA, zdB = zdA, qdB = zdA, lnB = zdA;
-      auto stats4 = [&](int d0, const float4& v, float2& zd, float2& qd, float2& ln) {
-        const float4 cu = *reinterpret_cast<const float4*>(coef_s + d0);
-        const float4 cq = *reinterpret_cast<const float4*>(coef_s + 2 * Dp + d0);
-        const float2 a01 = make_float2(v.x, v.y), a23 = make_float2(v.z, v.w);
-        const float2 s01 = __fmul2_rn(a01, a01), s23 = __fmul2_rn(a23, a23);
-        zd = __ffma2_rn(make_float2(cu.x, cu.y), s01, zd);
-        zd = __ffma2_rn(make_float2(cu.z, cu.w), s23, zd);
-        qd = __ffma2_rn(make_float2(cq.x, cq.y), s01, qd);
-        qd = __ffma2_rn(make_float2(cq.z, cq.w), s23, qd);
-        if (HAS_LIN) {
-          const float4 cl = *reinterpret_cast<const float4*>(coef_s + Dp + d0);
-          ln = __ffma2_rn(make_float2(cl.x, cl.y), a01, ln);
-          ln = __ffma2_rn(make_float2(cl.z, cl.w), a23, ln);
-        }
-      };
-      // residual the tensor core drops, as two packed fp16: exact subtraction, fp16 rounding 2^-11 of it
-      auto lo2 = [&](float a, float b) -> uint32_t {
-        const float2 rr = __ffma2_rn(make_float2(tf32_part(a), tf32_part(b)), make_float2(-1.f, -1.f), make_float2(a, b));
-        const __half2 p = __floats2half2_rn(rr.x, rr.y);
-        return *reinterpret_cast<const uint32_t*>(&p);
-      };
-      auto load4 = [&](int d0) -> float4 { return d0 < D ? *reinterpret_cast<const float4*>(hrow + d0) : zero4; };
-#pragma unroll 1
-      for (int o = o_begin; o < o_end; o += 2) {
-        const bool two = o + 1 < o_end;
-        const int d0 = o * 8;
-        const float4 v0 = load4(d0), v1 = load4(d0 + 4);
-        const float4 v2 = two ? load4(d0 + 8) : zero4, v3 = two ? load4(d0 + 12) : zero4;
-        if (d0 < D) stats4(d0, v0, zdA, qdA, lnA);
-        if (d0 + 4 < D) stats4(d0 + 4, v1, zdB, qdB, lnB);
-        if (two && d0 + 8 < D) stats4(d0 + 8, v2, zdA, qdA, lnA);
-        if (two && d0 + 12 < D) stats4(d0 + 12, v3, zdB, qdB, lnB);
-        uint32_t hi[16], lo[8];
-        hi[0] = __float_as_uint(v0.x); hi[1] = __float_as_uint(v0.y); hi[2] = __float_as_uint(v0.z); hi[3] = __float_as_uint(v0.w);
-        hi[4] = __float_as_uint(v1.x); hi[5] = __float_as_uint(v1.y); hi[6] = __float_as_uint(v1.z); hi[7] = __float_as_uint(v1.w);
-        hi[8] = __float_as_uint(v2.x); hi[9] = __float_as_uint(v2.y); hi[10] = __float_as_uint(v2.z); hi[11] = __float_as_uint(v2.w);
-        hi[12] = __float_as_uint(v3.x); hi[13] = __float_as_uint(v3.y); hi[14] = __float_as_uint(v3.z); hi[15] = __float_as_uint(v3.w);
-        lo[0] = lo2(v0.x, v0.y); lo[1] = lo2(v0.z, v0.w); lo[2] = lo2(v1.x, v1.y); lo[3] = lo2(v1.z, v1.w);
-        lo[4] = lo2(v2.x, v2.y); lo[5] = lo2(v2.z, v2.w); lo[6] = lo2(v3.x, v3.y); lo[7] = lo2(v3.z, v3.w);
-        // all conditions below are warp-uniform (o and h are): the stores are warp-collective
-        if (two && o + 1 < pl.K32) tmem_st16(colA + 8 * o, hi);
-        else if (o < pl.K32) tmem_st8(colA + 8 * o, hi);
-        if (two) tmem_st8(colL + 4 * o, lo);
-        else tmem_st4(colL + 4 * o, lo);
-      }
-      const float2 zd2 = __fadd2_rn(zdA, zdB), qd2 = __fadd2_rn(qdA, qdB), ln2 = __fadd2_rn(lnA, lnB);
-      zq_s[(b2 * 2 + h) * 128 + r] = make_float4(zd2.x + zd2.y, qd2.x + qd2.y, ln2.x + ln2.y, 0.f);
+      float zdot, quad, lin;
+      split_row<HAS_LIN, DT>(hrow, coef_s, Dp, D, o_begin, o_end, K32, colA, colL, zdot, quad, lin);
+      float* zq = zq_s + s * 768 + h * 128 + r;
+      zq[0] = zdot; zq[256] = quad;
+      if (HAS_LIN) zq[512] = lin;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&a_ready[b2]);
       TC_TRACE(2, i, 2);
     }
-  } else if (warp < 12) {
-    // ===== softmax warps: thread r owns accumulator row r (TMEM lane r) =====
-    const int r = threadIdx.x - 256;
+  } else if (warp >= kWarpSoft0 && warp < kWarpSoft0 + 8) {
+    // ===== softmax warpgroups: group p handles tiles i = p, p + 2, ...; thread r owns accumulator row r =====
+    reg_inc<kRegSoftmax>();
+    const int p = (warp - kWarpSoft0) >> 2;
+    const int r = (threadIdx.x - kWarpSoft0 * 32) & 127;
     const bool active = r < rows;
     const int k = active ? r / TB : 0, tt = active ? r - k * TB : 0;
     const bool tanh_on = d.add_tanh && d.simi != 4;
     const bool cosine = d.simi == 4;
     const float zc = d.use_time_warp ? zconst[n] : 0.f;
-    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(p * 64);
     float l_acc = 0.f, smax = -INFINITY, ties = 0.f, am_t = 3.0e38f, am_j = 0.f;
     const float4* col4 = reinterpret_cast<const float4*>(col_s);
     const float4* cap4 = reinterpret_cast<const float4*>(cap_s);
-    for (int i = 0; i < ntile; ++i) {
-      const int s = i % S, b2 = i & 1;
+    const uint8_t* mrow = hall_mask + ((size_t)n * d.K + k) * d.T;
+    // the mask byte of the NEXT tile is fetched while this one is processed (a global load per tile
+    // on the critical path costs ~1000 cycles)
+    uint8_t mh_next = 1;
+    {
+      const int t0 = (tile_begin + p) * TB + tt;
+      if (d.has_mask && active && p < ntile && t0 < d.T) mh_next = mrow[t0];
+    }
+    for (int i = p; i < ntile; i += 2) {
+      const int s = i % S;
       const int t = (tile_begin + i) * TB + tt;
       const bool in_range = active && t < d.T;
-      uint8_t mh_u = 1;
-      if (in_range && d.has_mask) mh_u = hall_mask[((size_t)n * d.K + k) * d.T + t];
+      const bool mh = in_range && mh_next != 0;
+      {
+        const int t2 = t + 2 * TB;
+        mh_next = 1;
+        if (d.has_mask && active && i + 2 < ntile && t2 < d.T) mh_next = mrow[t2];
+      }
       TC_TRACE(3, i, 0);
-      mbar_wait(&a_ready[b2], (i >> 1) & 1);     // the split warps' row statistics are visible
-      const float4* zq0 = zq_s + (b2 * 2) * 128;
-      const float4* zq1 = zq0 + 128;
-      const float4 p0 = zq0[active ? r : 0], p1 = zq1[active ? r : 0];
+      mbar_wait_relaxed(&a_ready[p], (i >> 1) & 1);     // the split warps' row statistics are visible
+      const float* zq = zq_s + s * 768;
       float g = 1.f;
       if (d.use_time_warp) {
         float z = zc;
-        for (int kk = 0; kk < d.K; ++kk) z += zq0[kk * TB + tt].x + zq1[kk * TB + tt].x;
+        for (int kk = 0; kk < d.K; ++kk) z += zq[kk * TB + tt] + zq[128 + kk * TB + tt];
         const int tc = t < d.T ? t : d.T - 1;
         const float tz = 1.f - 2.f * rcp_approx(exp2f_approx(z * 2.885390081777927f) + 1.f);   // tanh(z)
         g = tz * window_count(tc, d.T, d.warp_type, d.window);
         if (c_col != nullptr && k == 0 && in_range) c_col[(size_t)n * d.T + t] = tz;
       }
+      const int rr = active ? r : 0;
+      const float quad = zq[256 + rr] + zq[384 + rr];
+      const float lin = HAS_LIN ? zq[512 + rr] + zq[640 + rr] : 0.f;
       float c1, c0v;
-      row_coefs(d, g, p0.z + p1.z, p0.y + p1.y, c1, c0v);
+      row_coefs(d, g, lin, quad, c1, c0v);
       const float p_c0 = cosine ? 0.f : c0v;
-      const bool mh = in_range && mh_u != 0;
-      mbar_wait(&acc_full[b2], (i >> 1) & 1);
+      mbar_wait_relaxed(&acc_full[p], (i >> 1) & 1);
       TC_TRACE(3, i, 1);
       tc_fence_after();
-      const uint32_t taddr = lane_base + (uint32_t)(b2 * 64);
       float a[32];
       float m = -INFINITY;
       const float2 c1c1 = make_float2(c1, c1), c0c0 = make_float2(p_c0, p_c0);
@@ -487,9 +590,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         tmem_ld16_issue(taddr + 16 * hh, x0);
         tmem_ld16_issue(taddr + 32 + 16 * hh, x1);
         tmem_ld_wait();
-        if (hh == 1) {           // both accumulator halves are in registers: the buffers can be refilled
+        if (hh == 1) {           // both accumulator halves are in registers: the MMA warp may refill the buffer
           tc_fence_before();
-          mbar_arrive(&ep_done[b2]);
+          mbar_arrive(&ep_done[p]);
         }
         // branch-free logits.  |tanh| <= 1, so th + (-1e30) == -1e30 exactly: exp_mask is a min
         // with the per-column cap
@@ -517,6 +620,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         for (int j = 0; j < 32; ++j) { a[j] = fminf(cap_s[j], FVTA_VERY_NEGATIVE); m = fmaxf(m, a[j]); }
       }
       TC_TRACE(3, i, 2);
+      // softmax weight first: the weighted-sum warps are the next stage of the pipeline
+      float w = 0.f;
+      if (in_range) {
+        w = (m <= -1e29f) ? kMaskedWeight : exp2f_approx((m - 1.f) * 1.4426950408889634f);
+        l_acc += w;
+      }
+      wg_s[s * 128 + r] = w * g;
+      mbar_arrive(&wg_ready[s]);
       if (a_logits != nullptr && in_range) {
         float* arow = a_logits + (((size_t)n * d.K + k) * d.T + t) * d.JQ;
         if ((d.JQ & 3) == 0) {
@@ -547,120 +658,88 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
           if (jm >= 0 && (float)t < am_t) { am_t = (float)t; am_j = (float)jm; }
         }
       }
-      float w = 0.f;
-      if (in_range) {
-        w = (m <= -1e29f) ? kMaskedWeight : expf(m - 1.f);
-        l_acc += w;
-      }
-      wg_s[s * 128 + r] = w * g;
-      mbar_arrive(&wg_ready[s]);
       TC_TRACE(3, i, 3);
     }
-    // ---- slab statistics: per-modality reductions over the TB threads owning its rows ----
-    red_s[r] = l_acc; red_s[128 + r] = smax; red_s[256 + r] = ties; red_s[384 + r] = am_t; red_s[512 + r] = am_j;
-    named_bar_sync(1, 128);
-    if (r < d.K) {
+    // ---- slab statistics: per-modality reductions over the 2 x TB threads owning its rows ----
+    float* rp = red_s + p * 640;
+    rp[r] = l_acc; rp[128 + r] = smax; rp[256 + r] = ties; rp[384 + r] = am_t; rp[512 + r] = am_j;
+    named_bar_sync(1, 256);
+    if (p == 0 && r < d.K) {
       float l = 0.f, sm = -INFINITY, ti = 0.f, at = 3.0e38f, aj = 0.f;
-      for (int t2 = 0; t2 < TB; ++t2) {
-        const int rr = r * TB + t2;
-        l += red_s[rr];
-        const float v = red_s[128 + rr];
-        if (v > sm) { sm = v; ti = 0.f; at = 3.0e38f; }
-        if (v == sm) {
-          ti += red_s[256 + rr];
-          if (red_s[384 + rr] < at) { at = red_s[384 + rr]; aj = red_s[512 + rr]; }
+      for (int pp = 0; pp < 2; ++pp)
+        for (int t2 = 0; t2 < TB; ++t2) {
+          const float* q = red_s + pp * 640 + r * TB + t2;
+          l += q[0];
+          const float v = q[128];
+          if (v > sm) { sm = v; ti = 0.f; at = 3.0e38f; }
+          if (v == sm) {
+            ti += q[256];
+            if (q[384] < at) { at = q[384]; aj = q[512]; }
+          }
         }
-      }
       float* ps = part_stat + (((size_t)n * pl.slabs + slab) * d.K + r) * kPartW;
       ps[0] = 1.f; ps[1] = l; ps[2] = sm; ps[3] = ti; ps[4] = at; ps[5] = aj; ps[6] = 0.f; ps[7] = 0.f;
       __threadfence();
     }
   } else {
-    // ===== wsum warps: o[k][d4] += sum_rows (w*g) * h; thread u = part * D4 + d4 owns the float4 feature
-    // group d4 over the tile rows [wr0, wr1), which span at most three modalities =====
-    const int u = threadIdx.x - 384;
+    // ===== wsum warps: thread u owns (modality k, features 4*d4 .. 4*d4+3): o += sum_tt (w*g)[k,tt] * h[k,tt,:] =====
+    reg_dec<kRegWsum>();
+    const int u = threadIdx.x - kWarpWsum0 * 32;
     const int D4 = D >> 2;
-    const int nparts = 128 / D4;
-    const bool ws_on = u < nparts * D4;
-    const int ws_d4 = u % D4, ws_part = u / D4;
-    const int wr0 = ws_on ? (ws_part * rows) / nparts : 0;
-    const int wr1 = ws_on ? ((ws_part + 1) * rows) / nparts : 0;
-    const int kb1 = (wr0 / TB + 1) * TB;                      // first row of the next modality
-    const int e0 = min(wr1, kb1), e1 = min(wr1, kb1 + TB);
-    const int ws_n0 = max(e0 - wr0, 0), ws_n1 = max(e1 - e0, 0), ws_n2 = max(wr1 - e1, 0);
-    const int ws_off = wr0 * D + ws_d4 * 4;
-    float4 o_acc[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) o_acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = 0; i < ntile; ++i) {
+    const bool ws_on = u < d.K * D4;
+    const int ws_k = ws_on ? u / D4 : 0, ws_d4 = ws_on ? u - ws_k * D4 : 0;
+    const int ws_off = ws_k * TB * D + ws_d4 * 4;
+    float2 oa = make_float2(0.f, 0.f), ob = oa;
+    for (int i = 0; i < (warp - kWarpWsum0 < ws_warps ? ntile : 0); ++i) {      // warps without work skip the pipeline
       const int s = i % S;
       TC_TRACE(4, i, 0);
-      mbar_wait(&wg_ready[s], (i / S) & 1);
+      mbar_wait_relaxed(&wg_ready[s], (i / S) & 1);
       TC_TRACE(4, i, 1);
       if (ws_on) {
         const float* hp = reinterpret_cast<const float*>(ring + (size_t)s * pl.stage_bytes) + ws_off;
-        const float* wp = wg_s + s * 128 + wr0;
-        auto wsum = [&](int nrow, float4& acc) {
-          float2 oa = make_float2(acc.x, acc.y), ob = make_float2(acc.z, acc.w);
-          int t2 = 0;
-          for (; t2 + 4 <= nrow; t2 += 4) {
-            const float4 h0 = *reinterpret_cast<const float4*>(hp);
-            const float4 h1 = *reinterpret_cast<const float4*>(hp + D);
-            const float4 h2 = *reinterpret_cast<const float4*>(hp + 2 * D);
-            const float4 h3 = *reinterpret_cast<const float4*>(hp + 3 * D);
-            const float w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
-            oa = __ffma2_rn(make_float2(w0, w0), make_float2(h0.x, h0.y), oa);
-            ob = __ffma2_rn(make_float2(w0, w0), make_float2(h0.z, h0.w), ob);
-            oa = __ffma2_rn(make_float2(w1, w1), make_float2(h1.x, h1.y), oa);
-            ob = __ffma2_rn(make_float2(w1, w1), make_float2(h1.z, h1.w), ob);
-            oa = __ffma2_rn(make_float2(w2, w2), make_float2(h2.x, h2.y), oa);
-            ob = __ffma2_rn(make_float2(w2, w2), make_float2(h2.z, h2.w), ob);
-            oa = __ffma2_rn(make_float2(w3, w3), make_float2(h3.x, h3.y), oa);
-            ob = __ffma2_rn(make_float2(w3, w3), make_float2(h3.z, h3.w), ob);
-            hp += 4 * D;
-            wp += 4;
-          }
-          for (; t2 < nrow; ++t2) {
-            const float4 h0 = *reinterpret_cast<const float4*>(hp);
-            const float w0 = wp[0];
-            oa = __ffma2_rn(make_float2(w0, w0), make_float2(h0.x, h0.y), oa);
-            ob = __ffma2_rn(make_float2(w0, w0), make_float2(h0.z, h0.w), ob);
-            hp += D;
-            wp += 1;
-          }
-          acc = make_float4(oa.x, oa.y, ob.x, ob.y);
-        };
-        wsum(ws_n0, o_acc[0]);
-        wsum(ws_n1, o_acc[1]);
-        wsum(ws_n2, o_acc[2]);
+        const float* wp = wg_s + s * 128 + ws_k * TB;
+        int t2 = 0;
+#pragma unroll 2
+        for (; t2 + 4 <= TB; t2 += 4) {
+          const float4 h0 = *reinterpret_cast<const float4*>(hp);
+          const float4 h1 = *reinterpret_cast<const float4*>(hp + D);
+          const float4 h2 = *reinterpret_cast<const float4*>(hp + 2 * D);
+          const float4 h3 = *reinterpret_cast<const float4*>(hp + 3 * D);
+          const float w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+          oa = __ffma2_rn(make_float2(w0, w0), make_float2(h0.x, h0.y), oa);
+          ob = __ffma2_rn(make_float2(w0, w0), make_float2(h0.z, h0.w), ob);
+          oa = __ffma2_rn(make_float2(w1, w1), make_float2(h1.x, h1.y), oa);
+          ob = __ffma2_rn(make_float2(w1, w1), make_float2(h1.z, h1.w), ob);
+          oa = __ffma2_rn(make_float2(w2, w2), make_float2(h2.x, h2.y), oa);
+          ob = __ffma2_rn(make_float2(w2, w2), make_float2(h2.z, h2.w), ob);
+          oa = __ffma2_rn(make_float2(w3, w3), make_float2(h3.x, h3.y), oa);
+          ob = __ffma2_rn(make_float2(w3, w3), make_float2(h3.z, h3.w), ob);
+          hp += 4 * D;
+          wp += 4;
+        }
+        for (; t2 < TB; ++t2) {
+          const float4 h0 = *reinterpret_cast<const float4*>(hp);
+          const float w0 = wp[0];
+          oa = __ffma2_rn(make_float2(w0, w0), make_float2(h0.x, h0.y), oa);
+          ob = __ffma2_rn(make_float2(w0, w0), make_float2(h0.z, h0.w), ob);
+          hp += D;
+          wp += 1;
+        }
       }
       mbar_arrive(&empty[s]);
       TC_TRACE(4, i, 2);
     }
-    // the row ranges of one feature group live on nparts threads: stage every thread's partial
-    // sums and add them per (modality, feature group) in a fixed order (deterministic)
-    if (ws_on) { stg_s[u * 3] = o_acc[0]; stg_s[u * 3 + 1] = o_acc[1]; stg_s[u * 3 + 2] = o_acc[2]; }
-    named_bar_sync(2, 128);
-    for (int idx = u; idx < d.K * D4; idx += 128) {
-      const int k2 = idx / D4, d4 = idx - k2 * D4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int pp = 0; pp < nparts; ++pp) {
-        const int q0 = (pp * rows) / nparts, q1 = ((pp + 1) * rows) / nparts;
-        if (q1 <= q0) continue;
-        const int klo = q0 / TB;
-        const int slot = k2 - klo;
-        if (slot >= 0 && slot < 3 && (slot == 0 || q1 > (klo + slot) * TB)) {
-          const float4 o = stg_s[(pp * D4 + d4) * 3 + slot];
-          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-        }
-      }
-      *reinterpret_cast<float4*>(part_o + (((size_t)n * pl.slabs + slab) * d.K + k2) * Dp + d4 * 4) = v;
+    // one thread holds the whole slab sum of its (modality, feature group): no cross-thread reduction
+    if (ws_on) {
+      *reinterpret_cast<float4*>(part_o + (((size_t)n * pl.slabs + slab) * d.K + ws_k) * Dp + ws_d4 * 4) =
+          make_float4(oa.x, oa.y, ob.x, ob.y);
+      __threadfence();
     }
-    __threadfence();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 17) {
+  TC_STAMP(2);
+  if (warp == kWarpMma) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcTmemCols) : "memory");
   }
 
@@ -672,6 +751,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     *last_flag = (ticket == pl.slabs - 1) ? 1 : 0;
   }
   __syncthreads();
+  TC_STAMP(3);
   if (*last_flag == 0) return;
   __threadfence();
   {
@@ -785,7 +865,7 @@ int attn_fwd_tc_launch(const FvtaAttnDesc& d, const AttnLayout& L, const float* 
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed", cudaErrorInvalidValue); return FVTA_E_LAUNCH; }
   const bool has_lin = (d.simi == 1 || d.simi == 3);   // w_lin is identically zero otherwise
-  auto kern = has_lin ? attn_fwd_tc<true> : attn_fwd_tc<false>;
+  auto kern = has_lin ? attn_fwd_tc<true, 0> : (d.D == 100 ? attn_fwd_tc<false, 100> : attn_fwd_tc<false, 0>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
   if (e != cudaSuccess) { set_last_error("attn_fwd_tc smem attr", e); return FVTA_E_LAUNCH; }
   dim3 grid(pl.slabs, d.N);

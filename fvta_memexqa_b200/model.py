@@ -233,7 +233,7 @@ class Model:
         """Everything the device step reads, as ONE pinned host buffer (packing.to_blob): the packed
         reader inputs, the question mask, the labels and the two embedding tables.  A data loader
         builds this once per batch (TensorBatch caches it); to_device then issues a single copy."""
-        from .packing import build_pack, to_blob
+        from .packing import build_pack, to_blob, emb_touch_flags
         host = {k: (torch.as_tensor(v) if not isinstance(v, torch.Tensor) and hasattr(v, "shape") else v)
                 for k, v in feed.items()}
         tensors, meta = build_pack(host, self.config, min_text_cap=getattr(self, "pin_text_cap", 0),
@@ -241,6 +241,8 @@ class Model:
         for k in self._DEVICE_KEYS:
             if k in host and host[k] is not None:
                 tensors[k] = host[k]
+        if host.get("is_train", False) and self.params.touch_len:
+            tensors["emb_touch"] = emb_touch_flags(host, self.params.touch_rows, self.params.touch_len)
         blob, index = to_blob(tensors)
         meta["blob_bytes"] = blob.numel()
         return {"blob": blob, "index": index, "meta": meta, "host": host}

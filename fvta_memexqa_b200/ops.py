@@ -153,15 +153,22 @@ def attn_backward(fwd, d_g1_all, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=Non
     return out
 
 
-def adadelta_step(var, grad, accum, accum_update, update_mask, lr, rho=0.95, eps=1e-8, grad_scale=1.0):
-    """fvta_adadelta over flat buffers (in place)."""
+def adadelta_step(var, grad, accum, accum_update, update_mask, lr, rho=0.95, eps=1e-8, grad_scale=1.0,
+                  touch_index=None, touch=None):
+    """fvta_adadelta over flat buffers (in place).  touch_index / touch: sparse rows of the embedding
+    tables (tf.nn.embedding_lookup -> IndexedSlices -> sparse_apply_adadelta; see the header)."""
     lib = _lib.load()
     f32 = torch.float32
     for t, nme in ((var, "var"), (grad, "grad"), (accum, "accum"), (accum_update, "accum_update")):
         if _req(t, f32, nme) is not t:
             raise _lib.FvtaError("%s must be contiguous" % nme)
+    if touch_index is not None:
+        touch_index = _req(touch_index, torch.int32, "touch_index")
+        touch = _req(touch, f32, "touch")
+        if touch_index.numel() != var.numel():
+            raise _lib.FvtaError("touch_index must have one entry per parameter")
     rc = lib.fvta_adadelta(var.numel(), _ptr(var), _ptr(grad), _ptr(accum), _ptr(accum_update),
-                           _ptr(update_mask), lr, rho, eps, grad_scale, _stream())
+                           _ptr(update_mask), _ptr(touch_index), _ptr(touch), lr, rho, eps, grad_scale, _stream())
     check(rc, "fvta_adadelta")
 
 

@@ -115,6 +115,21 @@ def build_pack(feed, config, bucket=512, min_text_cap=0, min_img_cap=0):
     return t, meta
 
 
+def emb_touch_flags(feed, touch_rows, touch_len):
+    """1.0 for every row of the sparse embedding tables (params.SPARSE_TABLES) that some id of the FED
+    arrays looks up -- padding positions included: the reference feeds the padded id arrays to
+    tf.nn.embedding_lookup (model_v2.py:534-546, :599-606), so NULL (id 0) is looked up whenever a batch
+    has any padding, and TF's sparse Adadelta decays that row's accumulators even with a zero
+    gradient.  Ids >= VW address the fed GloVe matrix (model_v2.py:596, :1335), which is not trained."""
+    flags = torch.zeros(touch_len, dtype=torch.float32)
+    for name, (base, rows) in touch_rows.items():
+        suffix = "_c" if name.endswith("char_emb") else ""
+        for site in TEXT_SITES:
+            ids = feed[site + suffix].reshape(-1).long()
+            flags[base + ids[ids < rows]] = 1.0
+    return flags
+
+
 def to_blob(tensors, pin=True):
     """Concatenate CPU tensors into ONE (pinned) byte buffer so a step's inputs travel in a single
     host->device copy.  Returns (blob uint8 [nbytes], index: name -> (offset, shape, dtype))."""

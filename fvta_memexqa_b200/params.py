@@ -69,6 +69,11 @@ def param_specs(config):
 # ceil -> cast(int64): its gradient is None and apply_gradients skips it (trainer.py:23-27).
 NEVER_UPDATED = ("time_warp/time_warp_C/time_warp_window_t",)
 
+# Variables read through tf.nn.embedding_lookup (model_v2.py:534 char_emb, :596-600 word_emb_mat via
+# the axis-0 concat): their gradients are IndexedSlices, so AdadeltaOptimizer applies
+# sparse_apply_adadelta [TF] -- rows no id of the batch looked up keep var and both accumulators.
+SPARSE_TABLES = ("emb/var/char_emb", "emb/word/var/word_emb_mat")
+
 
 def _init(shape, kind, gen):
     if kind == "zeros":
@@ -117,7 +122,23 @@ class ParamStore:
             o, n, _ = self.offsets[name]
             flat[o:o + n] = _init(shape, kind, gen).reshape(-1)
         self.flat = flat.to(device=device, dtype=dtype)
-        self.grad_flat = torch.zeros_like(self.flat)
+        # "row was looked up this step" flags of the sparse tables live in a tail of the gradient
+        # buffer, so the data-parallel all-reduce of that ONE buffer also forms their union over ranks
+        self.touch_rows = OrderedDict()           # table name -> (first flag, rows)
+        tlen = 0
+        tindex = torch.full((off,), -1, dtype=torch.int32)
+        for name in SPARSE_TABLES:
+            if name in self.offsets:
+                o, n, shape = self.offsets[name]
+                rows, dim = shape
+                self.touch_rows[name] = (tlen, rows)
+                tindex[o:o + n] = (tlen + torch.arange(rows, dtype=torch.int32)).repeat_interleave(dim)
+                tlen += rows
+        self.touch_len = (tlen + 3) // 4 * 4
+        self.touch_index = tindex.to(device) if tlen else None
+        self.grad_buf = torch.zeros(off + self.touch_len, dtype=dtype, device=device)
+        self.grad_flat = self.grad_buf[:off]
+        self.touch = self.grad_buf[off:] if tlen else None
         self.accum = torch.zeros_like(self.flat)          # Adadelta E[g^2]
         self.accum_update = torch.zeros_like(self.flat)   # Adadelta E[dx^2]
         # 1.0 where Adadelta may touch the slot, 0.0 for never-updated variables / padding

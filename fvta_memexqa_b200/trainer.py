@@ -28,17 +28,21 @@ class Trainer:
         """forward + backward + (all-reduce) + Adadelta on device tensors; returns the loss tensor."""
         m = self.model
         ps = m.params
-        ps.grad_flat.zero_()
+        ps.grad_buf.zero_()
+        if ps.touch is not None:
+            # which embedding rows this batch looks up (tail of the gradient buffer: all-reduced with it)
+            ps.touch.copy_(dfeed["emb_touch"])
         loss, _, _ = m.forward(dfeed, is_train=True)
         loss.backward()
         loss = loss.detach()
         m.release_graph()
         scale = 1.0
         if self.dp is not None:
-            scale = self.dp.all_reduce_grads(ps.grad_flat)
+            scale = self.dp.all_reduce_grads(ps.grad_buf)
             loss = self.dp.mean_loss(loss)
         ops.adadelta_step(ps.flat, ps.grad_flat, ps.accum, ps.accum_update, ps.update_mask,
-                          self.lr, self.rho, self.eps, grad_scale=scale)
+                          self.lr, self.rho, self.eps, grad_scale=scale, touch_index=ps.touch_index,
+                          touch=ps.touch)
         m.global_step += 1
         self.global_step = m.global_step
         return loss
@@ -50,11 +54,24 @@ class Trainer:
         launch-latency bound, so replaying a graph is the difference between the GPU and the
         Python interpreter setting the pace.  Requires pinned padded shapes; graphs are keyed by
         the packed-token buckets (packing.build_pack) and captured on first use."""
-        self._graphs = {}
+        from collections import OrderedDict
+        self._graphs = OrderedDict()
         self._graph_warmup = warmup
+        self.max_graphs = 8          # bounded: each entry retains a static input blob and a memory pool
         if example_feed is not None:
             self._capture(self.model.to_device(example_feed))
         return self
+
+    @staticmethod
+    def _graph_key(meta, index):
+        """Everything a captured step bakes in as a constant: every shape-bearing field of the packing
+        meta (N, M, K, T, JMAX, JQ, arena rows, sequence counts, ranges, packed capacities, ...) and the
+        layout of the step input (name, offset, shape, dtype of every tensor in the blob -- this is
+        where e.g. the photo-table row count lives).  Only the true token counts may differ: the
+        kernels read the per-sequence lengths from the blob."""
+        m = tuple(sorted((k, v) for k, v in meta.items() if k not in ("text_ntok", "img_ntok")))
+        lay = tuple(sorted((k, int(o), tuple(shape), str(dtype)) for k, (o, shape, dtype) in index.items()))
+        return (m, lay)
 
     def _capture(self, dfeed):
         from . import _lib
@@ -62,10 +79,12 @@ class Trainer:
         m = self.model
         ps = m.params
         meta = dfeed["_meta"]
-        key = (meta["text_cap"], meta["img_cap"], meta["blob_bytes"])
         from .packing import blob_views
         hsi_index = {k: (v.data_ptr() - dfeed["_blob"].data_ptr(), tuple(v.shape), v.dtype)
                      for k, v in dfeed.items() if isinstance(v, torch.Tensor) and k != "_blob"}
+        key = self._graph_key(meta, hsi_index)
+        while len(self._graphs) >= self.max_graphs:
+            self._graphs.popitem(last=False)
         static_blob = dfeed["_blob"].clone()
         static = blob_views(static_blob, hsi_index)
         static.update({k: v for k, v in dfeed.items() if not isinstance(v, torch.Tensor)})
@@ -95,16 +114,22 @@ class Trainer:
     def graph_step(self, feed):
         """Replay the captured step on a new batch (host feed or device step input).  Returns the
         loss tensor (device)."""
-        meta = feed["meta"] if "blob" in feed else None
         dfeed = None
-        if meta is None:
+        if "blob" in feed:
+            key = feed.get("_graph_key")
+            if key is None:          # cached on the host step input: computed once per batch object
+                key = feed["_graph_key"] = self._graph_key(feed["meta"], feed["index"])
+        else:
             dfeed = self.model.to_device(feed)
-            meta = dfeed["_meta"]
-        key = (meta["text_cap"], meta["img_cap"], meta["blob_bytes"])
+            index = {k: (v.data_ptr() - dfeed["_blob"].data_ptr(), tuple(v.shape), v.dtype)
+                     for k, v in dfeed.items() if isinstance(v, torch.Tensor) and k != "_blob"}
+            key = self._graph_key(dfeed["_meta"], index)
         entry = self._graphs.get(key)
         if entry is None:
             dfeed = dfeed if dfeed is not None else self.model.to_device(feed)
             entry = self._capture(dfeed)
+        else:
+            self._graphs.move_to_end(key)
         graph, static, loss = entry
         src = feed["blob"] if "blob" in feed else dfeed["_blob"]     # pinned host blob: copy it straight in
         if src.numel() != static["_blob"].numel():

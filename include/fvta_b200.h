@@ -271,10 +271,15 @@ int fvta_output_loss(int32_t N, int32_t C, int32_t D, const float* gq, const flo
  * (trainer.py:16-27; TF defaults rho=0.95, eps=1e-8).  `update_mask` (nullable) is 1.0 where
  * the slot is trainable-and-has-a-gradient, 0.0 otherwise (window_t is never updated).
  * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce).
+ * touch_index [n] int32 / touch (both nullable): sparse rows.  The reference reads its embedding
+ * tables through tf.nn.embedding_lookup (model_v2.py:534, :596-600), whose gradient is IndexedSlices,
+ * so TF runs sparse_apply_adadelta on them: a row no id of the batch looked up keeps var AND both
+ * accumulators.  touch_index[i] >= 0 selects the entry of `touch` that is > 0 iff the row holding
+ * element i was looked up this step; -1 marks a dense variable.
  * ---------------------------------------------------------------------------------------- */
 int fvta_adadelta(int64_t n, float* var, const float* grad, float* accum, float* accum_update,
-                  const float* update_mask, float lr, float rho, float eps, float grad_scale,
-                  void* stream);
+                  const float* update_mask, const int32_t* touch_index, const float* touch,
+                  float lr, float rho, float eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,11 +41,29 @@ def forward(feed, params, config, is_train=False, block="collapsed"):
     return out
 
 
+# variables whose gradient TF holds as IndexedSlices (read through tf.nn.embedding_lookup:
+# model_v2.py:534 char_emb, :596-600 word_emb_mat via the axis-0 concat with the fed GloVe matrix)
+SPARSE_TABLES = {"emb/var/char_emb": "_c", "emb/word/var/word_emb_mat": ""}
+TEXT_INPUTS = ("q", "at", "ad", "when", "where", "pts", "choices")
+
+
+def looked_up_rows(feed, name, rows):
+    """Rows of a sparse table that the FED id arrays address (padding ids included: the reference
+    looks up the padded arrays, model_v2.py:534-546, :599-606)."""
+    hit = torch.zeros(rows, dtype=torch.bool)
+    for site in TEXT_INPUTS:
+        ids = feed[site + SPARSE_TABLES[name]].reshape(-1).long()
+        hit[ids[ids < rows]] = True
+    return hit
+
+
 def train_step(feed, params, state, config, block="collapsed", never_updated=()):
     """One reference training step (trainer.py:30-40): loss, d loss / d every trainable,
     Adadelta(lr=init_lr).  ``params``/``state`` are dicts of tensors; returns
     (loss, grads, new_params, new_state).  Variables whose gradient is None (window_t) are
-    skipped like ``apply_gradients`` skips them."""
+    skipped like ``apply_gradients`` skips them.  The two embedding tables get TF's sparse
+    Adadelta [TF: AdadeltaOptimizer._apply_sparse -> sparse_apply_adadelta on the de-duplicated
+    IndexedSlices]: rows that were not looked up keep var, accum and accum_update."""
     leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     out = forward(feed, leaves, config, is_train=True, block=block)
     loss = out["loss"]
@@ -59,7 +77,12 @@ def train_step(feed, params, state, config, block="collapsed", never_updated=())
         if g is None:
             new_state[k] = (acc, acc_u)
             continue
-        var, acc, acc_u = adadelta_update(params[k], g, acc, acc_u, config.init_lr)
+        var, acc_n, acc_un = adadelta_update(params[k], g, acc, acc_u, config.init_lr)
+        if k in SPARSE_TABLES:
+            hit = looked_up_rows(feed, k, params[k].shape[0]).unsqueeze(1)
+            var = torch.where(hit, var, params[k])
+            acc_n = torch.where(hit, acc_n, acc)
+            acc_un = torch.where(hit, acc_un, acc_u)
         new_params[k] = var
-        new_state[k] = (acc, acc_u)
+        new_state[k] = (acc_n, acc_un)
     return loss.detach(), grads, new_params, new_state, out

@@ -47,6 +47,8 @@ def oracle32(cfg, params, inp):
 CASE_BOUND = {
     (2, 6, 3, 17, 100, 25, 1, False, True, 3, False): 2e-3,
     (2, 6, 2, 40, 36, 13, 3, True, True, 4, True): 1e-3,
+    # D = 256 with N(0,1) rows: |c0| = g^2 |w2.h^2| reaches ~1e3 (ulp 6e-5) before the tanh
+    (2, 6, 2, 40, 256, 32, 2, True, True, 5, False): 3e-4,
 }
 
 

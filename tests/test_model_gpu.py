@@ -100,6 +100,43 @@ def test_c2_step_vs_collapsed_oracle(cuda_device):
     run_case(cfg, "collapsed", steps=1, glove=50)
 
 
+def test_sparse_adadelta_on_embedding_tables(cuda_device):
+    """The embedding tables are read through tf.nn.embedding_lookup, so TF updates them with
+    sparse_apply_adadelta: a row that the CURRENT batch does not look up keeps its accumulators
+    (a dense update would decay them by rho and change the row's NEXT update).  Batches A, B, A:
+    rows looked up by A only see the difference at step 3."""
+    cfg = tiny_config()
+    feeds = [make_feed(cfg, seed=s, glove_vocab=10) for s in (5, 6, 5)]
+    # make batch B avoid a few word / char ids that batch A uses, so the two sets really differ
+    for k in ("q", "at", "ad", "when", "where", "pts", "choices"):
+        feeds[1][k] = torch.where((feeds[1][k] >= 2) & (feeds[1][k] < 8), torch.full_like(feeds[1][k], 9), feeds[1][k])
+        feeds[1][k + "_c"] = torch.where((feeds[1][k + "_c"] >= 2) & (feeds[1][k + "_c"] < 6),
+                                         torch.full_like(feeds[1][k + "_c"], 7), feeds[1][k + "_c"])
+    model = get_model(cfg)
+    trainer = Trainer(model, cfg)
+    params = {k: model.params.view(k).detach().cpu().double() for k in model.params.offsets}
+    dense = dict(params)
+    state, dstate = {}, {}
+    for feed in feeds:
+        feed64 = {k: (v.double() if v.is_floating_point() else v) for k, v in feed.items()}
+        trainer.step(None, ((), TensorBatch(feed, cfg.batch_size)))
+        _, _, params, state, _ = oracle_full.train_step(feed64, params, state, cfg, block="literal",
+                                                        never_updated=NEVER_UPDATED)
+        saved = dict(oracle_full.SPARSE_TABLES)
+        oracle_full.SPARSE_TABLES.clear()                   # the dense variant, to prove the test can tell
+        try:
+            _, _, dense, dstate, _ = oracle_full.train_step(feed64, dense, dstate, cfg, block="literal",
+                                                            never_updated=NEVER_UPDATED)
+        finally:
+            oracle_full.SPARSE_TABLES.update(saved)
+    told_apart = False
+    for k in ("emb/var/char_emb", "emb/word/var/word_emb_mat"):
+        got = model.params.view(k).detach().cpu().double()
+        assert rel_err(got, params[k]) < 5 * TOL, k
+        told_apart |= rel_err(dense[k], params[k]) > 20 * TOL
+    assert told_apart, "batches A and B look up the same rows: the test cannot see sparse vs dense"
+
+
 def test_step_vis_surface(cuda_device):
     cfg = tiny_config()
     model = get_model(cfg)

@@ -124,6 +124,103 @@ __global__ void __launch_bounds__(128, 1) probe(const float* A32, const float* B
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tb) : "memory");
 }
 
+// ---- timing: cycles per tcgen05.mma for the operand sources / shapes the attention kernels consider ----
+// mode 0: A in TMEM (TS), 1: A in shared memory (SS).  fmt 0 = f16, 2 = tf32.  reps MMAs back to back into
+// one accumulator, then commit; cycles from first issue to the commit's arrival.
+__global__ void __launch_bounds__(128, 1) mma_rate(int mode, int fmt, int N, int reps, int nacc, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* a_s = smem;              // 128 rows x 128 B
+  uint8_t* b_s = smem + 16384;      // 256 rows x 128 B
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_ptr;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_ptr)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tmem_ptr;
+  {
+    uint32_t r[8];
+    for (int c = 0; c < 8; ++c) r[c] = 0x3c003c00u;
+    const uint32_t lane_base = tb + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < 64; c += 8)   // A region: columns 256..319
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(lane_base + 256 + c),
+                   "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid == 0) {
+    const uint32_t id = idesc(fmt, N);
+    const uint32_t tb0 = tb;
+    const long long t0 = clock64();
+    for (int i = 0; i < reps; ++i) {
+      const int ks = i & 3;
+      const uint64_t bd = desc_sw128(smem_u32(b_s) + ks * 32);
+      const uint32_t tb = tb0 + (uint32_t)((i % nacc) * 64);     // independent accumulators, round robin
+      if (mode == 0) {
+        if (fmt == 2)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                       ::"r"(tb), "r"(tb0 + 256 + ks * 8), "l"(bd), "r"(id), "r"((uint32_t)(i >= nacc)) : "memory");
+        else
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                       ::"r"(tb), "r"(tb0 + 256 + ks * 8), "l"(bd), "r"(id), "r"((uint32_t)(i >= nacc)) : "memory");
+      } else {
+        const uint64_t ad = desc_sw128(smem_u32(a_s) + ks * 32);
+        if (fmt == 2)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(tb), "l"(ad), "l"(bd), "r"(id), "r"((uint32_t)(i > 0)) : "memory");
+        else
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                       ::"r"(tb), "l"(ad), "l"(bd), "r"(id), "r"((uint32_t)(i > 0)) : "memory");
+      }
+    }
+    const long long t1 = clock64();
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                   : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tb) : "memory");
+}
+
+static void run_rates() {
+  long long* d; cudaMalloc(&d, 16);
+  cudaFuncSetAttribute(mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  const int reps = 256;
+  printf("cycles per tcgen05.mma (M=128, %d back to back): issue loop / until commit arrives\n", reps);
+  for (int mode = 0; mode < 2; ++mode)
+    for (int fmt = 0; fmt <= 2; fmt += 2)
+      for (int N = 32; N <= 64; N *= 2)
+      for (int nacc = 1; nacc <= 4; nacc *= 2) {
+        long long h[2];
+        for (int rep = 0; rep < 2; ++rep) {
+          mma_rate<<<1, 128, 49152>>>(mode, fmt, N, reps, nacc, d);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf("mma_rate failed: %s\n", cudaGetErrorString(e)); return; }
+        }
+        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("  A in %s  %-4s N=%-3d accumulators=%d  issue %.1f  complete %.1f\n", mode == 0 ? "TMEM" : "smem", fmt == 2 ? "tf32" : "f16", N, nacc,
+               (double)h[0] / reps, (double)h[1] / reps);
+      }
+}
+
 static float trunc_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 static float rn_tf32(float x) {
   uint32_t u; memcpy(&u, &x, 4);
@@ -152,6 +249,7 @@ int main() {
   cudaError_t e = cudaDeviceSynchronize();
   printf("probe: %s\n", cudaGetErrorString(e));
   if (e != cudaSuccess) return 1;
+  run_rates();
   std::vector<float> O(3 * 128 * NB);
   cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
   typedef float (*Cv)(float);
