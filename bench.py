@@ -208,16 +208,35 @@ def attention_roofline(dev, iters=10, with_logits=False):
                                      p["time_warp/WC/W"], p["time_warp/WC/b"], want_logits=with_logits,
                                      reuse=bufs["r"], folded=folded)
 
+    graphs = {}
+
+    def graph_for(folded):
+        """The call as a CUDA graph (what the training step replays): the host cost of the ctypes
+        binding (~50 us per call) would otherwise leave the GPU idle between 100 us launches."""
+        if folded not in graphs:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                call(folded)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                call(folded)
+            graphs[folded] = g_
+        return graphs[folded]
+
     def timed(n, folded, burst=20):
-        """n event pairs, each around `burst` back-to-back launches (no host sync inside a pair: the
+        """n event pairs, each around `burst` back-to-back replays (no host sync inside a pair: the
         GPU stays busy, so the SM clock is the sustained one, not the idle-ramp one a lone 0.1 ms launch
         sees).  The working set (315 MB) exceeds L2, so consecutive launches do not feed each other."""
+        g_ = graph_for(folded)
         ts = []
         for _ in range(n):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(burst):
-                call(folded)
+                g_.replay()
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e-3 / burst)
@@ -242,7 +261,7 @@ def attention_roofline(dev, iters=10, with_logits=False):
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
     h0 = time.perf_counter()
-    t_op, _ = timed(iters, False)        # the whole operator: operand folding (3 small kernels) + the tile kernel
+    t_op, _ = timed(iters, False)        # the whole operator: operand folding (one small kernel) + the tile kernel
     # the dominant kernel alone: the workspace already holds the folded question operands
     # (FvtaAttnDesc.ws_from_fwd), so the call is exactly ONE launch: attn_fwd_tc incl. its fused combine
     n0 = lib.fvta_launch_count()
@@ -268,7 +287,7 @@ def attention_roofline(dev, iters=10, with_logits=False):
             "launch_ms_min": t_min * 1e3, "parity": parity, "clocks": clocks,
             "whole_op": {"launch_ms": t_op * 1e3, "achieved": bytes_alg / t_op / 1e9,
                          "frac": bytes_alg / t_op / 1e9 / peak,
-                         "what": "fvta_attn_fwd = operand folding (3 small kernels) + attn_fwd_tc"},
+                         "what": "fvta_attn_fwd = operand folding (attn_prep_all) + attn_fwd_tc"},
             "workload": "C3-max: N=4 K=6 T=64*64*8=32768 D=100 JQ=32, mask density 1.0, working set "
                         "%.0f MB > L2" % (bytes_alg / 1e6),
             "algorithmic_bytes": bytes_alg, "launch_ms": t * 1e3, "peak_source": how}
@@ -336,6 +355,11 @@ def run_own(args):
     model = get_model(cfg)
     dp.broadcast_params(model.params.flat)
     trainer = Trainer(model, cfg, dp=dp if world > 1 else None)
+    collective = "none (1 GPU)"
+    if world > 1:
+        fused = (not args.nccl) and dp.enable_p2p(model.params)
+        collective = ("fvta_p2p_allreduce_adadelta: gradient sum over NVLink peer memory fused with Adadelta, one launch"
+                      if fused else "ncclAllReduce of the flat gradient buffer + fvta_adadelta")
     data = SyntheticDataset(cfg, num_examples=PER_GPU_BATCH * 4, seed=1234 + 1000 * rank, pin=True)
     batches = list(data.get_batches(PER_GPU_BATCH, num_steps=4, shuffle=False))
     # one packed-size bucket for every batch of every rank -> one graph, captured in lockstep
@@ -395,7 +419,16 @@ def run_own(args):
     for i in range(max(1, args.warmup // 2)):
         trainer.step(None, batches[i % len(batches)])
     sync_all()
-    t_steps, t_bracket, res = timed_steps(lambda i: trainer.step(None, batches[i % len(batches)]), args.steps)
+    def e2e_step(i):
+        # the reference-facing call with HOST buffers.  The input of step i+1 starts its host->device
+        # copy on a copy stream before step i is launched (Trainer.prefetch); step i then waits for ITS
+        # copy, issued one step earlier.  One H2D copy per step, all inside the bracketed region.
+        if not args.no_prefetch and not args.no_graph:
+            trainer.prefetch(batches[(i + 1) % len(batches)])
+        return trainer.step(None, batches[i % len(batches)])
+    if not args.no_prefetch and not args.no_graph:
+        trainer.prefetch(batches[0])
+    t_steps, t_bracket, res = timed_steps(e2e_step, args.steps)
     loss_val = res[0]
     t_e2e = dp.max_over_ranks(t_steps)
     t_e2e_bracket = dp.max_over_ranks(t_bracket)
@@ -414,7 +447,9 @@ def run_own(args):
                     "ms_per_step_incl_l2_flush": 1000.0 * t_e2e_bracket / args.steps},
             "ms_per_step_incl_l2_flush": 1000.0 * t_dev_bracket / args.steps,
             "gpu_launches": int(launches), "final_loss": loss_val}
-    line["config"]["execution"] = "eager launches" if args.no_graph else "one CUDA graph per step"
+    # how the step ran (not part of `config`: the workload is the same for both arms)
+    line["execution"] = "eager launches" if args.no_graph else "one CUDA graph per step"
+    line["collective"] = collective
     if world == 1:
         line["roofline"] = attention_roofline(dev)
         line["roofline_with_logits"] = attention_roofline(dev, with_logits=True)
@@ -453,6 +488,10 @@ def main():
     ap.add_argument("--impl", type=str, default="fvta_b200", choices=["fvta_b200", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="launch kernels eagerly")
+    ap.add_argument("--no-prefetch", dest="no_prefetch", action="store_true",
+                    help="e2e leg without Trainer.prefetch (the step input is copied in front of each step)")
+    ap.add_argument("--nccl", action="store_true",
+                    help="data parallel with ncclAllReduce + fvta_adadelta instead of the fused peer-memory kernel (A/B)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3

@@ -94,6 +94,10 @@ SYMBOLS = {
     "fvta_adadelta": (ctypes.c_int, [ctypes.c_int64, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                      c_i32_p, c_float_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                      ctypes.c_void_p]),
+    "fvta_p2p_allreduce_adadelta": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
+                                                   c_float_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                   c_float_p, c_float_p, c_float_p, c_float_p, c_i32_p,
+                                                   ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
 }
 
 _lib = None

@@ -8,21 +8,9 @@
 // accumulators by rho).  `touch_index[i]` >= 0 names the entry of `touch` that says whether the
 // row holding element i was looked up this step (> 0); -1 = ordinary dense variable.
 #include "common.cuh"
+#include "adadelta.cuh"
 
 namespace fvta {
-
-__device__ __forceinline__ void adadelta_one(float& v, float g, float& a, float& au, float mask, float lr,
-                                             float rho, float eps, float gs) {
-  g *= gs;
-  const float na = rho * a + (1.f - rho) * g * g;
-  const float upd = sqrtf(au + eps) * rsqrtf(na + eps) * g;
-  const float nau = rho * au + (1.f - rho) * upd * upd;
-  if (mask != 0.f) {
-    a = na;
-    v = v - lr * upd;
-    au = nau;
-  }
-}
 
 __global__ void adadelta_kernel(int64_t n, float* __restrict__ var, const float* __restrict__ grad,
                                 float* __restrict__ accum, float* __restrict__ accum_update,

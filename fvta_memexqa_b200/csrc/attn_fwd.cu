@@ -19,6 +19,7 @@
 //   s_k     = max_{t,j} a;  beta = softmax_k s;  g1_all = sum_k beta_k r_k
 #include "common.cuh"
 #include "attn_tile.cuh"
+#include "attn_tc_images.cuh"
 
 namespace fvta {
 
@@ -26,8 +27,9 @@ namespace fvta {
 // prep: coefficient vectors shared by all samples
 // coef[0] = u (zeros without time warp), coef[1] = w_lin, coef[2] = w_quad (ones for cosine)
 // ---------------------------------------------------------------------------------------
-__global__ void attn_prep_coef(FvtaAttnDesc d, FvtaAttnParams p, float* __restrict__ coef, int Dp) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__device__ __forceinline__ void prep_coef_block(const FvtaAttnDesc& d, const FvtaAttnParams& p, float* __restrict__ coef,
+                                                int Dp, int block) {
+  int warp = (block * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= Dp) return;
   int dd = warp;
@@ -54,16 +56,14 @@ __global__ void attn_prep_coef(FvtaAttnDesc d, FvtaAttnParams p, float* __restri
 // ---------------------------------------------------------------------------------------
 // prep: per-sample question operand (transposed, zero padded), column term, gate constant
 // ---------------------------------------------------------------------------------------
-__global__ void attn_prep_q(FvtaAttnDesc d, FvtaAttnParams p, const float* __restrict__ hq,
-                            const float* __restrict__ lq, float* __restrict__ qeffT,
-                            float* __restrict__ col, float* __restrict__ zconst, int Dp, int JQP) {
-  extern __shared__ float sm[];
-  float* scale = sm;  // [JQP] cosine scale per question word
-  // grid (N, kPrepSplit): block (n, y) owns question words j = y, y + kPrepSplit, ...
-  const int n = blockIdx.x;
+__device__ __forceinline__ void prep_q_block(const FvtaAttnDesc& d, const FvtaAttnParams& p, const float* __restrict__ hq,
+                                             const float* __restrict__ lq, float* __restrict__ qeffT,
+                                             float* __restrict__ col, float* __restrict__ zconst, int Dp, int JQP,
+                                             int n, float* scale /* smem [JQP]: cosine scale per question word */,
+                                             float* qeff_s /* smem [Dp][JQP] or null */, bool write_global) {
   const int D = d.D, JQ = d.JQ;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  const int jy = blockIdx.y, jstep = gridDim.y;
+  const int jy = 0, jstep = 1;
   const float* q = hq + (size_t)n * JQ * D;
   const float* wq_lin = nullptr;
   const float* wq_quad = nullptr;
@@ -85,10 +85,10 @@ __global__ void attn_prep_q(FvtaAttnDesc d, FvtaAttnParams p, const float* __res
     if (lane == 0) {
       scale[j] = rsqrtf(fmaxf(qq, 1e-12f));  // tf.nn.l2_normalize epsilon
       float bias = (d.simi == 4) ? 0.f : p.att_b[0];
-      col[(size_t)n * JQP + j] = (j < JQ && d.simi != 4) ? c + bias : 0.f;
+      if (write_global) col[(size_t)n * JQP + j] = (j < JQ && d.simi != 4) ? c + bias : 0.f;
     }
   }
-  if (warp == 0 && jy == 0) {
+  if (warp == 0 && jy == 0 && write_global) {
     float acc = 0.f;
     if (d.use_time_warp)
       for (int e = lane; e < D; e += 32) acc += (p.WH_b[e] + lq[(size_t)n * D + e]) * p.WC_W[e];
@@ -108,7 +108,8 @@ __global__ void attn_prep_q(FvtaAttnDesc d, FvtaAttnParams p, const float* __res
       else if (d.simi == 3) v = qv * (p.att_W[3 * D + dd] - 2.f * p.att_W[2 * D + dd]);
       else v = qv * scale[j];
     }
-    out[(size_t)dd * JQP + j] = v;
+    if (write_global) out[(size_t)dd * JQP + j] = v;
+    if (qeff_s != nullptr) qeff_s[dd * JQP + j] = v;
   }
 }
 
@@ -352,26 +353,48 @@ static int launch_tile_fwd(const FvtaAttnDesc& d, const AttnLayout& L, const flo
   return check_launch("attn_tile_fwd");
 }
 
-// tensor-core B images + per-sample CTA counters (attn_fwd_tc.cu)
-int attn_tc_prep_images_launch(const FvtaAttnDesc& d, const AttnLayout& L, float* ws, cudaStream_t st);
 bool attn_tc_covers(const FvtaAttnDesc& d);
 
-// Operand folding: coefficient vectors, per-sample question operand / column term / gate constant,
-// and (tc_images) what only the tensor-core kernel reads.
+// Operand folding in ONE launch (the three small kernels it replaces cost 17 us of launch latency
+// next to a 100 us tile kernel): blocks [0, N) fold sample n's question operand, column term and gate
+// constant and -- for the tensor-core kernel -- build its B images and reset its CTA counter; the
+// remaining blocks fold the coefficient vectors shared by all samples.
+constexpr int kPrepSplit = 4;   // blocks per sample: each folds the question operand (cheap) and builds a quarter of the images
+
+__global__ void __launch_bounds__(256) attn_prep_all(FvtaAttnDesc d, FvtaAttnParams p, const float* __restrict__ hq,
+                                                      const float* __restrict__ lq, float* __restrict__ coef,
+                                                      float* __restrict__ qeffT, float* __restrict__ col,
+                                                      float* __restrict__ zconst, uint8_t* __restrict__ qB32,
+                                                      uint8_t* __restrict__ qB16, int* __restrict__ counters, int Dp,
+                                                      int JQP, int tc_images) {
+  extern __shared__ float prep_sm[];
+  float* scale = prep_sm;          // [64]
+  float* qeff_s = prep_sm + 64;    // [Dp][JQP] (tensor-core path only)
+  const int nsb = tc_images ? d.N * kPrepSplit : d.N;
+  if ((int)blockIdx.x >= nsb) {
+    prep_coef_block(d, p, coef, Dp, blockIdx.x - nsb);
+    return;
+  }
+  const int n = tc_images ? blockIdx.x / kPrepSplit : blockIdx.x;
+  const int part = tc_images ? blockIdx.x % kPrepSplit : 0;
+  prep_q_block(d, p, hq, lq, qeffT, col, zconst, Dp, JQP, n, scale, tc_images ? qeff_s : nullptr, part == 0);
+  if (!tc_images) return;
+  __syncthreads();
+  const int C32 = (d.D + 31) / 32, C16 = (d.D + 63) / 64;
+  build_tc_images_block(d, qeff_s, qB32 + (size_t)n * C32 * 8192, qB16 + (size_t)n * C16 * 4096, Dp, JQP, part, kPrepSplit);
+  if (threadIdx.x == 0 && part == 0) counters[n] = 0;
+}
+
 int attn_prep_launch(const FvtaAttnDesc& d, const AttnLayout& L, const FvtaAttnParams& p, const float* hq,
                      const float* lq, float* ws, cudaStream_t st, bool tc_images) {
-  {
-    int threads = 256;
-    int blocks = (L.Dp * 32 + threads - 1) / threads;
-    attn_prep_coef<<<blocks, threads, 0, st>>>(d, p, ws + L.coef, L.Dp);
-    int rc = check_launch("attn_prep_coef");
-    if (rc) return rc;
-  }
-  attn_prep_q<<<dim3(d.N, L.JQP < 8 ? L.JQP : 8), 128, L.JQP * sizeof(float), st>>>(d, p, hq, lq, ws + L.qeffT, ws + L.col,
-                                                         ws + L.zconst, L.Dp, L.JQP);
-  int rc = check_launch("attn_prep_q");
-  if (rc || !tc_images) return rc;
-  return attn_tc_prep_images_launch(d, L, ws, st);
+  const int coef_blocks = (L.Dp * 32 + 255) / 256;
+  const int sample_blocks = tc_images ? d.N * kPrepSplit : d.N;
+  const size_t smem = (64 + (tc_images ? (size_t)L.Dp * L.JQP : 0)) * sizeof(float);
+  attn_prep_all<<<sample_blocks + coef_blocks, 256, smem, st>>>(d, p, hq, lq, ws + L.coef, ws + L.qeffT, ws + L.col, ws + L.zconst,
+                                                   reinterpret_cast<uint8_t*>(ws + L.qB32),
+                                                   reinterpret_cast<uint8_t*>(ws + L.qB16),
+                                                   reinterpret_cast<int*>(ws + L.counter), L.Dp, L.JQP, tc_images ? 1 : 0);
+  return check_launch("attn_prep_all");
 }
 
 int attn_fwd_tc_launch(const FvtaAttnDesc& d, const AttnLayout& L, const float* hall, const uint8_t* hall_mask,

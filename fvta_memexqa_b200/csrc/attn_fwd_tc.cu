@@ -68,11 +68,12 @@ constexpr int kWarpTma = 0, kWarpMma = 1, kWarpWsum0 = 4, kWarpSoft0 = 12, kWarp
 #else
 constexpr int kWarpTma = 0, kWarpMma = 1, kWarpWsum0 = 4, kWarpSplit0 = 12, kWarpSoft0 = 20;
 #endif
-constexpr int kRegSoftmax = 104, kRegWsum = 56, kRegIssue = 40;   // split keeps the launch value (72)
+constexpr int kRegSoftmax = 112, kRegWsum = 48, kRegIssue = 40;   // split keeps the launch value (72)
 constexpr int kTcJQP = 32;        // question positions per tile (N of the MMAs: 64 and 32)
 constexpr int kTcTmemCols = 512;
 constexpr int kTcMaxStages = 6;
 constexpr float kMaskedWeight = 7.888609052210118e-31f;  // 2^-100
+constexpr float kTanhScale = 2.885390081777927f;         // 2 * log2(e)
 constexpr int kTcStageExtra = 512 + 3 * 1024;   // per ring stage: wg [128] + row statistics [3][2][128]
 #ifndef FVTA_TC_MIN_STAGES
 #define FVTA_TC_MIN_STAGES 4
@@ -262,46 +263,6 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 // what kind::tf32 keeps of an fp32 operand (tools/umma_probe.cu: the tensor core truncates)
 __device__ __forceinline__ float tf32_part(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// ---- B operands, pre-swizzled, one image per sample (built by attn_prep_all, attn_fwd.cu) --------
-//   qB32: C32 chunks x 64 rows x 128 B: rows 0-31 tf32(qeff[j]), rows 32-63 qeff[j] - tf32(qeff[j])
-//   qB16: C16 chunks x 32 rows x 128 B: fp16(qeff[j])
-// 16-byte unit u of row n sits at unit (u ^ (n & 7)) of its 128-byte line.
-__global__ void attn_prep_images(FvtaAttnDesc d, const float* __restrict__ qeffT, uint8_t* __restrict__ qB32,
-                                 uint8_t* __restrict__ qB16, int* __restrict__ counters, int Dp, int JQP) {
-  const int n = blockIdx.x;
-  const int C32 = (d.D + 31) / 32, C16 = (d.D + 63) / 64;
-  const float* qeffT_n = qeffT + (size_t)n * Dp * JQP;
-  uint8_t* qB32_n = qB32 + (size_t)n * C32 * 8192;
-  uint8_t* qB16_n = qB16 + (size_t)n * C16 * 4096;
-  if (threadIdx.x == 0) counters[n] = 0;
-  for (int i = threadIdx.x; i < C32 * 64 * 8; i += blockDim.x) {
-    const int u = i & 7, row = (i >> 3) & 63, c = i >> 9;
-    const int j = row & 31;
-    const bool lo = row >= 32;
-    float v[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int dd = c * 32 + u * 4 + e;
-      const float x = (dd < d.D && j < d.JQ) ? qeffT_n[(size_t)dd * JQP + j] : 0.f;
-      // round to nearest on the question side: the low 13 bits of `hi` are zero, so the tensor
-      // core's own truncation leaves it alone, and x - hi is exact in fp32
-      const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-      v[e] = lo ? x - hi : hi;
-    }
-    *reinterpret_cast<float4*>(qB32_n + c * 8192 + row * 128 + ((u ^ (row & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-  }
-  for (int i = threadIdx.x; i < C16 * 32 * 8; i += blockDim.x) {
-    const int u = i & 7, row = (i >> 3) & 31, c = i >> 8;
-    __half v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int dd = c * 64 + u * 8 + e;
-      v[e] = __float2half_rn((dd < d.D && row < d.JQ) ? qeffT_n[(size_t)dd * JQP + row] : 0.f);
-    }
-    *reinterpret_cast<uint4*>(qB16_n + c * 4096 + row * 128 + ((u ^ (row & 7)) << 4)) = *reinterpret_cast<uint4*>(v);
-  }
-}
-
 // ---- the fused kernel: grid (slabs, N) ----------------------------------------------------------
 template <int NREG> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NREG)); }
 template <int NREG> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NREG)); }
@@ -433,8 +394,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     for (int i = threadIdx.x; i < pl.C32 * 512; i += blockDim.x) d32[i] = s32[i];
     for (int i = threadIdx.x; i < pl.C16 * 256; i += blockDim.x) d16[i] = s16[i];
     for (int i = threadIdx.x; i < 3 * Dp; i += blockDim.x) coef_s[i] = coef[i];
+    // with tanh on, the logit is 1 - 2 / (1 + 2^(kTanhScale * S)): the scale is folded into the row
+    // coefficients and this column term instead of costing a multiply per logit
+    const float col_scale = (d.add_tanh && d.simi != 4) ? kTanhScale : 1.f;
     for (int j = threadIdx.x; j < kTcJQP; j += blockDim.x) {
-      col_s[j] = j < JQPg ? col[(size_t)n * JQPg + j] : 0.f;
+      col_s[j] = j < JQPg ? col_scale * col[(size_t)n * JQPg + j] : 0.f;
       const bool qv = !d.has_mask || (j < d.JQ && hq_mask[(size_t)n * d.JQ + j]);
       cap_s[j] = j >= d.JQ ? -INFINITY : (qv ? INFINITY : FVTA_VERY_NEGATIVE);
     }
@@ -578,12 +542,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       float c1, c0v;
       row_coefs(d, g, lin, quad, c1, c0v);
       const float p_c0 = cosine ? 0.f : c0v;
+      const float s_scale = tanh_on ? kTanhScale : 1.f;
       mbar_wait_relaxed(&acc_full[p], (i >> 1) & 1);
       TC_TRACE(3, i, 1);
       tc_fence_after();
       float a[32];
       float m = -INFINITY;
-      const float2 c1c1 = make_float2(c1, c1), c0c0 = make_float2(p_c0, p_c0);
+      const float2 c1c1 = make_float2(c1 * s_scale, c1 * s_scale), c0c0 = make_float2(p_c0 * s_scale, p_c0 * s_scale);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t x0[16], x1[16];
@@ -604,9 +569,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
           const float2 P = __fadd2_rn(make_float2(__uint_as_float(x0[j]), __uint_as_float(x0[j + 1])),
                                       make_float2(__uint_as_float(x1[j]), __uint_as_float(x1[j + 1])));
           float2 Sv = __fadd2_rn(__ffma2_rn(c1c1, P, c0c0), make_float2(colr0, colr1));
-          if (tanh_on) {  // tanh(x) = 1 - 2 / (1 + e^{2x}), packed
-            const float2 e2 = __fmul2_rn(Sv, make_float2(2.885390081777927f, 2.885390081777927f));  // 2*log2(e)
-            const float2 den = __fadd2_rn(make_float2(exp2f_approx(e2.x), exp2f_approx(e2.y)), make_float2(1.f, 1.f));
+          if (tanh_on) {  // tanh(x) = 1 - 2 / (1 + e^{2x}), packed; Sv already carries the factor 2 log2(e)
+            const float2 den = __fadd2_rn(make_float2(exp2f_approx(Sv.x), exp2f_approx(Sv.y)), make_float2(1.f, 1.f));
             Sv = __ffma2_rn(make_float2(rcp_approx(den.x), rcp_approx(den.y)), make_float2(-2.f, -2.f), make_float2(1.f, 1.f));
           }
           const float a0 = fminf(Sv.x, capr0), a1 = fminf(Sv.y, capr1);
@@ -837,13 +801,6 @@ static EncodeTiledFn get_encode_fn() {
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
   fn = reinterpret_cast<EncodeTiledFn>(p);
   return fn;
-}
-
-int attn_tc_prep_images_launch(const FvtaAttnDesc& d, const AttnLayout& L, float* ws, cudaStream_t st) {
-  attn_prep_images<<<d.N, 256, 0, st>>>(d, ws + L.qeffT, reinterpret_cast<uint8_t*>(ws + L.qB32),
-                                        reinterpret_cast<uint8_t*>(ws + L.qB16), reinterpret_cast<int*>(ws + L.counter),
-                                        L.Dp, L.JQP);
-  return check_launch("attn_prep_images");
 }
 
 // Runs the tile kernel (+ fused combine) over a workspace whose folded operands are in place.

@@ -20,6 +20,7 @@ class DataParallel:
         self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.device = device
+        self.p2p = None
         if self.world_size > 1 and not dist.is_initialized():
             if backend is None:
                 backend = "nccl" if torch.cuda.is_available() else "gloo"
@@ -29,6 +30,55 @@ class DataParallel:
                 dist.init_process_group(backend, device_id=self.device)
             else:
                 dist.init_process_group(backend)
+
+    # ------------------------------------------------------------------ fused all-reduce + Adadelta
+    def enable_p2p(self, ps):
+        """Peer-mapped staging buffers for `fvta_p2p_allreduce_adadelta` (csrc/p2p_adadelta.cu): the
+        gradient sum over the ranks and the optimizer update run as ONE kernel per rank over NVLink,
+        replacing ncclAllReduce + fvta_adadelta.  torch's symmetric memory supplies the allocation and
+        the exchange of the peer mappings (plumbing only); the data path is this repo's kernel.
+        Returns False (and leaves the NCCL path in place) when peer mappings are unavailable."""
+        self.p2p = None
+        if self.world_size <= 1 or not torch.cuda.is_available():
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            total = ps.grad_buf.numel()
+            stage = symm_mem.empty(2 * total, dtype=torch.float32, device=self.device)
+            flags = symm_mem.empty(64, dtype=torch.int32, device=self.device)
+            stage.zero_()
+            flags.zero_()
+            torch.cuda.synchronize()
+            hs = symm_mem.rendezvous(stage, dist.group.WORLD)
+            hf = symm_mem.rendezvous(flags, dist.group.WORLD)
+            state = torch.zeros(4, dtype=torch.int32, device=self.device)
+            self.p2p = dict(stage=stage, flags=flags, hs=hs, hf=hf, state=state,
+                            stage_ptrs=int(hs.buffer_ptrs_dev), flag_ptrs=int(hf.buffer_ptrs_dev),
+                            n=ps.flat.numel(), n_tail=ps.touch_len)
+            dist.barrier()
+            torch.cuda.synchronize()
+            return True
+        except Exception as e:      # no peer access / no symmetric-memory support on this system
+            if self.rank == 0:
+                print("dp: peer-memory all-reduce unavailable (%s: %s); using ncclAllReduce + fvta_adadelta"
+                      % (type(e).__name__, e), flush=True)
+            self.p2p = None
+            return False
+
+    def allreduce_adadelta(self, ps, lr, rho, eps):
+        """One launch: sum of ps.grad_buf over the ranks (rank order) / world -> Adadelta on ps.flat."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        p = self.p2p
+        vp = ctypes.c_void_p
+        rc = lib.fvta_p2p_allreduce_adadelta(
+            self.world_size, self.rank, p["n"], p["n_tail"], vp(ps.grad_buf.data_ptr()), vp(p["stage_ptrs"]),
+            vp(p["flag_ptrs"]), vp(p["state"].data_ptr()), vp(ps.flat.data_ptr()), vp(ps.accum.data_ptr()),
+            vp(ps.accum_update.data_ptr()), vp(ps.update_mask.data_ptr()),
+            vp(ps.touch_index.data_ptr()) if ps.touch_index is not None else None, lr, rho, eps,
+            vp(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "fvta_p2p_allreduce_adadelta")
 
     def shard(self, n_global):
         """Half-open range of global sample indices this rank owns."""

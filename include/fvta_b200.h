@@ -281,6 +281,25 @@ int fvta_adadelta(int64_t n, float* var, const float* grad, float* accum, float*
                   const float* update_mask, const int32_t* touch_index, const float* touch,
                   float lr, float rho, float eps, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Data parallelism (north_star d; the reference is single-device, model_v2.py:14): the sum over the
+ * W ranks of the flat gradient buffer FUSED with the Adadelta update of trainer.py:16-27, in one
+ * kernel per rank over NVLink peer memory (no NCCL call on the path).
+ *   grad_local      [n + n_tail]  this rank's gradient, then the sparse tables' "row looked up" flags
+ *   stage_ptrs_dev  device array [world] of peer-mapped staging buffers, each 2 * (n + n_tail) floats
+ *                   (the halves alternate by step); entry `rank` is the local one
+ *   flag_ptrs_dev   device array [world] of peer-mapped flag arrays (>= world uint32, zero-initialised)
+ *   state           local, 4 x uint32, zero-initialised once: step counter and block counters
+ * Every rank must call it once per step, in step order, with the same n / n_tail.  The sum runs in rank
+ * order on every rank (bitwise identical replicas); the gradient is scaled by 1/world (batch mean over
+ * the global batch, model_v2.py:1090).  touch_index: see fvta_adadelta (flags come from the summed tail).
+ * ---------------------------------------------------------------------------------------- */
+int fvta_p2p_allreduce_adadelta(int32_t world, int32_t rank, int64_t n, int64_t n_tail,
+                                const float* grad_local, float* const* stage_ptrs_dev,
+                                uint32_t* const* flag_ptrs_dev, uint32_t* state, float* var, float* accum,
+                                float* accum_update, const float* update_mask, const int32_t* touch_index,
+                                float lr, float rho, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

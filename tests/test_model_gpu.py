@@ -133,7 +133,12 @@ def test_sparse_adadelta_on_embedding_tables(cuda_device):
     for k in ("emb/var/char_emb", "emb/word/var/word_emb_mat"):
         got = model.params.view(k).detach().cpu().double()
         assert rel_err(got, params[k]) < 5 * TOL, k
-        told_apart |= rel_err(dense[k], params[k]) > 20 * TOL
+        # the accumulators are where sparse and dense differ first (a factor rho on every row that a
+        # step did not look up); the weights follow one step later
+        for which, buf in ((0, model.params.accum), (1, model.params.accum_update)):
+            acc = model.params.view(k, buf).detach().cpu().double()
+            assert rel_err(acc, state[k][which]) < 5 * TOL, (k, which)
+            told_apart |= rel_err(dstate[k][which], state[k][which]) > 1e-3
     assert told_apart, "batches A and B look up the same rows: the test cannot see sparse vs dense"
 
 
@@ -176,7 +181,7 @@ def test_main_train_then_test_roundtrip(cuda_device, tmp_path):
     assert len(answers) == 6 and all(0 <= v < 4 for v in answers.values())   # test split = synthetic // 4
 
 
-def _dp_worker(rank, world, port, q):
+def _dp_worker(rank, world, port, q, fused=False):
     import os
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
                       MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -195,17 +200,28 @@ def _dp_worker(rank, world, port, q):
     model = get_model(cfg)
     dp.broadcast_params(model.params.flat)
     trainer = Trainer(model, cfg, dp=dp)
-    loss, _, _ = trainer.step(None, ((), TensorBatch(feed, hi - lo)))
+    if fused:
+        assert dp.enable_p2p(model.params), "peer-memory all-reduce could not be set up"
+    for _ in range(3):          # three steps: both staging halves and the flag epochs are exercised
+        loss, _, _ = trainer.step(None, ((), TensorBatch(feed, hi - lo)))
+    torch.cuda.synchronize()
+    flat = model.params.flat.detach().clone()
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    torch.distributed.all_gather(gathered, flat)
     if rank == 0:
-        q.put({k: model.params.view(k).detach().cpu() for k in model.params.offsets})
+        q.put(({k: model.params.view(k).detach().cpu() for k in model.params.offsets},
+               [bool(torch.equal(g, flat)) for g in gathered]))
     dp.barrier()
     torch.distributed.destroy_process_group()
 
 
-def test_two_gpu_step_equals_one_gpu_step(cuda_device):
-    """NCCL data parallel (north_star d): two ranks, each half of a 4-sample batch, one all-reduce
-    of the flat gradient -> same post-Adadelta weights as one GPU on the whole batch (padded shapes
-    pinned).  Skipped on a single-GPU box."""
+@pytest.mark.parametrize("fused", [False, True], ids=["nccl", "p2p-fused"])
+def test_two_gpu_step_equals_one_gpu_step(cuda_device, fused):
+    """Data parallel (north_star d): two ranks, each half of a 4-sample batch, the flat gradient summed
+    over the ranks -- by ncclAllReduce + fvta_adadelta, or by the fused peer-memory kernel
+    fvta_p2p_allreduce_adadelta -- gives the same post-Adadelta weights as one GPU on the whole batch
+    (padded shapes pinned) over three steps.  The fused kernel sums in rank order on every rank: its
+    replicas must be bitwise identical.  Skipped on a single-GPU box."""
     import socket
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -216,17 +232,21 @@ def test_two_gpu_step_equals_one_gpu_step(cuda_device):
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q, fused)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get(timeout=240)
+    got, same = q.get(timeout=240)
+    if fused:
+        assert all(same), "replicas diverged bitwise under the fused all-reduce"
     for p in procs:
         p.join(timeout=60)
     gcfg = tiny_config()
     gcfg.batch_size = 4
     gfeed = make_feed(gcfg, seed=5, glove_vocab=10, num_photos_pool=16)
     model = get_model(gcfg)
-    Trainer(model, gcfg).step(None, ((), TensorBatch(gfeed, 4)))
+    one = Trainer(model, gcfg)
+    for _ in range(3):
+        one.step(None, ((), TensorBatch(gfeed, 4)))
     for k, v in got.items():
         ref = model.params.view(k).detach().cpu()
         assert rel_err(v, ref) < 1e-4 or (v - ref).abs().max() < 1e-6, k
