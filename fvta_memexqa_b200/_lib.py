@@ -28,13 +28,14 @@ class FvtaAttnGrads(ctypes.Structure):
 
 
 class FvtaLstmDesc(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("B", "J", "In", "d")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "J", "In", "d", "path")]
 
 
 class FvtaReaderDesc(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("B", "ntok", "In", "d", "Jmax")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "ntok", "In", "d", "Jmax", "path")]
 
 
+LSTM_AUTO, LSTM_FFMA, LSTM_TC = 0, 1, 2
 PATH_AUTO, PATH_SMALL, PATH_FFMA, PATH_TC = 0, 1, 2, 3
 PATH_NAMES = {1: "attn_small", 2: "attn_tile_fwd (FFMA)", 3: "attn_fwd_tc (tcgen05)"}
 
@@ -77,6 +78,10 @@ SYMBOLS = {
     "fvta_gemm": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_float_p, ctypes.c_int32,
                                  ctypes.c_int32, c_float_p, ctypes.c_int32, ctypes.c_int32, c_float_p,
                                  ctypes.c_int32, c_float_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
+    "fvta_gemm_gather": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_float_p, ctypes.c_int32,
+                                        ctypes.c_void_p, ctypes.c_int32, c_float_p, ctypes.c_int32, ctypes.c_int32,
+                                        c_float_p, ctypes.c_int32, c_float_p, ctypes.c_int32, ctypes.c_int32,
+                                        ctypes.c_void_p]),
     "fvta_charcnn_fwd": (ctypes.c_int, [ctypes.c_int32] * 5 + [c_i32_p, c_float_p, c_float_p, c_float_p,
                                                                  ctypes.c_int32, c_u8_p, ctypes.c_void_p]),
     "fvta_charcnn_bwd": (ctypes.c_int, [ctypes.c_int32] * 5 + [c_i32_p, c_float_p, ctypes.c_int32, c_u8_p, c_float_p,

@@ -13,13 +13,12 @@
 // Backward = the mirrored recurrent kernel (BPTT) producing d gates, then GEMMs for d_x and
 // the weight gradients.
 #include "common.cuh"
+#include "bilstm.cuh"
 #include <cstdlib>
 
 namespace fvta {
 
 constexpr int kSG = 8;          // sequences per CTA
-constexpr int kResW = 6;        // reserve floats per (dir, b, t) in units of d: i, j, f, o, c, h_prev
-
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 struct LstmSmemPlan {
@@ -36,24 +35,6 @@ __host__ __device__ inline LstmSmemPlan lstm_smem_plan(int d) {
   p.bytes = (p.w_in_smem ? w : 0) + rest;
   return p;
 }
-
-// Addressing of one sequence b: its tokens are rows tok0 .. tok0+len-1 of the packed arrays
-// (projected inputs, reserve, d gates); its outputs go to rows out0 .. of the output arena
-// (out0 < 0: outputs are not stored).  Dense [B,J] layout = (b*J, b*J).
-struct SeqAddr {
-  const int32_t* tok_off;   // [B] or null (dense)
-  const int64_t* out_row;   // [B] or null (dense)
-  int ntok;                 // rows of the packed arrays
-  __device__ __forceinline__ int tok0(int b, int J) const { return tok_off ? tok_off[b] : b * J; }
-  __device__ __forceinline__ long long out0(int b, int J) const { return out_row ? out_row[b] : (long long)b * J; }
-};
-
-// MUFU-based activations (ex2.approx / rcp.approx): |error| < 1e-6, an order of magnitude cheaper
-// than expf / tanhf, which dominated the cell update
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx_(1.f + ex2_approx(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 1.f - 2.f * rcp_approx_(1.f + ex2_approx(2.885390081777927f * x)); }
 
 // Forward recurrence for d <= 64.  What bounds a step is the number of bytes shared memory returns
 // to registers (a broadcast float4 of h costs a full 512-byte warp write-back), so a gate thread
@@ -558,6 +539,11 @@ static int lstm_validate(const FvtaLstmDesc* L) {
 
 // Forward over `ntok` packed token rows (dense layout: ntok = B*J).
 //   workspace: xp_fw [ntok*4d], xp_bw [ntok*4d];   reserve: [2][ntok][6d]
+namespace fvta {
+int lstm_fwd_tc_try(const FvtaLstmDesc& L, const SeqAddr& A, const int32_t* lens, const float* xp_fw, const float* xp_bw,
+                    const float* wh_fw, const float* wh_bw, float* out, float* last, float* reserve, cudaStream_t st);
+}
+
 static int lstm_fwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x, const int32_t* lens,
                          const float* kernel_fw, const float* bias_fw, const float* kernel_bw,
                          const float* bias_bw, float* out, float* last, float* reserve, float* workspace,
@@ -584,7 +570,14 @@ static int lstm_fwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x
   if (e != cudaSuccess) { set_last_error("bilstm_rec_fwd smem attr", e); return FVTA_E_LAUNCH; }
   int threads = round_up(G < 1024 ? G : 1024, 32);
   dim3 grid((L.B + kSG - 1) / kSG, 2);
-  if (L.d <= 64) {   // the reference's hidden sizes (50; 100 is the flag default): W_h columns in registers
+  if (L.path == FVTA_LSTM_TC) {   // d <= 64: the recurrent product on tcgen05 (bilstm_tc.cu)
+    const int rc_tc = lstm_fwd_tc_try(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G, kernel_bw + (size_t)L.In * G,
+                                      out, last, reserve, st);
+    return rc_tc == 1 ? FVTA_E_SHAPE : rc_tc;
+  }
+  // FVTA_LSTM_AUTO: the CUDA-core recurrence is the faster one at the reference sizes (a step is bound by
+  // the cell update and the hand-over latency, not by the 4d x d product: profiles/README.md)
+  if (L.d <= 64) {   // W_h columns in registers (50; 100 is the flag default): W_h columns in registers
     const int th = round_up(8 * L.d, 32);
     if (L.d <= 32)
       bilstm_rec_fwd_split<8><<<grid, th, 0, st>>>(L, A, lens, xp_fw, xp_bw, kernel_fw + (size_t)L.In * G,
@@ -748,7 +741,7 @@ extern "C" int fvta_reader_fwd(const FvtaReaderDesc* desc, const float* x_tok, c
       !workspace)
     return FVTA_E_BADARG;
   if (workspace_bytes < fvta_reader_workspace_bytes(desc)) return FVTA_E_WORKSPACE;
-  FvtaLstmDesc L{desc->B, desc->Jmax, desc->In, desc->d};
+  FvtaLstmDesc L{desc->B, desc->Jmax, desc->In, desc->d, desc->path};
   SeqAddr A{seq_tok_off, seq_out_row, desc->ntok};
   return lstm_fwd_impl(L, A, x_tok, seq_len, kernel, bias, kernel, bias, out_arena, last, reserve,
                        (float*)workspace, stream);
@@ -765,7 +758,7 @@ extern "C" int fvta_reader_bwd(const FvtaReaderDesc* desc, const float* x_tok, c
       !d_bias || !workspace)
     return FVTA_E_BADARG;
   if (workspace_bytes < fvta_reader_workspace_bytes(desc)) return FVTA_E_WORKSPACE;
-  FvtaLstmDesc L{desc->B, desc->Jmax, desc->In, desc->d};
+  FvtaLstmDesc L{desc->B, desc->Jmax, desc->In, desc->d, desc->path};
   SeqAddr A{seq_tok_off, seq_out_row, desc->ntok};
   return lstm_bwd_impl(L, A, x_tok, seq_len, kernel, kernel, reserve, d_out_arena, d_last, d_x_tok, d_kernel,
                        d_bias, d_kernel, d_bias, (float*)workspace, stream);

@@ -22,7 +22,7 @@ constexpr int kCnnWordsPerBlock = 8;
 // grid ceil(ntok / 8), block 8 x 32: lane = group of 4 output channels, threadIdx.y = word
 __global__ void charcnn_fwd_kernel(int ntok, int W, int VC, int cw, int height, const int32_t* __restrict__ ids,
                                    const float* __restrict__ table, const float* __restrict__ bias,
-                                   float* __restrict__ y, int ldy, uint8_t* __restrict__ argpos) {
+                                   float* __restrict__ y, int ldy, uint8_t* __restrict__ argpos, int vec) {
   __shared__ int id_s[kCnnWordsPerBlock][64];
   const int wl = threadIdx.y, lane = threadIdx.x;
   const int w = blockIdx.x * kCnnWordsPerBlock + wl;
@@ -34,6 +34,21 @@ __global__ void charcnn_fwd_kernel(int ntok, int W, int VC, int cw, int height, 
   __syncthreads();
   if (w >= ntok) return;
   const int npos = W - height + 1;
+  if (!vec) {   // any cw / row stride: one output channel per lane
+    for (int o = lane; o < cw; o += 32) {
+      const float b = bias[o];
+      float best = -INFINITY;
+      int bp = 0;
+      for (int p = 0; p < npos; ++p) {
+        float a = b;
+        for (int h = 0; h < height; ++h) a += table[((size_t)id_s[wl][p + h] * height + h) * cw + o];
+        if (a > best) { best = a; bp = p; }
+      }
+      y[(size_t)w * ldy + o] = fmaxf(best, 0.f);
+      argpos[(size_t)w * cw + o] = (unsigned char)bp;
+    }
+    return;
+  }
   const int cw4 = cw >> 2;
   for (int o4 = lane; o4 < cw4; o4 += 32) {
     const float4 b4 = *reinterpret_cast<const float4*>(bias + o4 * 4);
@@ -100,11 +115,15 @@ extern "C" int fvta_charcnn_fwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw,
   if (ntok < 0 || W <= 0 || VC <= 0 || cw <= 0 || height <= 0) return FVTA_E_BADARG;
   if (ntok == 0) return FVTA_OK;
   if (!ids || !table || !bias || !y || !argpos) return FVTA_E_BADARG;
-  if ((cw & 3) != 0 || cw > 128 || W > 64 || W < height || W - height + 1 > 255) return FVTA_E_SHAPE;
-  if (ldy < cw || (ldy & 3) != 0 || (reinterpret_cast<uintptr_t>(y) & 15) != 0) return FVTA_E_BADARG;
+  if (cw > 128 || W > 64 || W < height || W - height + 1 > 255) return FVTA_E_SHAPE;
+  if (ldy < cw) return FVTA_E_BADARG;
+  // float4 path when the channel count, the row stride and every base pointer allow it
+  const int vec = ((cw & 3) == 0 && (ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(table) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(argpos) & 3) == 0) ? 1 : 0;
   dim3 block(32, kCnnWordsPerBlock);
   charcnn_fwd_kernel<<<(ntok + kCnnWordsPerBlock - 1) / kCnnWordsPerBlock, block, 0, (cudaStream_t)stream>>>(
-      ntok, W, VC, cw, height, ids, table, bias, y, ldy, argpos);
+      ntok, W, VC, cw, height, ids, table, bias, y, ldy, argpos, vec);
   return check_launch("charcnn_fwd_kernel");
 }
 
@@ -115,7 +134,7 @@ extern "C" int fvta_charcnn_bwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw,
   if (ntok < 0 || W <= 0 || VC <= 0 || cw <= 0 || height <= 0) return FVTA_E_BADARG;
   if (ntok == 0) return FVTA_OK;
   if (!ids || !y || !argpos || !dy || !d_table || !d_bias) return FVTA_E_BADARG;
-  if ((cw & 3) != 0 || cw > 128 || W > 64 || W < height) return FVTA_E_SHAPE;
+  if (cw > 128 || W > 64 || W < height) return FVTA_E_SHAPE;
   if (ldy < cw || lddy < cw) return FVTA_E_BADARG;
   dim3 block(32, kCnnWordsPerBlock);
   charcnn_bwd_kernel<<<(ntok + kCnnWordsPerBlock - 1) / kCnnWordsPerBlock, block, 0, (cudaStream_t)stream>>>(

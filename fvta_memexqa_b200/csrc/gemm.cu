@@ -156,22 +156,28 @@ __device__ __forceinline__ void cp_async4(float* dst, const float* src, int src_
 
 // One operand tile -> shared memory.  `rows` x `kk`: the operand is X[r][k] (r = m or n) stored
 // either with k contiguous (KMAJ: X + r * ld + k) or with r contiguous (X + k * ld + r).
+// `rowmap` (gather variant, null otherwise): the index that multiplies `ld` -- the storage row of X --
+// is looked up, rowmap[row], so the operand is a set of rows of a larger table read in place (the image
+// transform multiplies the batch's photo features image_emb_mat[pis], model_v2.py:634-645, without
+// materialising the gathered [tokens, 2537] matrix).
 template <bool KMAJ, int VEC>
 __device__ __forceinline__ void stage_operand(float* dst, const float* __restrict__ X, int ld, int r0, int R, int k0,
-                                              int kend, int tid) {
+                                              int kend, int tid, const int64_t* __restrict__ rowmap = nullptr) {
   if (VEC == 4) {
     if (KMAJ) {   // 64 rows x 4 chunks of 4 k
       const int r = tid >> 2, kq = (tid & 3) * 4;
       const int gr = r0 + r, gk = k0 + kq;
       int nb = (gr < R) ? (kend - gk) * 4 : 0;
       nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-      cp_async16(dst + r * kLdK + kq, nb ? X + (size_t)gr * ld + gk : X, nb);
+      const size_t row = (rowmap != nullptr && nb) ? (size_t)rowmap[gr] : (size_t)gr;
+      cp_async16(dst + r * kLdK + kq, nb ? X + row * ld + gk : X, nb);
     } else {      // 16 k x 16 chunks of 4 rows
       const int k = tid >> 4, rq = (tid & 15) * 4;
       const int gk = k0 + k, gr = r0 + rq;
       int nb = (gk < kend) ? (R - gr) * 4 : 0;
       nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-      cp_async16(dst + k * kLdM + rq, nb ? X + (size_t)gk * ld + gr : X, nb);
+      const size_t row = (rowmap != nullptr && nb) ? (size_t)rowmap[gk] : (size_t)gk;
+      cp_async16(dst + k * kLdM + rq, nb ? X + row * ld + gr : X, nb);
     }
   } else {
 #pragma unroll
@@ -180,11 +186,13 @@ __device__ __forceinline__ void stage_operand(float* dst, const float* __restric
       if (KMAJ) {
         const int k = i & (BK - 1), r = i >> 4;
         const bool ok = (r0 + r < R) && (k0 + k < kend);
-        cp_async4(dst + r * kLdK + k, ok ? X + (size_t)(r0 + r) * ld + k0 + k : X, ok ? 4 : 0);
+        const size_t row = (rowmap != nullptr && ok) ? (size_t)rowmap[r0 + r] : (size_t)(r0 + r);
+        cp_async4(dst + r * kLdK + k, ok ? X + row * ld + k0 + k : X, ok ? 4 : 0);
       } else {
         const int r = i & (BM - 1), k = i >> 6;
         const bool ok = (r0 + r < R) && (k0 + k < kend);
-        cp_async4(dst + k * kLdM + r, ok ? X + (size_t)(k0 + k) * ld + r0 + r : X, ok ? 4 : 0);
+        const size_t row = (rowmap != nullptr && ok) ? (size_t)rowmap[k0 + k] : (size_t)(k0 + k);
+        cp_async4(dst + k * kLdM + r, ok ? X + row * ld + r0 + r : X, ok ? 4 : 0);
       }
     }
   }
@@ -196,7 +204,7 @@ __global__ void __launch_bounds__(256) gemm_mma_kernel(int M, int N, int K, cons
                                                        const float* __restrict__ B, int ldb,
                                                        const float* __restrict__ bias, int act,
                                                        float* __restrict__ C, int ldc, int accumulate,
-                                                       int k_per_split) {
+                                                       int k_per_split, const int64_t* __restrict__ a_rows) {
   static_assert(BM == 64 && BN == 64 && BK == 16, "warp layout below is written for 64x64x16");
   __shared__ __align__(16) float As[kStages][kOpFloats];
   __shared__ __align__(16) float Bs[kStages][kOpFloats];
@@ -220,7 +228,7 @@ __global__ void __launch_bounds__(256) gemm_mma_kernel(int M, int N, int K, cons
   auto issue = [&](int tile) {
     if (tile < ntile) {
       const int k0 = kbeg + tile * BK, st = tile % kStages;
-      stage_operand<!TA, VA>(As[st], A, lda, m0, M, k0, kend, tid);   // A[m][k]: k contiguous unless transposed
+      stage_operand<!TA, VA>(As[st], A, lda, m0, M, k0, kend, tid, a_rows);   // A[m][k]: k contiguous unless transposed
       stage_operand<TB, VB>(Bs[st], B, ldb, n0, N, k0, kend, tid);    // B[k][n]: k contiguous only if transposed
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -305,9 +313,9 @@ __global__ void gemm_epilogue(int M, int N, float* __restrict__ C, int ldc, cons
 
 }  // namespace fvta
 
-extern "C" int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t trans_a,
-                         const float* B, int32_t ldb, int32_t trans_b, const float* bias, int32_t act,
-                         float* C, int32_t ldc, int32_t accumulate, void* stream) {
+static int gemm_impl(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t trans_a,
+                     const float* B, int32_t ldb, int32_t trans_b, const float* bias, int32_t act,
+                     float* C, int32_t ldc, int32_t accumulate, void* stream, const int64_t* a_rows) {
   using namespace fvta;
   if (M < 0 || N < 0 || K < 0 || !C) return FVTA_E_BADARG;
   if (M == 0 || N == 0) return FVTA_OK;
@@ -343,7 +351,7 @@ extern "C" int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_
   const int kact = split_epilogue ? 0 : act;
   static const bool use_ffma = [] { const char* e = getenv("FVTA_GEMM_FFMA"); return e && e[0] == '1'; }();
 #define FVTA_GEMM_ARGS M, N, K, A, lda, B, ldb, kbias, kact, C, ldc, accumulate, kps
-  if (use_ffma) {
+  if (use_ffma && a_rows == nullptr) {
     if (!trans_a && !trans_b) gemm_kernel<false, false><<<grid, 256, 0, st>>>(FVTA_GEMM_ARGS);
     else if (!trans_a && trans_b) gemm_kernel<false, true><<<grid, 256, 0, st>>>(FVTA_GEMM_ARGS);
     else if (trans_a && !trans_b) gemm_kernel<true, false><<<grid, 256, 0, st>>>(FVTA_GEMM_ARGS);
@@ -355,10 +363,10 @@ extern "C" int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_
     const bool vb = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 4 == 0);
 #define FVTA_GEMM_V(TA_, TB_)                                                                          \
     do {                                                                                               \
-      if (va && vb) gemm_mma_kernel<TA_, TB_, 4, 4><<<grid, 256, 0, st>>>(FVTA_GEMM_ARGS);             \
-      else if (va) gemm_mma_kernel<TA_, TB_, 4, 1><<<grid, 256, 0, st>>>(FVTA_GEMM_ARGS);              \
-      else if (vb) gemm_mma_kernel<TA_, TB_, 1, 4><<<grid, 256, 0, st>>>(FVTA_GEMM_ARGS);              \
-      else gemm_mma_kernel<TA_, TB_, 1, 1><<<grid, 256, 0, st>>>(FVTA_GEMM_ARGS);                      \
+      if (va && vb) gemm_mma_kernel<TA_, TB_, 4, 4><<<grid, 256, 0, st>>>(FVTA_GEMM_ARGS, a_rows);     \
+      else if (va) gemm_mma_kernel<TA_, TB_, 4, 1><<<grid, 256, 0, st>>>(FVTA_GEMM_ARGS, a_rows);      \
+      else if (vb) gemm_mma_kernel<TA_, TB_, 1, 4><<<grid, 256, 0, st>>>(FVTA_GEMM_ARGS, a_rows);      \
+      else gemm_mma_kernel<TA_, TB_, 1, 1><<<grid, 256, 0, st>>>(FVTA_GEMM_ARGS, a_rows);              \
     } while (0)
     if (!trans_a && !trans_b) FVTA_GEMM_V(false, false);
     else if (!trans_a && trans_b) FVTA_GEMM_V(false, true);
@@ -371,4 +379,18 @@ extern "C" int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_
   if (rc || !split_epilogue) return rc;
   gemm_epilogue<<<(M * N + 255) / 256, 256, 0, st>>>(M, N, C, ldc, bias, act);
   return check_launch("gemm_epilogue");
+}
+
+extern "C" int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t trans_a,
+                         const float* B, int32_t ldb, int32_t trans_b, const float* bias, int32_t act,
+                         float* C, int32_t ldc, int32_t accumulate, void* stream) {
+  return gemm_impl(M, N, K, A, lda, trans_a, B, ldb, trans_b, bias, act, C, ldc, accumulate, stream, nullptr);
+}
+
+extern "C" int fvta_gemm_gather(int32_t M, int32_t N, int32_t K, const float* A_table, int32_t lda,
+                                const int64_t* a_rows, int32_t trans_a, const float* B, int32_t ldb,
+                                int32_t trans_b, const float* bias, int32_t act, float* C, int32_t ldc,
+                                int32_t accumulate, void* stream) {
+  if (!a_rows) return FVTA_E_BADARG;
+  return gemm_impl(M, N, K, A_table, lda, trans_a, B, ldb, trans_b, bias, act, C, ldc, accumulate, stream, a_rows);
 }

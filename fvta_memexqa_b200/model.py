@@ -282,7 +282,7 @@ class Model:
             filt = v["emb/conv/conv1d/filter"]                          # [1,5,cdim,cwdim]
             height, cdim, cw = filt.shape[1], filt.shape[2], filt.shape[3]
             dropped = is_train and cfg.keep_prob < 1.0                  # conv1d input dropout (:60-61)
-            table_ok = (not dropped and cw % 4 == 0 and cw <= 128 and ids_c.shape[1] <= 64
+            table_ok = (not dropped and cw <= 128 and ids_c.shape[1] <= 64
                         and ids_c.shape[1] - height + 1 <= 255)
         if not cfg.use_char or table_ok:
             # a window's conv output depends only on its `height` char ids: tabulate
@@ -323,12 +323,15 @@ class Model:
             if (is_train and cfg.keep_prob < 1.0) else (lambda t: t)
         # embeddings of the valid tokens only (padding never reaches a consumer: dynamic_rnn ignores it)
         x_text = self._embed_tokens(f["text_tok_ids"], f.get("text_tok_cids"), f["existing_emb_mat"], is_train)
-        x_img = ops.embed(f["image_emb_mat"], f["img_tok_pidx"])
         if cfg.use_image_trans:                                        # model_v2.py:634-645
-            x_img = ops.linear(x_img, v["emb/image/image_transform/image_trans_linear/W"],
-                               v["emb/image/image_transform/image_trans_linear/b"], cfg.add_tanh,
-                               *self._sink("emb/image/image_transform/image_trans_linear/W",
-                                           "emb/image/image_transform/image_trans_linear/b"))
+            # lookup + linear (+tanh) as one product: the A rows are read in place from the fed table
+            x_img = ops.gather_linear(f["image_emb_mat"], f["img_tok_pidx"],
+                                      v["emb/image/image_transform/image_trans_linear/W"],
+                                      v["emb/image/image_transform/image_trans_linear/b"], cfg.add_tanh,
+                                      *self._sink("emb/image/image_transform/image_trans_linear/W",
+                                                  "emb/image/image_transform/image_trans_linear/b"))
+        else:
+            x_img = ops.embed(f["image_emb_mat"], f["img_tok_pidx"])
         # the eight reader call sites (model_v2.py:694-823) + the context tensor (:862-914)
         arena, last_t, last_i = ops.ReaderFn.apply(
             drop(x_text), drop(x_img), f["text_seq_off"], f["text_seq_len"], f["text_seq_out"],

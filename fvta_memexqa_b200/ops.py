@@ -238,18 +238,76 @@ def linear(x, W, b, add_tanh=False, gW=None, gb=None):
     return LinearFn.apply(x, W, b, add_tanh, gW, gb)
 
 
+def gemm_gather(table, rows, B, bias=None, act=None, trans_a=False, out=None, accumulate=False):
+    """fvta_gemm_gather: act(op(table[rows]) @ B + bias) without materialising table[rows]."""
+    lib = _lib.load()
+    f32 = torch.float32
+    table, B, bias = _req(table, f32, "table"), _req(B, f32, "B"), _req(bias, f32, "bias")
+    rows = _req(rows, torch.int64, "rows")
+    n_rows, width = rows.numel(), table.shape[1]
+    M, K = (width, n_rows) if trans_a else (n_rows, width)
+    if B.shape[0] != K:
+        raise _lib.FvtaError("gemm_gather: inner dimensions differ (%d vs %d)" % (K, B.shape[0]))
+    N = B.shape[1]
+    if out is None:
+        out = torch.empty(M, N, dtype=f32, device=table.device)
+    rc = lib.fvta_gemm_gather(M, N, K, _ptr(table), width, _ptr(rows), int(trans_a), _ptr(B), N, 0, _ptr(bias),
+                              ACT[act], _ptr(out), out.shape[1], int(accumulate), _stream())
+    check(rc, "fvta_gemm_gather")
+    return out
+
+
+class GatherLinearFn(torch.autograd.Function):
+    """tf.nn.embedding_lookup(image_emb_mat, pis) -> `linear` (+tanh) of model_v2.py:634-645 as ONE
+    product whose A rows are read in place from the fed photo-feature table (fvta_gemm_gather): the
+    gathered [tokens, image_feat_dim] matrix never exists, forward or backward.  The table is fed, not
+    trained: no gradient flows to it."""
+
+    @staticmethod
+    def forward(ctx, table, rows, W, b, add_tanh, gW=None, gb=None):
+        y = gemm_gather(table, rows, W, b, "tanh" if add_tanh else None)
+        ctx.save_for_backward(table, rows, y)
+        ctx.add_tanh = add_tanh
+        ctx.wshape = W.shape
+        ctx.sinks = (gW, gb)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        table, rows, y = ctx.saved_tensors
+        N = ctx.wshape[1]
+        dy = _req(dy, torch.float32, "dy")
+        gW, gb = ctx.sinks
+        db = gb if gb is not None else torch.zeros(N, dtype=dy.dtype, device=dy.device)
+        dz = torch.empty_like(dy) if ctx.add_tanh else dy
+        rc = lib.fvta_bias_act_grad(dy.shape[0], N, _ptr(dy), N, _ptr(y) if ctx.add_tanh else None, N,
+                                    1 if ctx.add_tanh else 0, _ptr(dz) if ctx.add_tanh else None, N, _ptr(db),
+                                    _stream())
+        check(rc, "fvta_bias_act_grad")
+        if gW is not None:
+            gemm_gather(table, rows, dz, trans_a=True, out=gW, accumulate=True)
+            return None, None, None, None, None, None, None
+        dW = gemm_gather(table, rows, dz, trans_a=True)
+        return None, None, dW, db, None, None, None
+
+
+def gather_linear(table, rows, W, b, add_tanh=False, gW=None, gb=None):
+    return GatherLinearFn.apply(table, rows, W, b, add_tanh, gW, gb)
+
+
 # ---------------------------------------------------------------------------------------------
 # BiLSTM reader
 # ---------------------------------------------------------------------------------------------
-def _lstm_desc(x, kernel):
+def _lstm_desc(x, kernel, path=0):
     B, J, In = x.shape
     d = kernel.shape[1] // 4
     if kernel.shape[0] != In + d:
         raise _lib.FvtaError("bilstm: kernel rows %d != In + d = %d" % (kernel.shape[0], In + d))
-    return FvtaLstmDesc(B=B, J=J, In=In, d=d)
+    return FvtaLstmDesc(B=B, J=J, In=In, d=d, path=path)
 
 
-def bilstm_forward(x, lens, kernel_fw, bias_fw, kernel_bw=None, bias_bw=None):
+def bilstm_forward(x, lens, kernel_fw, bias_fw, kernel_bw=None, bias_bw=None, path=0):
     """fvta_bilstm_fwd.  x [B,J,In] fp32, lens [B] int32.  Passing no bw weights shares fw's
     (the reference hands the same cell object to both directions)."""
     lib = _lib.load()
@@ -261,7 +319,7 @@ def bilstm_forward(x, lens, kernel_fw, bias_fw, kernel_bw=None, bias_bw=None):
         kernel_bw, bias_bw = kernel_fw, bias_fw
     else:
         kernel_bw, bias_bw = _req(kernel_bw, f32, "kernel_bw"), _req(bias_bw, f32, "bias_bw")
-    desc = _lstm_desc(x, kernel_fw)
+    desc = _lstm_desc(x, kernel_fw, path)      # path: _lib.LSTM_AUTO / LSTM_FFMA / LSTM_TC (forward recurrence)
     B, J, d = desc.B, desc.J, desc.d
     dev = x.device
     out = torch.empty(B, J, 2 * d, dtype=f32, device=dev)
@@ -412,7 +470,7 @@ def _reader_call(lib, x_tok, off, lens, outrow, kernel, bias, arena, Jmax):
     from ._lib import FvtaReaderDesc
     f32 = torch.float32
     d = kernel.shape[1] // 4
-    desc = FvtaReaderDesc(B=lens.numel(), ntok=x_tok.shape[0], In=x_tok.shape[1], d=d, Jmax=Jmax)
+    desc = FvtaReaderDesc(B=lens.numel(), ntok=x_tok.shape[0], In=x_tok.shape[1], d=d, Jmax=Jmax, path=0)
     dev = x_tok.device
     last = torch.empty(lens.numel(), 2 * d, dtype=f32, device=dev)
     reserve = torch.empty(lib.fvta_reader_reserve_floats(ctypes.byref(desc)), dtype=f32, device=dev)

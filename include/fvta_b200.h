@@ -133,11 +133,16 @@ int fvta_attn_bwd(const FvtaAttnDesc* desc, const float* hall, const uint8_t* ha
  * model_v2.py:694-823 (gate order i,j,f,o; forget_bias 1; zero outputs past the length;
  * final state = state at the last valid step; backward direction reverses the valid prefix).
  * ---------------------------------------------------------------------------------------- */
+#define FVTA_LSTM_AUTO 0   /* the faster measured recurrence for the shape (today: CUDA cores at d = 50) */
+#define FVTA_LSTM_FFMA 1   /* packed-fp32 CUDA-core recurrence, W_h in registers */
+#define FVTA_LSTM_TC 2     /* forward recurrence on tcgen05 (d <= 64): W_h^T . h^T as split-fp16 UMMAs */
+
 typedef struct {
   int32_t B;     /* sequences */
   int32_t J;     /* padded length */
   int32_t In;    /* input width */
   int32_t d;     /* hidden size */
+  int32_t path;  /* FVTA_LSTM_AUTO / _FFMA / _TC: forward recurrence kernel (per call, not process state) */
 } FvtaLstmDesc;
 
 size_t fvta_bilstm_workspace_bytes(const FvtaLstmDesc* desc);
@@ -180,6 +185,7 @@ typedef struct {
   int32_t In;    /* input width */
   int32_t d;     /* hidden size */
   int32_t Jmax;  /* upper bound on any sequence length */
+  int32_t path;  /* FVTA_LSTM_AUTO / _FFMA / _TC */
 } FvtaReaderDesc;
 
 size_t fvta_reader_workspace_bytes(const FvtaReaderDesc* desc);
@@ -216,15 +222,24 @@ int fvta_gemm(int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int3
               const float* B, int32_t ldb, int32_t trans_b, const float* bias, int32_t act,
               float* C, int32_t ldc, int32_t accumulate, void* stream);
 
+/* The same product with the rows of op(A) GATHERED from a larger table: storage row r of A is
+ * A_table[a_rows[r]] (trans_a == 0: a_rows has M entries; trans_a != 0: K entries).  Replaces
+ * tf.nn.embedding_lookup(image_emb_mat, pis) followed by `linear` (model_v2.py:634-645) and its
+ * weight gradient without materialising the gathered [tokens, image_feat_dim] matrix. */
+int fvta_gemm_gather(int32_t M, int32_t N, int32_t K, const float* A_table, int32_t lda,
+                     const int64_t* a_rows, int32_t trans_a, const float* B, int32_t ldb, int32_t trans_b,
+                     const float* bias, int32_t act, float* C, int32_t ldc, int32_t accumulate, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Character CNN (replaces conv1d, model_v2.py:52-70, when its input dropout is off): the conv
  * output of a window depends only on its `height` character ids, so with
  * table[:,h,:] = char_emb @ filter[h] (caller, [VC,height,cw]) the layer is
  *   y[w,:] = relu( max_p ( bias + sum_h table[ids[w,p+h]][h][:] ) ),  p in [0, W-height].
  * argpos [ntok,cw] u8 records the arg-max position for the backward, which accumulates
- * d_table / d_bias (+=, caller zeroes them).  cw % 4 == 0, cw <= 128, W <= 64.
- * y and dy are addressed with row strides ldy / lddy (floats; ldy % 4 == 0, y 16-byte aligned) so
- * the features can live inside the [char | word] token matrix of model_v2.py:617.
+ * d_table / d_bias (+=, caller zeroes them).  cw <= 128, W <= 64 (float4 path when cw % 4 == 0, the row
+ * stride is a multiple of 4 and the bases are 16-byte aligned; one channel per lane otherwise).
+ * y and dy are addressed with row strides ldy / lddy (floats) so the features can live inside the
+ * [char | word] token matrix of model_v2.py:617.
  * ---------------------------------------------------------------------------------------- */
 int fvta_charcnn_fwd(int32_t ntok, int32_t W, int32_t VC, int32_t cw, int32_t height, const int32_t* ids,
                      const float* table, const float* bias, float* y, int32_t ldy, uint8_t* argpos,

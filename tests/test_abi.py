@@ -40,7 +40,7 @@ def test_descriptor_queries_without_gpu():
     bad = _lib.FvtaAttnDesc(N=32, K=6, T=256, D=100, JQ=25, simi=7, add_tanh=1, use_time_warp=0, warp_type=1,
                             window=3, time_warp_att=0, has_mask=1)
     assert lib.fvta_attn_workspace_bytes(ctypes.byref(bad)) == 0      # unknown simiMatrix
-    L = _lib.FvtaLstmDesc(B=128, J=8, In=200, d=50)
+    L = _lib.FvtaLstmDesc(B=128, J=8, In=200, d=50, path=0)
     assert lib.fvta_bilstm_reserve_floats(ctypes.byref(L)) == 2 * 128 * 8 * 6 * 50
 
 

@@ -82,6 +82,40 @@ def test_bilstm_parity(cuda_device, case):
     assert out.detach().cpu()[pad].abs().max().item() == 0.0 if pad.any() else True
 
 
+TC_LSTM_CASES = [(5, 4, 6, 3), (37, 8, 200, 50), (32, 25, 200, 50), (100, 10, 100, 50), (16, 8, 100, 64)]
+
+
+@pytest.mark.parametrize("case", TC_LSTM_CASES, ids=[str(c) for c in TC_LSTM_CASES])
+def test_bilstm_tcgen05_recurrence(cuda_device, case):
+    """The forward recurrence on tcgen05 (csrc/bilstm_tc.cu, FvtaLstmDesc.path = FVTA_LSTM_TC; north_star c):
+    outputs, final states and the reserve it leaves for the BPTT, against the fp64 oracle and against
+    the CUDA-core recurrence on the same inputs.  Fixed bound 1e-4 of the largest entry."""
+    from fvta_memexqa_b200 import _lib
+    B, J, In, d = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3 * B + J)
+    x = torch.randn(B, J, In, generator=g)
+    lens = torch.randint(0, J + 1, (B,), generator=g)
+    lens[0] = J
+    if B > 1:
+        lens[1] = 0
+    kernel = (torch.rand(In + d, 4 * d, generator=g) * 2 - 1) * (6.0 / (In + 5 * d)) ** 0.5
+    bias = torch.randn(4 * d, generator=g) * 0.1
+    (fw, bw), (fh, bh) = tf_ops.bidirectional_dynamic_rnn(x.double(), lens, kernel.double(), bias.double())
+    ref_out, ref_last = torch.cat([fw, bw], -1), torch.cat([fh, bh], -1)
+    with torch.no_grad():
+        args = (x.to(dev), lens.to(torch.int32).to(dev), kernel.to(dev), bias.to(dev))
+        out_tc, last_tc, res_tc, _ = ops.bilstm_forward(*args, path=_lib.LSTM_TC)
+        out_ff, last_ff, res_ff, _ = ops.bilstm_forward(*args, path=_lib.LSTM_FFMA)
+    e_out, e_last = rel_err(out_tc, ref_out), rel_err(last_tc, ref_last)
+    e_res = rel_err(res_tc, res_ff)
+    print("[lstm tcgen05] %s out %.2e last %.2e reserve-vs-ffma %.2e" % (case, e_out, e_last, e_res))
+    assert e_out < TOL and e_last < TOL and e_res < TOL
+    pad = (torch.arange(J).unsqueeze(0) >= lens.unsqueeze(1))
+    if pad.any():
+        assert out_tc.cpu()[pad].abs().max().item() == 0.0
+
+
 @pytest.mark.parametrize("shape", [(7, 6, 15, 6, 8), (300, 16, 80, 100, 100), (33, 9, 40, 12, 24)])
 def test_charcnn_table_parity(cuda_device, shape):
     """fvta_charcnn_fwd/bwd (per-character table + gather-add) vs the oracle's conv1d
