@@ -293,6 +293,73 @@ def attention_roofline(dev, iters=10, with_logits=False):
             "algorithmic_bytes": bytes_alg, "launch_ms": t * 1e3, "peak_source": how}
 
 
+def attention_roofline_bwd(dev, iters=10):
+    """Backward of the focal attention at the C3-max shape: fvta_attn_bwd as a whole (accumulator memset,
+    per-modality scalars, the tensor-core tile kernel attn_bwd_tc, question / parameter gradient kernels)
+    against SURVEY 8(d)'s B_bwd = 8 N K T D (hall read, d_hall written) + masks + small."""
+    import torch
+    from fvta_memexqa_b200 import ops, _lib
+    from fvta_memexqa_b200.config import fvta_config
+    from fvta_memexqa_b200.params import ParamStore
+    N, K, M, JI, JXP, D, JQ = 4, 6, 64, 64, 8, 100, 32
+    T = M * JI * JXP
+    cfg = fvta_config(batch_size=N)
+    p = ParamStore(cfg, seed=7, device=dev).as_dict()
+    g = torch.Generator(device=dev).manual_seed(1)
+    hall = torch.randn(N, K, T, D, device=dev, generator=g)
+    hmask = torch.ones(N, K, T, dtype=torch.bool, device=dev)
+    hq = torch.randn(N, JQ, D, device=dev, generator=g)
+    qmask = torch.ones(N, JQ, dtype=torch.bool, device=dev)
+    lq = torch.randn(N, D, device=dev, generator=g)
+    dg1 = torch.randn(N, D, device=dev, generator=g)
+    acfg = ops.AttnConfig(2, True, True, 5, 3.0, False)
+    names = ("attention/all/att_logits/W", "attention/all/att_logits/b", "time_warp/WH/W", "time_warp/WH/b",
+             "time_warp/WC/W", "time_warp/WC/b")
+    args = [p[k] for k in names]
+    fwd = ops.attn_forward(acfg, hall, hmask, hq, qmask, lq, *args)
+    d_hall, d_hq = torch.empty_like(hall), torch.empty_like(hq)
+    sinks = [torch.empty_like(a) for a in args]
+
+    def call():
+        ops.attn_backward(fwd, dg1, *args, sinks=sinks, d_hall_out=d_hall, d_hq_out=d_hq)
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        call()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    n0 = _lib.load().fvta_launch_count()
+    with torch.cuda.graph(gr):
+        call()
+    launches = int(_lib.load().fvta_launch_count() - n0)
+    t_end = time.time() + 0.3
+    while time.time() < t_end:
+        for _ in range(10):
+            gr.replay()
+        torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-4)
+    t = statistics.mean(ts)
+    bytes_alg = 8 * N * K * T * D + N * K * T + 8 * N * JQ * D + N * JQ + 8 * N * D
+    peak, how = measured_peaks()
+    return {"bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": bytes_alg / t / 1e9 / peak, "traffic": None,
+            "kernel": "fvta_attn_bwd, whole operator (%d launches; the tile kernel is attn_bwd_tc)" % launches,
+            "launch_ms": t * 1e3, "launch_ms_min": min(ts) * 1e3, "algorithmic_bytes": bytes_alg,
+            "workload": "C3-max: N=4 K=6 T=32768 D=100 JQ=32, mask density 1.0", "peak_source": how}
+
+
 def attention_roofline_parity(acfg, p, hall, hmask, hq, qmask, lq, t_slice=1024):
     """The kernel the roofline leg times vs the fp64 collapsed oracle (oracle/ is the checker here, never
     the thing measured): sample 0, first `t_slice` positions, run through the same entry point (the
@@ -453,6 +520,7 @@ def run_own(args):
     if world == 1:
         line["roofline"] = attention_roofline(dev)
         line["roofline_with_logits"] = attention_roofline(dev, with_logits=True)
+        line["roofline_bwd"] = attention_roofline_bwd(dev)
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)

@@ -464,6 +464,10 @@ static int launch_tile_bwd(const FvtaAttnDesc& d, const AttnLayout& L, const flo
 using namespace fvta;
 
 namespace fvta {
+bool attn_bwd_tc_covers(const FvtaAttnDesc& d);
+int attn_bwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hall, const uint8_t* hall_mask,
+                    const uint8_t* hq_mask, float* ws, const float* stats, const float* dg1, float* d_hall,
+                    cudaStream_t st);
 bool attn_small_ok(const FvtaAttnDesc& d);
 size_t attn_small_ws_floats(const FvtaAttnDesc& d);
 int attn_small_bwd(const FvtaAttnDesc& d, const float* hall, const uint8_t* hall_mask, const float* hq,
@@ -495,8 +499,11 @@ extern "C" int fvta_attn_bwd(const FvtaAttnDesc* desc, const float* hall, const 
     return attn_small_bwd(d, hall, hall_mask, hq, hq_mask, *params, d_g1_all, d_hall, d_hq, *grads, ws, st);
   // The folded operands are recomputed (cheap) so the workspace need not survive between
   // the forward and the backward call.
-  if (!d.ws_from_fwd) {
-    rc = attn_prep_launch(d, L, *params, hq, lq, ws, st, false);
+  // tensor-core tile kernel (attn_bwd_tc.cu) when the shape / flags are covered; it needs the question
+  // images next to the folded operands: ws_from_fwd == 2 says the forward left both
+  const bool use_tc = d.path != FVTA_PATH_FFMA && attn_bwd_tc_covers(d);
+  if (!d.ws_from_fwd || (use_tc && d.ws_from_fwd != 2)) {
+    rc = attn_prep_launch(d, L, *params, hq, lq, ws, st, use_tc);
     if (rc) return rc;
   }
   cudaError_t e = cudaMemsetAsync(ws + L.dqeffT, 0, (L.drow - L.dqeffT) * sizeof(float), st);
@@ -504,7 +511,11 @@ extern "C" int fvta_attn_bwd(const FvtaAttnDesc* desc, const float* hall, const 
   attn_bwd_prep<<<d.N, d.K * 32, 0, st>>>(d, stats, d_g1_all, ws + L.drow);
   rc = check_launch("attn_bwd_prep");
   if (rc) return rc;
-  switch (L.JQP) {
+  if (use_tc) {
+    rc = attn_bwd_tc_try(d, L, hall, hall_mask, hq_mask, ws, stats, d_g1_all, d_hall, st);
+    if (rc < 0) return rc;
+  }
+  if (!use_tc || rc == 1) switch (L.JQP) {
     case 4: rc = launch_tile_bwd<1>(d, L, hall, hall_mask, hq_mask, ws, stats, d_g1_all, d_hall, st); break;
     case 8: rc = launch_tile_bwd<2>(d, L, hall, hall_mask, hq_mask, ws, stats, d_g1_all, d_hall, st); break;
     case 16: rc = launch_tile_bwd<4>(d, L, hall, hall_mask, hq_mask, ws, stats, d_g1_all, d_hall, st); break;

@@ -35,8 +35,8 @@
 // exactly by any unmasked weight, and it reproduces TF's uniform softmax over a fully masked row.
 #include "common.cuh"
 #include "attn_tile.cuh"
-#include <cuda.h>
-#include <cuda_fp16.h>
+#include "tc_ptx.cuh"
+#include "attn_tc_common.cuh"
 
 namespace fvta {
 
@@ -69,74 +69,13 @@ constexpr int kWarpTma = 0, kWarpMma = 1, kWarpWsum0 = 4, kWarpSoft0 = 12, kWarp
 constexpr int kWarpTma = 0, kWarpMma = 1, kWarpWsum0 = 4, kWarpSplit0 = 12, kWarpSoft0 = 20;
 #endif
 constexpr int kRegSoftmax = 112, kRegWsum = 48, kRegIssue = 40;   // split keeps the launch value (72)
-constexpr int kTcJQP = 32;        // question positions per tile (N of the MMAs: 64 and 32)
-constexpr int kTcTmemCols = 512;
-constexpr int kTcMaxStages = 6;
-constexpr float kMaskedWeight = 7.888609052210118e-31f;  // 2^-100
-constexpr float kTanhScale = 2.885390081777927f;         // 2 * log2(e)
 constexpr int kTcStageExtra = 512 + 3 * 1024;   // per ring stage: wg [128] + row statistics [3][2][128]
 #ifndef FVTA_TC_MIN_STAGES
 #define FVTA_TC_MIN_STAGES 4
 #endif
 
-struct TcPlan {
-  int TB;           // context positions per tile
-  int rows;         // K * TB <= 128
-  int K32;          // tf32 k-steps (8 features)  = ceil(D / 8)
-  int K16;          // f16 k-steps (16 features)  = ceil(D / 16)
-  int C32;          // 32-feature (128-byte) chunks of the tf32 B image
-  int C16;          // 64-feature (128-byte) chunks of the f16 B image
-  int stages;       // fp32 ring depth
-  int stage_bytes;  // fp32 tile, rounded to 128 B
-  int tiles;        // tiles per sample
-  int slabs;        // CTAs per sample
-  int col_ahi, w_ahi, col_alo, w_alo;   // TMEM columns of the two A buffers (buffer b at col + b * w)
-  size_t smem;
-};
-
-__host__ __device__ inline size_t tc_fixed_smem(const TcPlan& p, int Dp) {
-  return (size_t)p.C32 * 8192 + (size_t)p.C16 * 4096 + (size_t)(3 * Dp + 2 * kTcJQP) * 4 + 5120 /*red*/ +
-         1024 /*combine scratch*/ + 256 /*barriers*/;
-}
-
 static bool tc_make_plan(const FvtaAttnDesc& d, TcPlan& p) {
-  if ((d.D & 3) != 0 || d.D > 128 || d.D < 8 || d.JQ > kTcJQP || d.K > 8) return false;
-  const bool bounded = (d.simi == 4) || d.add_tanh;
-  if (!bounded || d.time_warp_att) return false;
-  p.K32 = (d.D + 7) / 8;
-  p.K16 = (d.D + 15) / 16;
-  p.C32 = (d.D + 31) / 32;
-  p.C16 = (d.D + 63) / 64;
-  p.w_ahi = 8 * p.K32;
-  p.w_alo = 8 * p.K16;
-  p.col_ahi = 128;
-  p.col_alo = p.col_ahi + 2 * p.w_ahi;
-  if (p.col_alo + 2 * p.w_alo > kTcTmemCols) return false;
-  const size_t fixed = tc_fixed_smem(p, round_up(d.D, 4));
-  const size_t budget = 227 * 1024;
-  int best_tb = 0, best_st = 0;
-#ifdef FVTA_TC_TB
-  const int tb_max = FVTA_TC_TB;
-#else
-  const int tb_max = 128 / d.K;
-#endif
-  for (int TB = tb_max; TB >= 2; --TB) {
-    const int sb = round_up(d.K * TB * d.D * 4, 128);
-    int st = (int)((budget - fixed) / (size_t)(sb + kTcStageExtra));
-    if (st > kTcMaxStages) st = kTcMaxStages;
-    if (st >= FVTA_TC_MIN_STAGES) { best_tb = TB; best_st = st; break; }
-    if (st >= 2 && best_tb == 0) { best_tb = TB; best_st = st; }   // deepest ring is not reachable: take the widest tile
-  }
-  if (best_tb == 0) return false;
-  p.TB = best_tb;
-  p.stages = best_st;
-  p.rows = d.K * p.TB;
-  p.stage_bytes = round_up(p.rows * d.D * 4, 128);
-  p.smem = fixed + (size_t)p.stages * (p.stage_bytes + kTcStageExtra);
-  p.tiles = (d.T + p.TB - 1) / p.TB;
-  const int want = (148 + d.N - 1) / d.N;  // one CTA per SM
-  p.slabs = want < 1 ? 1 : (want > p.tiles ? p.tiles : want);
-  return true;
+  return tc_plan(d, p, /*fixed=*/5120 /*red*/ + 1024 /*combine scratch*/ + 512 /*barriers*/, kTcStageExtra, FVTA_TC_MIN_STAGES);
 }
 
 bool attn_tc_covers(const FvtaAttnDesc& d) {
@@ -144,193 +83,7 @@ bool attn_tc_covers(const FvtaAttnDesc& d) {
   return tc_make_plan(d, p);
 }
 
-// ---- PTX wrappers -----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// try_wait suspends the warp in hardware until the phase completes or an implementation time limit
-// passes, so the loop around it rarely iterates and waiting warps do not compete for issue slots.
-// (A suspend-time hint makes ptxas emit a NANOSLEEP.SYNCS loop that wakes on every barrier event of
-// the CTA: measured 33 % of all issued instructions.)  Far more iterations than any real wait can
-// need mean a pipeline bug: trap (the launch fails with an error) instead of hanging the device.
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P1;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try(bar, parity))
-    if (++spins > (1u << 24)) __trap();
-}
-// for the roles with slack (everything but the split warps, which set the pace): sleep between polls so
-// that waiting warps leave the issue slots to the working ones (plain polling was 45 % of all issued
-// instructions); the wake-up delay only adds pipeline latency, which the ring absorbs
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try(bar, parity)) {
-    __nanosleep(64);
-    if (++spins > (1u << 22)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// one lane of a converged warp; the branch it guards keeps warp-uniform values in uniform registers
-// (a `lane == 0` branch makes ptxas re-broadcast every tcgen05.mma operand through an R2UR loop:
-// ~110 cycles per MMA instead of ~10, tools/umma_probe.cu)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-      "elect.sync rx|px, 0xffffffff;\n\t"
-      "@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// D[tmem] (+)= A[tmem] . B[smem]^T, M = 128
-__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]));
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
-}
-
-// K-major, 128B-swizzled operand: 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// D = fp32, M = 128, A and B K-major; fmt 0 = fp16, 2 = tf32
-__device__ __forceinline__ uint32_t umma_idesc(int fmt, int N) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24);
-}
-
-// MUFU.EX2 / MUFU.RCP; tanh(x) = 1 - 2 / (1 + 2^{2 log2(e) x}) built from them has |error| < 1e-6
-// and never exceeds 1 in magnitude
-__device__ __forceinline__ float exp2f_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-// what kind::tf32 keeps of an fp32 operand (tools/umma_probe.cu: the tensor core truncates)
-__device__ __forceinline__ float tf32_part(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-
 // ---- the fused kernel: grid (slabs, N) ----------------------------------------------------------
-template <int NREG> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NREG)); }
-template <int NREG> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NREG)); }
-
-// One split thread's share of a tile row: `NO` 8-feature groups starting at group o0 (compile-time when
-// DT > 0: straight-line code, every bound folded).  Loads first, then statistics, residuals and the
-// two TMEM stores per pair of groups.
-template <bool HAS_LIN, int DT>
-__device__ __forceinline__ void split_row(const float* __restrict__ hrow, const float* __restrict__ coef_s, int Dp,
-                                          int D, int o_begin, int o_end, int K32, uint32_t colA, uint32_t colL,
-                                          float& zdot, float& quad, float& lin) {
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float2 zdA = make_float2(0.f, 0.f), qdA = zdA, lnA = zdA, zdB = zdA, qdB = zdA, lnB = zdA;
-  auto stats4 = [&](int d0, const float4& v, float2& zd, float2& qd, float2& ln) {
-    const float4 cu = *reinterpret_cast<const float4*>(coef_s + d0);
-    const float4 cq = *reinterpret_cast<const float4*>(coef_s + 2 * Dp + d0);
-    const float2 a01 = make_float2(v.x, v.y), a23 = make_float2(v.z, v.w);
-    const float2 s01 = __fmul2_rn(a01, a01), s23 = __fmul2_rn(a23, a23);
-    zd = __ffma2_rn(make_float2(cu.x, cu.y), s01, zd);
-    zd = __ffma2_rn(make_float2(cu.z, cu.w), s23, zd);
-    qd = __ffma2_rn(make_float2(cq.x, cq.y), s01, qd);
-    qd = __ffma2_rn(make_float2(cq.z, cq.w), s23, qd);
-    if (HAS_LIN) {
-      const float4 cl = *reinterpret_cast<const float4*>(coef_s + Dp + d0);
-      ln = __ffma2_rn(make_float2(cl.x, cl.y), a01, ln);
-      ln = __ffma2_rn(make_float2(cl.z, cl.w), a23, ln);
-    }
-  };
-  // residual the tensor core drops, as two packed fp16: exact subtraction, fp16 rounding 2^-11 of it
-  auto lo2 = [&](float a, float b) -> uint32_t {
-    const float2 rr = __ffma2_rn(make_float2(tf32_part(a), tf32_part(b)), make_float2(-1.f, -1.f), make_float2(a, b));
-    const __half2 p = __floats2half2_rn(rr.x, rr.y);
-    return *reinterpret_cast<const uint32_t*>(&p);
-  };
-  auto pair = [&](int o, bool two) {
-    const int d0 = o * 8;
-    const float4 v0 = d0 < D ? *reinterpret_cast<const float4*>(hrow + d0) : zero4;
-    const float4 v1 = d0 + 4 < D ? *reinterpret_cast<const float4*>(hrow + d0 + 4) : zero4;
-    const float4 v2 = (two && d0 + 8 < D) ? *reinterpret_cast<const float4*>(hrow + d0 + 8) : zero4;
-    const float4 v3 = (two && d0 + 12 < D) ? *reinterpret_cast<const float4*>(hrow + d0 + 12) : zero4;
-    if (d0 < D) stats4(d0, v0, zdA, qdA, lnA);
-    if (d0 + 4 < D) stats4(d0 + 4, v1, zdB, qdB, lnB);
-    if (two && d0 + 8 < D) stats4(d0 + 8, v2, zdA, qdA, lnA);
-    if (two && d0 + 12 < D) stats4(d0 + 12, v3, zdB, qdB, lnB);
-    uint32_t hi[16], lo[8];
-    hi[0] = __float_as_uint(v0.x); hi[1] = __float_as_uint(v0.y); hi[2] = __float_as_uint(v0.z); hi[3] = __float_as_uint(v0.w);
-    hi[4] = __float_as_uint(v1.x); hi[5] = __float_as_uint(v1.y); hi[6] = __float_as_uint(v1.z); hi[7] = __float_as_uint(v1.w);
-    hi[8] = __float_as_uint(v2.x); hi[9] = __float_as_uint(v2.y); hi[10] = __float_as_uint(v2.z); hi[11] = __float_as_uint(v2.w);
-    hi[12] = __float_as_uint(v3.x); hi[13] = __float_as_uint(v3.y); hi[14] = __float_as_uint(v3.z); hi[15] = __float_as_uint(v3.w);
-    lo[0] = lo2(v0.x, v0.y); lo[1] = lo2(v0.z, v0.w); lo[2] = lo2(v1.x, v1.y); lo[3] = lo2(v1.z, v1.w);
-    lo[4] = lo2(v2.x, v2.y); lo[5] = lo2(v2.z, v2.w); lo[6] = lo2(v3.x, v3.y); lo[7] = lo2(v3.z, v3.w);
-    // every condition below is warp-uniform (o and the half are): the stores are warp-collective
-    if (two && o + 1 < K32) tmem_st16(colA + 8 * o, hi);
-    else if (o < K32) tmem_st8(colA + 8 * o, hi);
-    if (two) tmem_st8(colL + 4 * o, lo);
-    else tmem_st4(colL + 4 * o, lo);
-  };
-  if (DT > 0) {
-    constexpr int kOT = 2 * ((DT + 15) / 16), kHalf = kOT / 2;     // groups per thread half
-#pragma unroll
-    for (int j = 0; j < kHalf; j += 2) pair(o_begin + j, j + 1 < kHalf);
-  } else {
-#pragma unroll 1
-    for (int o = o_begin; o < o_end; o += 2) pair(o, o + 1 < o_end);
-  }
-  const float2 zd2 = __fadd2_rn(zdA, zdB), qd2 = __fadd2_rn(qdA, qdB), ln2 = __fadd2_rn(lnA, lnB);
-  zdot = zd2.x + zd2.y; quad = qd2.x + qd2.y; lin = ln2.x + ln2.y;
-}
 
 // DT: compile-time D (100, the reference hidden size 50) or 0 = any supported D at run time.
 template <bool HAS_LIN, int DT>
@@ -360,7 +113,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   uint64_t* full = bars;                              // [S]  TMA -> split
   uint64_t* empty = bars + kTcMaxStages;              // [S]  wsum -> TMA
   uint64_t* wg_ready = bars + 2 * kTcMaxStages;       // [S]  softmax -> wsum
-  uint64_t* a_ready = bars + 3 * kTcMaxStages;        // [2]  split -> MMA (operands), softmax (row statistics)
+  uint64_t* zq_ready = bars + 3 * kTcMaxStages;       // [S]  split -> softmax (row statistics).  Per STAGE, not per
+                                                      //      TMEM buffer: a softmax group that lags cannot see this
+                                                      //      barrier run two phases ahead (parity waits would alias)
+  uint64_t* a_ready = bars + 4 * kTcMaxStages;        // [2]  split -> MMA (operands in tensor memory)
   uint64_t* acc_full = a_ready + 2;                   // [2]  MMA -> softmax (accumulator), split (A buffers free)
   uint64_t* ep_done = a_ready + 4;                    // [2]  softmax -> MMA (accumulator drained)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_ready + 6);
@@ -376,7 +132,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
   const int ws_warps = (d.K * (D >> 2) + 31) >> 5;      // weighted-sum warps with work (<= 8)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], ws_warps * 32); mbar_init(&wg_ready[s], 128); }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1); mbar_init(&empty[s], ws_warps * 32); mbar_init(&wg_ready[s], 128); mbar_init(&zq_ready[s], 256);
+    }
     for (int b2 = 0; b2 < 2; ++b2) { mbar_init(&a_ready[b2], 256); mbar_init(&acc_full[b2], 1); mbar_init(&ep_done[b2], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -483,10 +241,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       const uint32_t colA = lane_base + (uint32_t)(pl.col_ahi + b2 * pl.w_ahi);
       const uint32_t colL = lane_base + (uint32_t)(pl.col_alo + b2 * pl.w_alo);
       float zdot, quad, lin;
-      split_row<HAS_LIN, DT>(hrow, coef_s, Dp, D, o_begin, o_end, K32, colA, colL, zdot, quad, lin);
+      float hg_unused;
+      split_row<HAS_LIN, false, DT>(hrow, coef_s, nullptr, Dp, D, o_begin, o_end, K32, colA, colL, zdot, quad, lin, hg_unused);
       float* zq = zq_s + s * 768 + h * 128 + r;
       zq[0] = zdot; zq[256] = quad;
       if (HAS_LIN) zq[512] = lin;
+      mbar_arrive(&zq_ready[s]);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&a_ready[b2]);
@@ -525,7 +285,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         if (d.has_mask && active && i + 2 < ntile && t2 < d.T) mh_next = mrow[t2];
       }
       TC_TRACE(3, i, 0);
-      mbar_wait_relaxed(&a_ready[p], (i >> 1) & 1);     // the split warps' row statistics are visible
+#ifdef FVTA_AB_AREADY
+      mbar_wait_relaxed(&a_ready[p], (i >> 1) & 1);
+#else
+      mbar_wait_relaxed(&zq_ready[s], (i / S) & 1);     // the split warps' row statistics are visible
+#endif
       const float* zq = zq_s + s * 768;
       float g = 1.f;
       if (d.use_time_warp) {
@@ -789,20 +553,6 @@ extern "C" int fvta_tc_trace_read(long long* out) {
 #endif
 
 // ---- host side --------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;   // resolved once; the same pointer for every caller
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(p);
-  return fn;
-}
-
 // Runs the tile kernel (+ fused combine) over a workspace whose folded operands are in place.
 int attn_fwd_tc_launch(const FvtaAttnDesc& d, const AttnLayout& L, const float* hall, const uint8_t* hall_mask,
                        const uint8_t* hq_mask, float* ws, float* g1_all, float* a_logits, float* c_col, float* stats,
@@ -810,17 +560,11 @@ int attn_fwd_tc_launch(const FvtaAttnDesc& d, const AttnLayout& L, const float* 
   TcPlan pl;
   if (!tc_make_plan(d, pl)) return FVTA_E_SHAPE;
   if (pl.slabs > L.npart) return FVTA_E_SHAPE;
-  EncodeTiledFn encode = get_encode_fn();
-  if (!encode) { set_last_error("cuTensorMapEncodeTiled not found", cudaErrorUnknown); return FVTA_E_LAUNCH; }
   CUtensorMap tmap;
-  cuuint64_t gdim[3] = {(cuuint64_t)d.D, (cuuint64_t)d.T, (cuuint64_t)d.N * d.K};
-  cuuint64_t gstr[2] = {(cuuint64_t)d.D * 4, (cuuint64_t)d.T * d.D * 4};
-  cuuint32_t box[3] = {(cuuint32_t)d.D, (cuuint32_t)pl.TB, (cuuint32_t)d.K};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(hall), gdim, gstr, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed", cudaErrorInvalidValue); return FVTA_E_LAUNCH; }
+  if (!tc_make_tile_map(&tmap, hall, d.N, d.K, d.T, d.D, pl.TB)) {
+    set_last_error("cuTensorMapEncodeTiled failed", cudaErrorInvalidValue);
+    return FVTA_E_LAUNCH;
+  }
   const bool has_lin = (d.simi == 1 || d.simi == 3);   // w_lin is identically zero otherwise
   auto kern = has_lin ? attn_fwd_tc<true, 0> : (d.D == 100 ? attn_fwd_tc<false, 100> : attn_fwd_tc<false, 0>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);

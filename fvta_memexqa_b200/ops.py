@@ -115,7 +115,7 @@ def attn_forward(cfg, hall, hall_mask, hq, hq_mask, lq, W, b, WH_W=None, WH_b=No
 
 
 def attn_backward(fwd, d_g1_all, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=None, sinks=None,
-                  d_hall_out=None, d_hq_out=None):
+                  d_hall_out=None, d_hq_out=None, path=None):
     """fvta_attn_bwd given the dict attn_forward returned.  Returns dict of gradients.  `sinks`:
     optional tensors the six parameter gradients are written into (the entry point overwrites).
     d_hall_out / d_hq_out: optional contiguous tensors to receive d_hall / d_hq (overwritten)."""
@@ -143,7 +143,10 @@ def attn_backward(fwd, d_g1_all, W, b, WH_W=None, WH_b=None, WC_W=None, WC_b=Non
                           WC_W=_ptr(gs[2]), WC_b=_ptr(gs[3]))
     params = _attn_params(W, b, WH_W, WH_b, WC_W, WC_b)
     ws = fwd["ws"]
-    desc.ws_from_fwd = 1        # the forward's workspace is kept alive in `fwd`: reuse its folded operands
+    # the forward's workspace is kept alive in `fwd`: reuse its folded operands (2: and the tensor-core images)
+    desc.ws_from_fwd = 2 if fwd.get("path") == _lib.PATH_TC else 1
+    if path is not None:        # A/B: _lib.PATH_FFMA pins the CUDA-core backward tile kernel
+        desc.path = int(path)
     rc = lib.fvta_attn_bwd(ctypes.byref(desc), _ptr(hall), _ptr(hm), _ptr(hq), _ptr(qm), _ptr(lq),
                            ctypes.byref(params), _ptr(fwd["stats"]), _ptr(d_g1_all), _ptr(out["d_hall"]),
                            _ptr(out["d_hq"]), _ptr(out["d_lq"]), ctypes.byref(grads), _ptr(ws),

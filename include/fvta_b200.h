@@ -58,7 +58,8 @@ typedef struct {
   int32_t window;        /* ceil(window_t) for warp_type 5 (model_v2.py:333-337); 3 */
   int32_t time_warp_att; /* --use_time_warp_att (model_v2.py:269-275) */
   int32_t has_mask;      /* 0: hinfo_mask/hq_mask are None (exp_mask skipped, model_v2.py:263) */
-  int32_t ws_from_fwd;   /* 1 = `workspace` still holds what an earlier fvta_attn_fwd call left there for
+  int32_t ws_from_fwd;   /* 1 (2: incl. the tensor-core question images, i.e. the forward ran FVTA_PATH_TC) =
+                            `workspace` still holds what an earlier fvta_attn_fwd call left there for
                             the same hq / hq_mask / lq / parameters, so the operand folding is not redone
                             (fvta_attn_bwd after its forward; fvta_attn_fwd over a new context with the
                             same question, e.g. repeated inference) */

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import collapsed
-from fvta_memexqa_b200 import ops
+from fvta_memexqa_b200 import _lib, ops
 from tests.helpers import attn_case, rel_err
 
 pytestmark = pytest.mark.gpu
@@ -192,9 +192,22 @@ def test_attn_bwd_parity(cuda_device, case):
         assert rel_err(gr[key], r) < tol, (key, rel_err(gr[key], r), tol)
 
 
-def test_attn_golden_c2(cuda_device):
+# Gradients that are sums with heavy cancellation (d_lq = K*W_WC*sum_t dz, and the time-warp projection
+# gradients that are sums of the same dz): the softmax makes sum_t a*(S - sum a*S) vanish exactly, so what
+# is left is ~1e-4 of the partial sums and every relative error of the logits is amplified ~5000x.  The
+# fp32 CPU oracle itself is 3e-4 off the fp64 golden there.  The tensor-core path carries logits to ~21
+# mantissa bits (tf32 hi/lo split + fp16 residual, attn_fwd_tc.cu), 4x the fp32 rounding, hence this
+# stated bound for those five gradients on that path; every other output keeps 2*TOL.
+TC_CANCELLING_BOUND = 1.5e-2
+CANCELLING = ("d_lq", "d_WH_W", "d_WH_b", "d_WC_W", "d_WC_b")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", [_lib.PATH_FFMA, _lib.PATH_AUTO], ids=["ffma", "auto"])
+def test_attn_golden_c2(cuda_device, path):
     """The committed golden vectors (tests/golden/attn_c2.npz, made by tools/make_golden.py from
-    the fp64 oracle) at the C2 shape: forward outputs and every gradient."""
+    the fp64 oracle) at the C2 shape: forward outputs and every gradient, on the FFMA kernels and on
+    whatever the library picks by itself (the tensor-core kernels at this shape)."""
     import os
     import numpy as np
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "attn_c2.npz"))
@@ -204,7 +217,9 @@ def test_attn_golden_c2(cuda_device):
     for k in list(params):
         if "param/" + k in z.files:
             params[k] = torch.as_tensor(z["param/" + k])
-    out, p = run_gpu_fwd(cfg, params, inp, cuda_device, want_logits=True, want_c=True)
+    out, p = run_gpu_fwd(cfg, params, inp, cuda_device, want_logits=True, want_c=True, path=path)
+    if path == _lib.PATH_AUTO:
+        assert out["path"] == _lib.PATH_TC, "the C2 shape must run on the tensor-core kernels"
     assert rel_err(out["g1_all"], torch.as_tensor(z["g1_all"])) < TOL
     assert rel_err(out["c_col"], torch.as_tensor(z["c"])) < TOL
     ref_a = torch.as_tensor(z["att_logits"]).double()
@@ -233,4 +248,6 @@ def test_attn_golden_c2(cuda_device):
     for k, ref in pairs.items():
         ref = torch.as_tensor(ref).double()
         tol = 2 * TOL if k not in g32 else max(2 * TOL, 6 * rel_err(g32[k], ref))
+        if out["path"] == _lib.PATH_TC and k in CANCELLING:
+            tol = max(tol, TC_CANCELLING_BOUND)
         assert rel_err(gr[k], ref) < tol, (k, rel_err(gr[k], ref), tol)

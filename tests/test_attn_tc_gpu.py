@@ -200,6 +200,62 @@ def test_tc_backward_after_tc_forward(cuda_device):
         assert e < bounds.get(k, BOUND), (k, e)
 
 
+BWD_TC_CASES = {
+    "bench shape N=8": (8, 6, 4, 64, 100, 25, 2, True, True, 5, 0.3, 0.6),
+    "dense masks, N=3": (3, 6, 4, 64, 100, 25, 2, True, True, 5, 1.0, 1.0),
+    "long T, ring wraps": (2, 6, 8, 128, 100, 32, 2, True, True, 5, 0.6, 0.8),
+    "K=5": (3, 5, 4, 64, 100, 25, 2, True, True, 5, 0.4, 0.6),
+    "simi 1 + tanh": (2, 6, 4, 40, 100, 25, 1, True, True, 5, 0.5, 0.6),
+    "simi 3 + tanh": (2, 6, 4, 40, 100, 25, 3, True, True, 5, 0.5, 0.6),
+    "cosine": (2, 6, 4, 40, 100, 32, 4, False, True, 5, 0.5, 0.6),
+    "no time warp": (2, 6, 4, 64, 100, 25, 2, True, False, 1, 0.5, 0.6),
+    "D=36": (2, 6, 4, 40, 36, 13, 2, True, True, 5, 0.5, 0.6),
+    "D=128, K=8": (2, 8, 4, 64, 128, 32, 2, True, True, 5, 0.5, 0.6),
+    "T=12": (3, 6, 1, 12, 100, 25, 2, True, True, 5, 0.5, 0.6),
+}
+
+
+@pytest.mark.parametrize("name", list(BWD_TC_CASES))
+def test_tc_backward_vs_oracle_and_ffma(cuda_device, name):
+    """The tensor-core backward (csrc/attn_bwd_tc.cu: tcgen05 recompute + sparse d-logit routing) against the
+    fp64 oracle's autograd and against the CUDA-core backward on the same forward.  Fixed bounds: 1e-4 of
+    the largest entry of each gradient, 5e-4 for the four gradients that are sums over every row with heavy
+    cancellation (d_lq, d_WC_W, d_WC_b, d_WH_b)."""
+    N, K, M, JMAX, D, JQ, simi, tanh, warp, wtype, dens, qd = BWD_TC_CASES[name]
+    cfg, params, inp = attn_case(N, K, M, JMAX, D, JQ, simi, tanh, warp, wtype, False, density=dens,
+                                 q_density=qd, seed=5 + N + D)
+    out, p = _run(cfg, params, inp, cuda_device)
+    assert out["path"] == _lib.PATH_TC
+    g = torch.Generator().manual_seed(5)
+    dg1 = torch.randn(N, D, generator=g)
+    names = ("attention/all/att_logits/W", "attention/all/att_logits/b", "time_warp/WH/W", "time_warp/WH/b",
+             "time_warp/WC/W", "time_warp/WC/b")
+    args = [p.get(k) for k in names]
+    gr = ops.attn_backward(out, dg1.to(cuda_device), *args)
+    gr_ff = ops.attn_backward(out, dg1.to(cuda_device), *args, path=_lib.PATH_FFMA)
+    pp = {k: v.double().clone().requires_grad_(True) for k, v in params.items()}
+    hall = inp["hall"].double().clone().requires_grad_(True)
+    hq = inp["hq"].double().clone().requires_grad_(True)
+    lq = inp["lq"].double().clone().requires_grad_(True)
+    o = collapsed.fvta_attention(hall, inp["hall_mask"], hq, inp["q_mask"], lq, pp, cfg)
+    (o["g1_all"] * dg1.double()).sum().backward()
+    refs = {"d_hall": hall.grad.reshape(N, K, -1, D), "d_hq": hq.grad, "d_lq": lq.grad}
+    for key, nme in zip(("d_att_W", "d_att_b", "d_WH_W", "d_WH_b", "d_WC_W", "d_WC_b"), names):
+        refs[key] = pp[nme].grad if nme in pp else None
+    bounds = {"d_lq": 5e-4, "d_WC_W": 5e-4, "d_WC_b": 5e-4, "d_WH_b": 5e-4}
+    for k, r in refs.items():
+        if r is None or gr.get(k) is None:
+            continue
+        if r.abs().max() == 0:
+            assert gr[k].abs().max().item() == 0.0, k
+            continue
+        e = ((gr[k].double().cpu() - r).abs().max() / r.abs().max()).item()
+        e_ff = ((gr[k].double().cpu() - gr_ff[k].double().cpu()).abs().max() / r.abs().max()).item()
+        print("[tc bwd] %-22s %-8s vs oracle %.2e  vs ffma %.2e" % (name, k, e, e_ff))
+        assert e < bounds.get(k, BOUND), (k, e)
+        assert e_ff < 2 * bounds.get(k, BOUND), (k, e_ff)
+
+
 def test_folded_workspace_reuse(cuda_device):
     """FvtaAttnDesc.ws_from_fwd on the forward: a second call over a NEW context with the same question
     reuses the folded operands and launches exactly one kernel."""
