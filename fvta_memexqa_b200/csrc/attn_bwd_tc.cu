@@ -33,19 +33,31 @@ namespace fvta {
 constexpr int kBtThreads = 896;
 // warp 0 TMA, 1 MMA, 2-3 idle, 4-11 update, 12-19 split, 20-27 row warpgroups
 constexpr int kBwTma = 0, kBwMma = 1, kBwUpd0 = 4, kBwSplit0 = 12, kBwRow0 = 20;
-constexpr int kBtRegRow = 88, kBtRegUpd = 72, kBtRegIssue = 40;     // split keeps the launch value (72)
-constexpr int kBtBucketCap = 48;       // entries per column bucket; the rest goes to the overflow list
-constexpr int kBtOvCap = 64;
-constexpr int kBtStageExtra = 4 * 1024 + 128 * 32;   // per stage: row statistics [4][2][128] + records [128][8]
+constexpr int kBtRegRow = 80, kBtRegUpd = 80, kBtRegIssue = 40, kBtRegLaunch = 72;   // split keeps the launch value
+// setmaxnreg.inc waits until the pool holds the registers: a split that does not fit the file deadlocks
+static_assert(128 * kBtRegIssue + 256 * (kBtRegLaunch + kBtRegRow + kBtRegUpd) <= 65536, "register file");
+static_assert(kBtThreads * kBtRegLaunch <= 65536, "launch registers");
+constexpr int kBtEnd = 0xffff;         // end of a column's entry list
+constexpr int kBtStageExtra = 4 * 1024;   // per stage: half-row statistics [4][2][128]
 
-struct BtOverflow { int r, j; float v; };
+#ifdef FVTA_TC_TRACE
+constexpr int kBtTraceTiles = 24;
+__device__ long long g_bt_trace[5][kBtTraceTiles][8];
+__device__ int g_bt_count[8];
+__device__ long long g_bt_iter[32];
+#define BT_TRACE(role, i, ev)                                                                       \
+  do { if (blockIdx.x == 0 && blockIdx.y == 0 && (i) < kBtTraceTiles && (threadIdx.x & 127) == 0)     \
+         g_bt_trace[role][(i)][ev] = clock64(); } while (0)
+#else
+#define BT_TRACE(role, i, ev) do {} while (0)
+#endif
 
-// fixed scratch: buckets 2 x (32 counts + 32 x cap u16), overflow 2 x (count + cap x 12 B), gvec [Dp<=128],
-// dg exchange [2][128], dcol [32], per-k statistics [8][12], barriers
-constexpr int kBtFixedExtra = 2 * (128 + 32 * kBtBucketCap * 2) + 2 * (16 + kBtOvCap * 12) + 512 + 1024 + 128 + 384 + 512 + 256;
+// fixed scratch: gvec [128], d gate exchange [2 groups][2 phases][128], dcol [32], per-k statistics [8][12],
+// per-row records [2 parities][128][8], entry lists (heads [2][32], links [2][3 x 128] u16), d zconst, barriers
+constexpr int kBtFixedExtra = 512 + 2048 + 128 + 384 + 8192 + 256 + 1536 + 16 + 512;
 
 static bool bt_make_plan(const FvtaAttnDesc& d, TcPlan& p) {
-  return tc_plan(d, p, kBtFixedExtra, kBtStageExtra, 3);
+  return tc_plan(d, p, kBtFixedExtra, kBtStageExtra, 4);
 }
 
 bool attn_bwd_tc_covers(const FvtaAttnDesc& d) {
@@ -71,16 +83,14 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
   float* col_s = coef_s + 3 * Dp;                 // [32] (prescaled like the forward's)
   float* cap_s = col_s + kTcJQP;                  // [32]
   float* gvec_s = cap_s + kTcJQP;                 // [128] upstream gradient d g1_all[n, :]
-  float* dgx_s = gvec_s + 128;                    // [2][128] per-row d gate of a tile (per row warpgroup)
-  float* dcol_s = dgx_s + 256;                    // [32]
+  float* dgx_s = gvec_s + 128;                    // [2 groups][2 phases][128] per-row d gate of a tile
+  float* dcol_s = dgx_s + 512;                    // [32]
   float* kst_s = dcol_s + 32;                     // [8][12] per-modality statistics
   float* zq_s = kst_s + 96;                       // [S][4][2][128] half-row statistics: zdot, quad, lin, hg
-  float4* rec_s = reinterpret_cast<float4*>(zq_s + S * 1024);   // [S][128][2] per-row records
-  int* bcnt_s = reinterpret_cast<int*>(rec_s + S * 256);        // [2][32]
-  uint16_t* blist_s = reinterpret_cast<uint16_t*>(bcnt_s + 64); // [2][32][cap]
-  int* ovcnt_s = reinterpret_cast<int*>(blist_s + 2 * 32 * kBtBucketCap);   // [2] (+2 pad)
-  BtOverflow* ov_s = reinterpret_cast<BtOverflow*>(ovcnt_s + 4);            // [2][cap]
-  float* dzc_s = reinterpret_cast<float*>(ov_s + 2 * kBtOvCap);             // [1] (+3 pad)
+  float4* rec_s = reinterpret_cast<float4*>(zq_s + S * 1024);   // [2][128][2] per-row records, by tile parity
+  int* head_s = reinterpret_cast<int*>(rec_s + 2 * 256);        // [2][32] newest entry of column j
+  uint16_t* next_s = reinterpret_cast<uint16_t*>(head_s + 64);  // [2][3 x 128] entry -> older entry of its column
+  float* dzc_s = reinterpret_cast<float*>(next_s + 2 * 384);    // [1] (+3 pad)
   uint64_t* bars = reinterpret_cast<uint64_t*>(dzc_s + 4);
   uint64_t* full = bars;                              // [S]  TMA -> split
   uint64_t* empty = bars + kTcMaxStages;              // [S]  update -> TMA (tile stored, stage free)
@@ -133,8 +143,7 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       cap_s[j] = j >= d.JQ ? -INFINITY : (qv ? INFINITY : FVTA_VERY_NEGATIVE);
       dcol_s[j] = 0.f;
     }
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) bcnt_s[i] = 0;
-    if (threadIdx.x < 2) ovcnt_s[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) head_s[i] = kBtEnd;
     if (threadIdx.x == 0) dzc_s[0] = 0.f;
     if (threadIdx.x < d.K) {
       const int k = threadIdx.x;
@@ -157,6 +166,7 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       for (int i = 0; i < ntile; ++i) {
         const int s = i % S;
         if (i >= S) mbar_wait_relaxed(&empty[s], ((i / S) - 1) & 1);
+        BT_TRACE(0, i, 0);
         if (elect_one()) {
           mbar_expect_tx(&full[s], (uint32_t)(rows * D * 4));
           tma_load_3d(ring + (size_t)s * pl.stage_bytes, &tmap_in, &full[s], 0, (tile_begin + i) * TB, n * d.K);
@@ -172,7 +182,9 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
         const uint32_t a_hi = tmem_base + (uint32_t)(pl.col_ahi + b2 * pl.w_ahi);
         const uint32_t a_lo = tmem_base + (uint32_t)(pl.col_alo + b2 * pl.w_alo);
         mbar_wait_relaxed(&a_ready[b2], (i >> 1) & 1);
+        BT_TRACE(1, i, 0);
         if (i >= 2) mbar_wait_relaxed(&ep_done[b2], ((i - 2) >> 1) & 1);
+        BT_TRACE(1, i, 1);
         tc_fence_after();
         if (elect_one()) {
           if (DT > 0) {
@@ -206,11 +218,14 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       const int s = i % S, b2 = i & 1;
       // every role of this kernel sleeps between polls: a spinning role starves the others of issue slots
       // (measured: the update warps, lowest in the scheduler's order, ran 4x slower next to spinning split warps)
+      BT_TRACE(2, i, 0);
       mbar_wait_relaxed(&full[s], (i / S) & 1);
+      BT_TRACE(2, i, 1);
       if (i >= 2) {
         mbar_wait_relaxed(&acc_full[b2], ((i - 2) >> 1) & 1);
         tc_fence_after();
       }
+      BT_TRACE(2, i, 2);
       const float* hrow = reinterpret_cast<const float*>(ring + (size_t)s * pl.stage_bytes) + roff;
       const uint32_t colA = lane_base + (uint32_t)(pl.col_ahi + b2 * pl.w_ahi);
       const uint32_t colL = lane_base + (uint32_t)(pl.col_alo + b2 * pl.w_alo);
@@ -223,6 +238,7 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&a_ready[b2]);
+      BT_TRACE(2, i, 3);
     }
   } else if (warp >= kBwRow0) {
     // ===== row warpgroups: group p handles tiles i = p, p + 2, ...; thread r owns context row r =====
@@ -239,18 +255,22 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
     const uint8_t* mrow = hall_mask + ((size_t)n * d.K + k) * d.T;
     // per-modality statistics of the forward and the upstream gradients derived from them
     const float* ks = kst_s + k * 12;
-    const float Mk = ks[0], Lk = ks[1], sk = ks[2], tiesk = ks[3];
+    const float Mk = ks[0], sk = ks[2], tiesk = ks[3];
+    const float rLk = ks[1] > 0.f ? 1.f / ks[1] : 0.f;
     const int amax_t = (int)ks[4], amax_j = (int)ks[5];
     const float dsk = ks[6], rdr = ks[7], beta = ks[8];
     const float ds_each = dsk / tiesk;
-    int* bcnt = bcnt_s + p * 32;
-    uint16_t* blist = blist_s + p * 32 * kBtBucketCap;
+    const float s_scale = tanh_on ? kTanhScale : 1.f;
+    int* head = head_s + p * 32;
+    uint16_t* nxt = next_s + p * 384;
+    float4* rec = rec_s + p * 256;
+    float dzc_acc = 0.f;
     uint8_t mh_next = 1;
     {
       const int t0 = (tile_begin + p) * TB + tt;
       if (d.has_mask && active && p < ntile && t0 < d.T) mh_next = mrow[t0];
     }
-    int use = 0;    // how many tiles this group has processed (parity of bk_free)
+    int use = 0;    // how many tiles this group has processed (parity of bk_free, phase of the d gate exchange)
     for (int i = p; i < ntile; i += 2, ++use) {
       const int s = i % S;
       const int t = (tile_begin + i) * TB + tt;
@@ -261,7 +281,9 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
         mh_next = 1;
         if (d.has_mask && active && i + 2 < ntile && t2 < d.T) mh_next = mrow[t2];
       }
+      BT_TRACE(3, i, 0);
       mbar_wait_relaxed(&zq_ready[s], (i / S) & 1);
+      BT_TRACE(3, i, 1);
       const float* zq = zq_s + s * 1024;
       float g = 1.f, tz = 0.f, cnt = 0.f;
       if (d.use_time_warp) {
@@ -279,51 +301,65 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       float c1, c0v;
       row_coefs(d, g, lin, quad, c1, c0v);
       const float p_c0 = cosine ? 0.f : c0v;
-      const float s_scale = tanh_on ? kTanhScale : 1.f;
-      const float2 c1c1 = make_float2(c1 * s_scale, c1 * s_scale), c0c0 = make_float2(p_c0 * s_scale, p_c0 * s_scale);
-      // the previous tile of this group must have left the buckets of this parity
+      const float c1s = c1 * s_scale, c0s = p_c0 * s_scale;
+      const float2 c1c1 = make_float2(c1s, c1s), c0c0 = make_float2(c0s, c0s);
+      // the previous tile of this group must have left the records and entry lists of this parity
       if (use >= 1) mbar_wait_relaxed(&bk_free[p], (use - 1) & 1);
+      BT_TRACE(3, i, 2);
       mbar_wait_relaxed(&acc_full[p], (i >> 1) & 1);
       tc_fence_after();
+      BT_TRACE(3, i, 3);
 
-      // ---- logits with the forward's instruction sequence: row maximum, its first column, ties ----
-      float m = -INFINITY, Pm = 0.f, Pg = 0.f, ag = 0.f;
+      // ---- the logits with the forward's instruction sequence; row maximum, its first column, ties.
+      //      Straight-line selects: a branchy argmax costs 2x here (the pass is issue-bound). ----
+      float m = -INFINITY, Pm = 0.f;
       int jm = 0, rowcnt = 0;
-      const bool want_g = in_range && tiesk == 1.f && t == amax_t;    // the unique sequence maximum sits in this row
-      auto logits_pass = [&](auto&& visit) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t x0[16], x1[16];
-          tmem_ld16_issue(taddr + 16 * hh, x0);
-          tmem_ld16_issue(taddr + 32 + 16 * hh, x1);
-          tmem_ld_wait();
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t x0[16], x1[16];
+        tmem_ld16_issue(taddr + 16 * hh, x0);
+        tmem_ld16_issue(taddr + 32 + 16 * hh, x1);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {
-            const float4 cq = col4[(16 * hh + j) >> 2], kq = cap4[(16 * hh + j) >> 2];
-            const float colr0 = (j & 2) ? cq.z : cq.x, colr1 = (j & 2) ? cq.w : cq.y;
-            const float capr0 = (j & 2) ? kq.z : kq.x, capr1 = (j & 2) ? kq.w : kq.y;
-            const float2 P = __fadd2_rn(make_float2(__uint_as_float(x0[j]), __uint_as_float(x0[j + 1])),
-                                        make_float2(__uint_as_float(x1[j]), __uint_as_float(x1[j + 1])));
-            float2 Sv = __fadd2_rn(__ffma2_rn(c1c1, P, c0c0), make_float2(colr0, colr1));
-            if (tanh_on) {
-              const float2 den = __fadd2_rn(make_float2(exp2f_approx(Sv.x), exp2f_approx(Sv.y)), make_float2(1.f, 1.f));
-              Sv = __ffma2_rn(make_float2(rcp_approx(den.x), rcp_approx(den.y)), make_float2(-2.f, -2.f), make_float2(1.f, 1.f));
-            }
-            float a0 = fminf(Sv.x, capr0), a1 = fminf(Sv.y, capr1);
-            if (!mh) { a0 = fminf(capr0, FVTA_VERY_NEGATIVE); a1 = fminf(capr1, FVTA_VERY_NEGATIVE); }
-            visit(16 * hh + j, a0, P.x);
-            visit(16 * hh + j + 1, a1, P.y);
+        for (int j = 0; j < 16; j += 2) {
+          const float4 cq = col4[(16 * hh + j) >> 2], kq = cap4[(16 * hh + j) >> 2];
+          const float colr0 = (j & 2) ? cq.z : cq.x, colr1 = (j & 2) ? cq.w : cq.y;
+          const float capr0 = (j & 2) ? kq.z : kq.x, capr1 = (j & 2) ? kq.w : kq.y;
+          const float2 P = __fadd2_rn(make_float2(__uint_as_float(x0[j]), __uint_as_float(x0[j + 1])),
+                                      make_float2(__uint_as_float(x1[j]), __uint_as_float(x1[j + 1])));
+          float2 Sv = __fadd2_rn(__ffma2_rn(c1c1, P, c0c0), make_float2(colr0, colr1));
+          if (tanh_on) {
+            const float2 den = __fadd2_rn(make_float2(exp2f_approx(Sv.x), exp2f_approx(Sv.y)), make_float2(1.f, 1.f));
+            Sv = __ffma2_rn(make_float2(rcp_approx(den.x), rcp_approx(den.y)), make_float2(-2.f, -2.f), make_float2(1.f, 1.f));
           }
+          float a0 = fminf(Sv.x, capr0), a1 = fminf(Sv.y, capr1);
+          if (!mh) { a0 = fminf(capr0, FVTA_VERY_NEGATIVE); a1 = fminf(capr1, FVTA_VERY_NEGATIVE); }
+          x0[j] = __float_as_uint(a0); x0[j + 1] = __float_as_uint(a1);        // logits
+          x1[j] = __float_as_uint(P.x); x1[j + 1] = __float_as_uint(P.y);      // raw similarities
         }
-      };
-      logits_pass([&](int j, float a, float P) {
-        if (a > m) { m = a; jm = j; Pm = P; rowcnt = 1; }
-        else if (a == m) { rowcnt++; }
-        if (want_g && j == amax_j) { Pg = P; ag = a; }
-      });
+        float mq = __uint_as_float(x0[0]);
+#pragma unroll
+        for (int j = 1; j < 16; ++j) mq = fmaxf(mq, __uint_as_float(x0[j]));
+        int jh = 0, ch = 0;
+        float Ph = 0.f;
+#pragma unroll
+        for (int j = 15; j >= 0; --j) {
+          const bool eq = __uint_as_float(x0[j]) == mq;
+          jh = eq ? j : jh;
+          Ph = eq ? __uint_as_float(x1[j]) : Ph;
+          ch += eq ? 1 : 0;
+        }
+        const bool gt = mq > m, eqm = mq == m;
+        jm = gt ? 16 * hh + jh : jm;
+        Pm = gt ? Ph : Pm;
+        rowcnt = gt ? ch : (eqm ? rowcnt + ch : rowcnt);
+        m = gt ? mq : m;
+      }
+      BT_TRACE(3, i, 6);
 
       // ---- upstream of the logits ----
-      const float alpha = !in_range ? 0.f : (sk <= -1e29f ? 1.f / (float)d.T : expf(m - Mk) / Lk);
+      const float alpha = !in_range ? 0.f
+                          : (sk <= -1e29f ? 1.f / (float)d.T : exp2f_approx((m - Mk) * 1.4426950408889634f) * rLk);
       const float e_up = beta * hg;                    // h . d r_k
       const float dm = alpha * (g * e_up - rdr);       // through the softmax over T
       float dg = alpha * e_up;                         // r_k = sum alpha * g * h
@@ -331,48 +367,78 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       float dSsum = 0.f, dSP = 0.f;
       float v0 = 0.f, v1 = 0.f, v2 = 0.f;       // scalars, not an indexed array: the record stays in registers
       int j0 = 0, j1 = 0, j2 = 0, nrec = 0;
-      auto add_entry = [&](int j, float da, float P, float a) {
+      // one non-zero d a[t, j]: the row sums it feeds; returns d P[t, j] (0: nothing to route)
+      auto entry = [&](int j, float da, float P, float a) -> float {
         const float dS = tanh_on ? da * (1.f - a * a) : da;
-        if (dS == 0.f || !(a > -1e29f)) return;        // saturated tanh / masked entry: no gradient
+        if (dS == 0.f || !(a > -1e29f)) return 0.f;     // saturated tanh / masked entry: no gradient
         dSsum += dS;
         dSP = fmaf(dS, P, dSP);
-        const float dP = c1 * dS;
         if (!cosine) atomicAdd(dcol_s + j, dS);
-        if (dP == 0.f) return;
-        if (nrec < 3) {
-          const int pos = atomicAdd(bcnt + j, 1);
-          if (pos < kBtBucketCap) {
-            blist[j * kBtBucketCap + pos] = (uint16_t)(r | (nrec << 8));
-            if (nrec == 0) { v0 = dP; j0 = j; } else if (nrec == 1) { v1 = dP; j1 = j; } else { v2 = dP; j2 = j; }
-            ++nrec;
-            return;
-          }
-        }
-        const int o = atomicAdd(ovcnt_s + p, 1);
-        if (o < kBtOvCap) { ov_s[p * kBtOvCap + o].r = r; ov_s[p * kBtOvCap + o].j = j; ov_s[p * kBtOvCap + o].v = dP; }
-        else __trap();      // more exact ties than any real input produces
+        return c1 * dS;
       };
-      // fast path: a unique row maximum (+ the unique sequence maximum when it sits in this row)
+      // entry `slot` of this row joins the list of column j (the update warps walk the lists)
+      auto push = [&](int slot, int j) {
+        const int e = slot * 128 + r;
+        nxt[e] = (uint16_t)atomicExch(head + j, e);
+      };
+      const bool want_g = in_range && tiesk == 1.f && t == amax_t;    // the unique sequence maximum sits in this row
+      // fast path: a unique row maximum.  Everything else -- exact ties among unsaturated logits, the row
+      // that holds the sequence maximum -- walks the columns once more, one at a time.
       const bool ties_m = in_range && rowcnt > 1 && dm != 0.f && !(tanh_on && fabsf(m) == 1.f);
       // (a saturated sequence maximum, |s_k| == 1 under tanh, has a zero derivative wherever it is attained)
       const bool ties_s = in_range && tiesk > 1.f && m == sk && dsk != 0.f && !(tanh_on && fabsf(sk) == 1.f);
-      const bool slow = ties_m || ties_s;
-      if (in_range && !slow) {
-        if (rowcnt == 1) add_entry(jm, dm_each, Pm, m);
-        if (want_g) add_entry(amax_j, ds_each, Pg, ag);
+      const bool slow = ties_m || ties_s || (want_g && dsk != 0.f);
+      if (in_range && !slow && rowcnt == 1) {
+        v0 = entry(jm, dm_each, Pm, m);
+        if (v0 != 0.f) { j0 = jm; nrec = 1; push(0, jm); }
       }
+      BT_TRACE(3, i, 7);
+#ifdef FVTA_TC_TRACE
+      { const unsigned bm = __ballot_sync(0xffffffffu, slow);
+        if (lane == 0) { atomicAdd(&g_bt_count[0], 1); atomicAdd(&g_bt_count[1], bm != 0); atomicAdd(&g_bt_count[2], __popc(bm)); } }
+#endif
+      bool dense = false;     // more than three entries in this row: its d P vector stays in tensor memory
       if (__any_sync(0xffffffffu, slow)) {
-        // exact ties among unsaturated logits (rare): walk the columns again and route per column
-        logits_pass([&](int j, float a, float P) {
-          if (!slow) return;
-          float da = 0.f;
-          if (a == m) da += dm_each;
-          if (tiesk == 1.f ? (want_g && j == amax_j) : (a == sk)) da += ds_each;
-          if (da != 0.f) add_entry(j, da, P, a);
-        });
+        int ne = 0;
+#pragma unroll 1
+        for (int j = 0; j < kTcJQP; ++j) {
+          __syncwarp();
+          const uint32_t y0 = tmem_ld1(taddr + j), y1 = tmem_ld1(taddr + 32 + j);
+          tmem_ld_wait();
+          float dP = 0.f;
+          if (slow) {
+            const float P = __fadd_rn(__uint_as_float(y0), __uint_as_float(y1));
+            float Sv = __fadd_rn(__fmaf_rn(c1s, P, c0s), col_s[j]);
+            if (tanh_on) Sv = __fmaf_rn(rcp_approx(__fadd_rn(exp2f_approx(Sv), 1.f)), -2.f, 1.f);
+            float a = fminf(Sv, cap_s[j]);
+            if (!mh) a = fminf(cap_s[j], FVTA_VERY_NEGATIVE);
+            float da = 0.f;
+            if (a == m) da += dm_each;
+            if (tiesk == 1.f ? (want_g && j == amax_j) : (a == sk)) da += ds_each;
+            if (da != 0.f) dP = entry(j, da, P, a);
+            if (dP != 0.f) {
+              if (ne == 0) { v0 = dP; j0 = j; } else if (ne == 1) { v1 = dP; j1 = j; } else if (ne == 2) { v2 = dP; j2 = j; }
+              ++ne;
+            }
+          }
+          __syncwarp();
+          tmem_st1(taddr + j, __float_as_uint(dP));     // column j has been read: it now holds d P[t, j]
+        }
+        tmem_st_wait();
+        dense = slow && ne > 3;
+        if (slow && !dense) {
+          nrec = ne;
+          if (ne > 0) push(0, j0);
+          if (ne > 1) push(1, j1);
+          if (ne > 2) push(2, j2);
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&ep_done[p]);
+      const bool dense_w = __any_sync(0xffffffffu, dense);
+      if (!dense_w) {
+        tc_fence_before();
+        mbar_arrive(&ep_done[p]);
+      }
+      BT_TRACE(3, i, 4);
 
       float dlin = 0.f, dquad = 0.f;
       if (cosine) {
@@ -391,23 +457,71 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       // ---- gate backward: d z[t] = (sum_k d g[k,t]) * cnt * (1 - tanh^2 z) ----
       float dz = 0.f;
       if (d.use_time_warp) {
-        dgx_s[p * 128 + r] = in_range ? dg : 0.f;
+        float* dgx = dgx_s + (p * 2 + (use & 1)) * 128;      // two phases: one barrier per tile is enough
+        dgx[r] = in_range ? dg : 0.f;
         named_bar_sync(1 + p, 128);
         float dgt = 0.f;
-        for (int kk = 0; kk < d.K; ++kk) dgt += dgx_s[p * 128 + kk * TB + tt];
+        for (int kk = 0; kk < d.K; ++kk) dgt += dgx[kk * TB + tt];
         dz = in_range ? dgt * cnt * (1.f - tz * tz) : 0.f;
-        if (k == 0 && in_range && dz != 0.f) atomicAdd(dzc_s, dz);
-        named_bar_sync(1 + p, 128);     // dgx is rewritten by this group's next tile
+        if (k == 0) dzc_acc += dz;
       }
       const float hcoef = alpha * g * beta;
-      const uint32_t jbits = (uint32_t)j0 | ((uint32_t)j1 << 8) | ((uint32_t)j2 << 16) | ((uint32_t)nrec << 24);
-      rec_s[(s * 128 + r) * 2] = make_float4(v0, v1, v2, __uint_as_float(jbits));
-      rec_s[(s * 128 + r) * 2 + 1] = make_float4(dlin, dquad, hcoef, dz);
+      if (dense_w) {
+        // (rare: four or more exact ties among the unsaturated logits of one row, e.g. an all-zero context
+        // row.)  The row's thread applies its own gradient, serially: d qeff and the coefficient sums go to
+        // the global accumulators, d h[t, :] is written in place, and the update warps skip the row.
+        float* trow = reinterpret_cast<float*>(ring + (size_t)s * pl.stage_bytes) + rr * D;
+        float* dq_n = dqeffT + (size_t)n * Dp * JQPg;
+        float* dc_n = dcoef + (size_t)n * 3 * Dp;
+#pragma unroll 1
+        for (int j = 0; j < kTcJQP; ++j) {
+          __syncwarp();
+          const float dP = __uint_as_float(tmem_ld1(taddr + j));
+          tmem_ld_wait();
+          if (dense && dP != 0.f && j < JQPg)
+            for (int dd = 0; dd < D; ++dd) atomicAdd(dq_n + (size_t)dd * JQPg + j, dP * trow[dd]);
+        }
+        if (dense) {
+          for (int dd = 0; dd < D; ++dd) {
+            const float hv = trow[dd], hh = hv * hv;
+            float o = fmaf(2.f * hv, fmaf(coef_s[2 * Dp + dd], dquad, coef_s[dd] * dz), hcoef * gvec_s[dd]);
+            if (HAS_LIN) { o = fmaf(coef_s[Dp + dd], dlin, o); atomicAdd(dc_n + Dp + dd, dlin * hv); }
+            trow[dd] = o;
+            atomicAdd(dc_n + dd, dz * hh);
+            atomicAdd(dc_n + 2 * Dp + dd, dquad * hh);
+          }
+        }
+#pragma unroll 1
+        for (int j = 0; j < kTcJQP; ++j) {
+          __syncwarp();
+          const float dP = __uint_as_float(tmem_ld1(taddr + j));
+          tmem_ld_wait();
+          if (dense && dP != 0.f)
+            for (int dd = 0; dd < D; ++dd) {
+              const int d4 = dd >> 2;
+              const uint8_t* ph = b32_s + (d4 >> 3) * 8192 + j * 128 + (((d4 & 7) ^ (j & 7)) << 4) + (dd & 3) * 4;
+              trow[dd] = fmaf(dP, *reinterpret_cast<const float*>(ph) + *reinterpret_cast<const float*>(ph + 4096), trow[dd]);
+            }
+        }
+        __syncwarp();
+        fence_async_smem();       // the row was written through the generic proxy; the TMA store reads it
+        tc_fence_before();
+        mbar_arrive(&ep_done[p]);
+      }
+      const uint32_t jbits = (uint32_t)j0 | ((uint32_t)j1 << 8) | ((uint32_t)j2 << 16) | ((uint32_t)(dense ? 0xff : nrec) << 24);
+      rec[r * 2] = make_float4(v0, v1, v2, __uint_as_float(jbits));
+      rec[r * 2 + 1] = make_float4(dlin, dquad, hcoef, dz);
       mbar_arrive(&rec_ready[s]);
+      BT_TRACE(3, i, 5);
+    }
+    if (d.use_time_warp) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dzc_acc += __shfl_xor_sync(0xffffffffu, dzc_acc, o);
+      if (lane == 0 && dzc_acc != 0.f) atomicAdd(dzc_s, dzc_acc);
     }
   } else {
     // ===== update warps =====
-    reg_dec<kBtRegUpd>();
+    reg_inc<kBtRegUpd>();
     const int u = threadIdx.x - kBwUpd0 * 32;          // 0..255
     // pass A ownership: pairs (column j, float4 group d4), idx = u + 256 q
     float4 accq[4];
@@ -417,106 +531,119 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
     // pass B ownership: float4 group d4 = u % D4, rows u / D4, u / D4 + nph, ...
     const int nph = 256 / D4;
     const bool b_on = u < nph * D4;
-    const int bd4 = u % D4, bph = u / D4;
-    // (the coefficient vectors are re-read from shared memory per row: keeping them in registers next to
-    // the seven float4 accumulators spills at the 72 registers this role gets)
-    float4 du4 = make_float4(0.f, 0.f, 0.f, 0.f), dwl4 = du4, dwq4 = du4;
-    const float* cu_p = coef_s + (b_on ? bd4 * 4 : 0);
-    const float* gv_p = gvec_s + (b_on ? bd4 * 4 : 0);
-    // question operand rows from the tf32 image: q = hi + lo, float4 group d4 of row j
-    const uint32_t qoff = (uint32_t)((bd4 >> 3) * 8192), qunit = (uint32_t)(bd4 & 7);
-    auto qrow4 = [&](int j) -> float4 {
-      const uint8_t* ph = b32_s + qoff + j * 128 + ((qunit ^ (uint32_t)(j & 7)) << 4);
+    const int bd4 = b_on ? u % D4 : 0, bph = u / D4;
+    // (pass B runs on packed pairs -- FFMA2 -- throughout)
+    float2 du01 = make_float2(0.f, 0.f), du23 = du01, dwl01 = du01, dwl23 = du01, dwq01 = du01, dwq23 = du01;
+    float2 cu01, cu23, cq01, cq23, gv01, gv23;       // 2 u, 2 w_quad (the factor of d(h^2) folded in), g_hat
+    {
+      const float4 cu4 = *reinterpret_cast<const float4*>(coef_s + bd4 * 4);
+      const float4 cq4 = *reinterpret_cast<const float4*>(coef_s + 2 * Dp + bd4 * 4);
+      const float4 gv4 = *reinterpret_cast<const float4*>(gvec_s + bd4 * 4);
+      cu01 = make_float2(2.f * cu4.x, 2.f * cu4.y); cu23 = make_float2(2.f * cu4.z, 2.f * cu4.w);
+      cq01 = make_float2(2.f * cq4.x, 2.f * cq4.y); cq23 = make_float2(2.f * cq4.z, 2.f * cq4.w);
+      gv01 = make_float2(gv4.x, gv4.y); gv23 = make_float2(gv4.z, gv4.w);
+    }
+    // question operand rows from the tf32 image (128-byte swizzled rows): q = hi + lo, float4 group d4 of row j
+    const uint8_t* qbase = b32_s + (bd4 >> 3) * 8192 + ((bd4 & 7) << 4);
+    auto q_ptr = [&](uint32_t j) -> const uint8_t* {
+      return reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(qbase + j * 128) ^ (uintptr_t)((j & 7) << 4));
+    };
+    auto add_q = [&](uint32_t j, float v, float2& o01, float2& o23) {
+      const uint8_t* ph = q_ptr(j);
       const float4 hi = *reinterpret_cast<const float4*>(ph);
       const float4 lo = *reinterpret_cast<const float4*>(ph + 4096);
-      return make_float4(hi.x + lo.x, hi.y + lo.y, hi.z + lo.z, hi.w + lo.w);
+      const float2 vv = make_float2(v, v);
+      o01 = __ffma2_rn(vv, __fadd2_rn(make_float2(hi.x, hi.y), make_float2(lo.x, lo.y)), o01);
+      o23 = __ffma2_rn(vv, __fadd2_rn(make_float2(hi.z, hi.w), make_float2(lo.z, lo.w)), o23);
     };
     for (int i = 0; i < ntile; ++i) {
       const int s = i % S, par = i & 1;
+      BT_TRACE(4, i, 0);
       mbar_wait_relaxed(&rec_ready[s], (i / S) & 1);
+      BT_TRACE(4, i, 1);
       float* tile = reinterpret_cast<float*>(ring + (size_t)s * pl.stage_bytes);
-      const float4* rec = rec_s + s * 256;
-      const int* bcnt = bcnt_s + par * 32;
-      const uint16_t* blist = blist_s + par * 32 * kBtBucketCap;
-      const int novf = min(ovcnt_s[par], kBtOvCap);
-      const BtOverflow* ov = ov_s + par * kBtOvCap;
-      // ---- A: d qeff[j, 4 d4 ..] += sum over the rows bucketed under column j of v * h ----
+      const float4* rec = rec_s + par * 256;
+      const int* head = head_s + par * 32;
+      const uint16_t* nxt = next_s + par * 384;
+      // ---- A: d qeff[j, 4 d4 ..] += sum over the entries listed under column j of v * h ----
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int idx = u + 256 * q;
         if (idx < npair) {
           const int j = idx / D4, d4 = idx - j * D4;
-          const int ne = min(bcnt[j], kBtBucketCap);
           float4 a = accq[q];
-          for (int e = 0; e < ne; ++e) {
-            const int ref = blist[j * kBtBucketCap + e];
-            const int rr = ref & 0xff, slot = ref >> 8;
+          for (int e = head[j]; e != kBtEnd; e = nxt[e]) {
+            const int rr = e & 127, slot = e >> 7;
             const float4 ra = rec[rr * 2];
             const float vv = slot == 0 ? ra.x : (slot == 1 ? ra.y : ra.z);
             const float4 h4 = *reinterpret_cast<const float4*>(tile + rr * D + d4 * 4);
             a.x = fmaf(vv, h4.x, a.x); a.y = fmaf(vv, h4.y, a.y); a.z = fmaf(vv, h4.z, a.z); a.w = fmaf(vv, h4.w, a.w);
           }
-          for (int o = 0; o < novf; ++o)
-            if (ov[o].j == j) {
-              const float4 h4 = *reinterpret_cast<const float4*>(tile + ov[o].r * D + d4 * 4);
-              const float vv = ov[o].v;
-              a.x = fmaf(vv, h4.x, a.x); a.y = fmaf(vv, h4.y, a.y); a.z = fmaf(vv, h4.z, a.z); a.w = fmaf(vv, h4.w, a.w);
-            }
           accq[q] = a;
         }
       }
+      BT_TRACE(4, i, 2);
       named_bar_sync(3, 256);           // every reader of h is done: the tile may be overwritten
-      // ---- B: d h in place, coefficient-vector sums ----
+      BT_TRACE(4, i, 3);
+      // ---- B: d h in place, coefficient-vector sums.  Two rows per step: one warp issues a dependent
+      //      instruction every ~5 cycles, so the role is bound by the length of its dependency chains, and
+      //      two independent rows shorten that.  (Measured alternatives, cycles per 96-row tile: one row per
+      //      step with the next row prefetched ~3900; this form 4300; all loads hoisted into two waves 5400;
+      //      sixteen threads per row with two float4 groups each 7300.) ----
       if (b_on) {
-        for (int rr = bph; rr < rows; rr += nph) {
-          const float4 ra = rec[rr * 2], rb = rec[rr * 2 + 1];
+        auto row_math = [&](const float4& ra, const float4& rb, const float4& h4, float* hp, int nrec) {
           const uint32_t jb = __float_as_uint(ra.w);
-          const int nrec = (int)(jb >> 24);
-          float* hp = tile + rr * D + bd4 * 4;
-          const float4 h4 = *reinterpret_cast<const float4*>(hp);
-          const float dlin = rb.x, dquad = rb.y, hcoef = rb.z, dz = rb.w;
-          const float4 hh = make_float4(h4.x * h4.x, h4.y * h4.y, h4.z * h4.z, h4.w * h4.w);
-          const float4 cu4 = *reinterpret_cast<const float4*>(cu_p);
-          const float4 cq4 = *reinterpret_cast<const float4*>(cu_p + 2 * Dp);
-          const float4 gv4 = *reinterpret_cast<const float4*>(gv_p);
-          // d h = 2 h (w_quad dquad + u dz) + g_hat hcoef (+ w_lin dlin)
-          const float4 cc = make_float4(2.f * fmaf(cq4.x, dquad, cu4.x * dz), 2.f * fmaf(cq4.y, dquad, cu4.y * dz),
-                                        2.f * fmaf(cq4.z, dquad, cu4.z * dz), 2.f * fmaf(cq4.w, dquad, cu4.w * dz));
-          float4 o = make_float4(fmaf(h4.x, cc.x, hcoef * gv4.x), fmaf(h4.y, cc.y, hcoef * gv4.y),
-                                 fmaf(h4.z, cc.z, hcoef * gv4.z), fmaf(h4.w, cc.w, hcoef * gv4.w));
+          const bool skip = nrec == 0xff;     // no row here, or its own thread has written it (row warpgroups)
+          const float2 h01 = make_float2(h4.x, h4.y), h23 = make_float2(h4.z, h4.w);
+          const float dzv = skip ? 0.f : rb.w, dqv = skip ? 0.f : rb.y;
+          const float2 dq2 = make_float2(dqv, dqv), dz2 = make_float2(dzv, dzv), hc2 = make_float2(rb.z, rb.z);
+          // d h = 2 h (w_quad dquad + u dz) + g_hat hcoef (+ w_lin dlin) + sum_e v_e qeff[j_e]
+          const float2 cc01 = __ffma2_rn(cq01, dq2, __fmul2_rn(cu01, dz2));
+          const float2 cc23 = __ffma2_rn(cq23, dq2, __fmul2_rn(cu23, dz2));
+          float2 o01 = __ffma2_rn(h01, cc01, __fmul2_rn(hc2, gv01));
+          float2 o23 = __ffma2_rn(h23, cc23, __fmul2_rn(hc2, gv23));
           if (HAS_LIN) {
-            const float4 cl4 = *reinterpret_cast<const float4*>(cu_p + Dp);
-            o.x = fmaf(cl4.x, dlin, o.x); o.y = fmaf(cl4.y, dlin, o.y); o.z = fmaf(cl4.z, dlin, o.z); o.w = fmaf(cl4.w, dlin, o.w);
+            const float4 cl4 = *reinterpret_cast<const float4*>(coef_s + Dp + bd4 * 4);
+            const float dlv = skip ? 0.f : rb.x;
+            const float2 dl2 = make_float2(dlv, dlv);
+            o01 = __ffma2_rn(make_float2(cl4.x, cl4.y), dl2, o01);
+            o23 = __ffma2_rn(make_float2(cl4.z, cl4.w), dl2, o23);
+            dwl01 = __ffma2_rn(dl2, h01, dwl01);
+            dwl23 = __ffma2_rn(dl2, h23, dwl23);
           }
-          if (nrec > 0) {
-            const float4 q0 = qrow4((int)(jb & 0xff));
-            o.x = fmaf(ra.x, q0.x, o.x); o.y = fmaf(ra.x, q0.y, o.y); o.z = fmaf(ra.x, q0.z, o.z); o.w = fmaf(ra.x, q0.w, o.w);
-            if (nrec > 1) {
-              const float4 q1 = qrow4((int)((jb >> 8) & 0xff));
-              o.x = fmaf(ra.y, q1.x, o.x); o.y = fmaf(ra.y, q1.y, o.y); o.z = fmaf(ra.y, q1.z, o.z); o.w = fmaf(ra.y, q1.w, o.w);
-              if (nrec > 2) {
-                const float4 q2 = qrow4((int)((jb >> 16) & 0xff));
-                o.x = fmaf(ra.z, q2.x, o.x); o.y = fmaf(ra.z, q2.y, o.y); o.z = fmaf(ra.z, q2.z, o.z); o.w = fmaf(ra.z, q2.w, o.w);
-              }
-            }
+          add_q(jb & 0x1f, ra.x, o01, o23);              // v0 = 0 (and j0 = 0) when the row has no entry
+          if (nrec > 1 && !skip) {
+            add_q((jb >> 8) & 0x1f, ra.y, o01, o23);
+            add_q((jb >> 16) & 0x1f, ra.z, o01, o23);    // v2 = 0 when there are two
           }
-          for (int oo = 0; oo < novf; ++oo)
-            if (ov[oo].r == rr) {
-              const float4 qx = qrow4(ov[oo].j);
-              const float vv = ov[oo].v;
-              o.x = fmaf(vv, qx.x, o.x); o.y = fmaf(vv, qx.y, o.y); o.z = fmaf(vv, qx.z, o.z); o.w = fmaf(vv, qx.w, o.w);
-            }
-          *reinterpret_cast<float4*>(hp) = o;
-          du4.x = fmaf(dz, hh.x, du4.x); du4.y = fmaf(dz, hh.y, du4.y); du4.z = fmaf(dz, hh.z, du4.z); du4.w = fmaf(dz, hh.w, du4.w);
-          if (HAS_LIN) { dwl4.x = fmaf(dlin, h4.x, dwl4.x); dwl4.y = fmaf(dlin, h4.y, dwl4.y); dwl4.z = fmaf(dlin, h4.z, dwl4.z); dwl4.w = fmaf(dlin, h4.w, dwl4.w); }
-          dwq4.x = fmaf(dquad, hh.x, dwq4.x); dwq4.y = fmaf(dquad, hh.y, dwq4.y); dwq4.z = fmaf(dquad, hh.z, dwq4.z); dwq4.w = fmaf(dquad, hh.w, dwq4.w);
+          if (!skip) *reinterpret_cast<float4*>(hp) = make_float4(o01.x, o01.y, o23.x, o23.y);
+          const float2 hh01 = __fmul2_rn(h01, h01), hh23 = __fmul2_rn(h23, h23);
+          du01 = __ffma2_rn(dz2, hh01, du01);
+          du23 = __ffma2_rn(dz2, hh23, du23);
+          dwq01 = __ffma2_rn(dq2, hh01, dwq01);
+          dwq23 = __ffma2_rn(dq2, hh23, dwq23);
+        };
+        for (int rr = bph; rr < rows; rr += 2 * nph) {
+          float* hp0 = tile + rr * D + bd4 * 4;
+          float* hp1 = hp0 + nph * D;
+          const bool two = rr + nph < rows;
+          const int r1 = two ? rr + nph : rr;
+          const float4 ra0 = rec[rr * 2], rb0 = rec[rr * 2 + 1], h0 = *reinterpret_cast<const float4*>(hp0);
+          const float4 ra1 = rec[r1 * 2], rb1 = rec[r1 * 2 + 1], h1 = *reinterpret_cast<const float4*>(two ? hp1 : hp0);
+          const int n0 = (int)(__float_as_uint(ra0.w) >> 24);
+          const int n1 = two ? (int)(__float_as_uint(ra1.w) >> 24) : 0xff;
+          row_math(ra0, rb0, h0, hp0, n0);
+          row_math(ra1, rb1, h1, hp1, n1);
         }
       }
+      BT_TRACE(4, i, 4);
       fence_async_smem();               // the tile was written through the generic proxy; the TMA store reads it
       named_bar_sync(3, 256);
-      if (u < 32) bcnt_s[par * 32 + u] = 0;
-      if (u == 32) ovcnt_s[par] = 0;
-      if (u < 64) named_bar_sync(4, 64);   // the two warps that reset the bucket state
+      BT_TRACE(4, i, 5);
+      if (u < 32) {
+        head_s[par * 32 + u] = kBtEnd;
+        __syncwarp();
+      }
       if (u == 0) {
         mbar_arrive(&bk_free[par]);
         tma_store_3d(&tmap_out, tile, 0, (tile_begin + i) * TB, n * d.K);
@@ -527,6 +654,7 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
           mbar_arrive(&empty[(i - 1) % S]);
         }
       }
+      BT_TRACE(4, i, 6);
     }
     if (u == 0 && ntile > 0) {
       tma_store_wait_read();
@@ -550,9 +678,9 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
     }
     if (b_on) {
       float* dc = dcoef + (size_t)n * 3 * Dp + bd4 * 4;
-      atomicAdd(dc, du4.x); atomicAdd(dc + 1, du4.y); atomicAdd(dc + 2, du4.z); atomicAdd(dc + 3, du4.w);
-      if (HAS_LIN) { atomicAdd(dc + Dp, dwl4.x); atomicAdd(dc + Dp + 1, dwl4.y); atomicAdd(dc + Dp + 2, dwl4.z); atomicAdd(dc + Dp + 3, dwl4.w); }
-      atomicAdd(dc + 2 * Dp, dwq4.x); atomicAdd(dc + 2 * Dp + 1, dwq4.y); atomicAdd(dc + 2 * Dp + 2, dwq4.z); atomicAdd(dc + 2 * Dp + 3, dwq4.w);
+      atomicAdd(dc, du01.x); atomicAdd(dc + 1, du01.y); atomicAdd(dc + 2, du23.x); atomicAdd(dc + 3, du23.y);
+      if (HAS_LIN) { atomicAdd(dc + Dp, dwl01.x); atomicAdd(dc + Dp + 1, dwl01.y); atomicAdd(dc + Dp + 2, dwl23.x); atomicAdd(dc + Dp + 3, dwl23.y); }
+      atomicAdd(dc + 2 * Dp, dwq01.x); atomicAdd(dc + 2 * Dp + 1, dwq01.y); atomicAdd(dc + 2 * Dp + 2, dwq23.x); atomicAdd(dc + 2 * Dp + 3, dwq23.y);
     }
     if (u == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every tile store has landed
   }
@@ -594,3 +722,15 @@ int attn_bwd_tc_try(const FvtaAttnDesc& d, const AttnLayout& L, const float* hal
 }
 
 }  // namespace fvta
+
+#ifdef FVTA_TC_TRACE
+extern "C" int fvta_bt_iter_read(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, fvta::g_bt_iter, sizeof(long long) * 32);
+}
+extern "C" int fvta_bt_count_read(int* out) {
+  return (int)cudaMemcpyFromSymbol(out, fvta::g_bt_count, sizeof(int) * 8);
+}
+extern "C" int fvta_bt_trace_read(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, fvta::g_bt_trace, sizeof(long long) * 5 * fvta::kBtTraceTiles * 8);
+}
+#endif

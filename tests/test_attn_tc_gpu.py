@@ -256,6 +256,55 @@ def test_tc_backward_vs_oracle_and_ffma(cuda_device, name):
         assert e_ff < 2 * bounds.get(k, BOUND), (k, e_ff)
 
 
+@pytest.mark.parametrize("warp", [False, True], ids=["no-warp", "time-warp"])
+def test_tc_backward_tied_columns(cuda_device, warp):
+    """Six identical question words: their logit columns tie EXACTLY in every context row, so a row whose
+    maximum falls on them has six equal, unsaturated maxima (tf.reduce_max splits the gradient evenly).
+    More than three entries per row is the tensor-core backward's serial path (the row's thread keeps its
+    d P vector in tensor memory and applies the row's gradient itself) -- with small inputs so that the
+    tanh stays away from +-1 and the entries really carry gradient."""
+    N, K, M, JMAX, D, JQ = 2, 6, 4, 32, 100, 25
+    cfg, params, inp = attn_case(N, K, M, JMAX, D, JQ, 2, True, warp, 5, False, density=0.7, q_density=1.0, seed=77)
+    inp["hall"] = inp["hall"] * 0.15
+    inp["hq"] = inp["hq"] * 0.15
+    inp["hq"][:, 1:6] = inp["hq"][:, 0:1]
+    inp["q_mask"][:, :6] = True
+    out, p = _run(cfg, params, inp, cuda_device, want_logits=True)
+    assert out["path"] == _lib.PATH_TC
+    a = out["a_logits"].cpu().reshape(N, K, -1, out["a_logits"].shape[-1])
+    valid = inp["hall_mask"].reshape(N, K, -1)
+    rowmax = a[..., :JQ].max(-1).values
+    tied6 = ((a[..., :6] == rowmax[..., None]).all(-1) & valid & (rowmax.abs() < 1.0))
+    assert tied6.sum().item() >= 10, "the case must contain rows with six tied, unsaturated maxima"
+    g = torch.Generator().manual_seed(11)
+    dg1 = torch.randn(N, D, generator=g)
+    names = ("attention/all/att_logits/W", "attention/all/att_logits/b", "time_warp/WH/W", "time_warp/WH/b",
+             "time_warp/WC/W", "time_warp/WC/b")
+    args = [p.get(k) for k in names]
+    gr = ops.attn_backward(out, dg1.to(cuda_device), *args)
+    gr_ff = ops.attn_backward(out, dg1.to(cuda_device), *args, path=_lib.PATH_FFMA)
+    pp = {k: v.double().clone().requires_grad_(True) for k, v in params.items()}
+    hall = inp["hall"].double().clone().requires_grad_(True)
+    hq = inp["hq"].double().clone().requires_grad_(True)
+    lq = inp["lq"].double().clone().requires_grad_(True)
+    o = collapsed.fvta_attention(hall, inp["hall_mask"], hq, inp["q_mask"], lq, pp, cfg)
+    (o["g1_all"] * dg1.double()).sum().backward()
+    refs = {"d_hall": hall.grad.reshape(N, K, -1, D), "d_hq": hq.grad, "d_lq": lq.grad if warp else None}
+    for key, nme in zip(("d_att_W", "d_att_b", "d_WH_W", "d_WH_b", "d_WC_W", "d_WC_b"), names):
+        refs[key] = pp[nme].grad if nme in pp else None
+    # the five time-warp gradients are sums of d z over every row with heavy cancellation (see
+    # tests/test_attn_gpu.py::TC_CANCELLING_BOUND); with inputs this small the sums are smaller still
+    bounds = {"d_lq": 1.5e-3, "d_WC_W": 1.5e-3, "d_WC_b": 1.5e-3, "d_WH_b": 1.5e-3, "d_WH_W": 1.5e-3}
+    for k, r in refs.items():
+        if r is None or gr.get(k) is None or r.abs().max() == 0:
+            continue
+        e = ((gr[k].double().cpu() - r).abs().max() / r.abs().max()).item()
+        e_ff = ((gr[k].double().cpu() - gr_ff[k].double().cpu()).abs().max() / r.abs().max()).item()
+        print("[tc bwd tied columns] %-8s vs oracle %.2e  vs ffma %.2e" % (k, e, e_ff))
+        assert e < bounds.get(k, BOUND), (k, e)
+        assert e_ff < 2 * bounds.get(k, BOUND), (k, e_ff)
+
+
 def test_folded_workspace_reuse(cuda_device):
     """FvtaAttnDesc.ws_from_fwd on the forward: a second call over a NEW context with the same question
     reuses the folded operands and launches exactly one kernel."""
