@@ -226,26 +226,33 @@ class Model:
         feed["is_train"] = is_train
         return feed
 
-    # tensors the device step consumes besides the packed reader inputs
-    _DEVICE_KEYS = ("q_mask", "y", "existing_emb_mat", "image_emb_mat")
+    def set_resident_tables(self, image_emb_mat=None, existing_emb_mat=None):
+        """Keep the photo-feature table and / or the GloVe matrix on the device for the whole run instead
+        of feeding them with every batch (model_v2.py:468-477 feeds both per step: 5 MB of the C2 step
+        input is the batch's photo rows).  A feed that omits a table uses the resident one; ``pis`` then
+        indexes the resident photo table (pipeline.TokenizedStore.feed(resident_photos=True)), whose rows
+        the image transform reads in place (fvta_gemm_gather).  Same arithmetic, same results."""
+        if not hasattr(self, "resident"):
+            self.resident = {}
+        for k, v in (("image_emb_mat", image_emb_mat), ("existing_emb_mat", existing_emb_mat)):
+            if v is not None:
+                self.resident[k] = torch.as_tensor(v, dtype=torch.float32).to(self.device).contiguous()
+
+    def _table(self, f, name):
+        t = f.get(name)
+        if t is None:
+            t = getattr(self, "resident", {}).get(name)
+        if t is None:
+            raise KeyError("%s is neither fed nor resident (Model.set_resident_tables)" % name)
+        return t
 
     def host_step_input(self, feed):
-        """Everything the device step reads, as ONE pinned host buffer (packing.to_blob): the packed
-        reader inputs, the question mask, the labels and the two embedding tables.  A data loader
-        builds this once per batch (TensorBatch caches it); to_device then issues a single copy."""
-        from .packing import build_pack, to_blob, emb_touch_flags
-        host = {k: (torch.as_tensor(v) if not isinstance(v, torch.Tensor) and hasattr(v, "shape") else v)
-                for k, v in feed.items()}
-        tensors, meta = build_pack(host, self.config, min_text_cap=getattr(self, "pin_text_cap", 0),
-                                   min_img_cap=getattr(self, "pin_img_cap", 0))
-        for k in self._DEVICE_KEYS:
-            if k in host and host[k] is not None:
-                tensors[k] = host[k]
-        if host.get("is_train", False) and self.params.touch_len:
-            tensors["emb_touch"] = emb_touch_flags(host, self.params.touch_rows, self.params.touch_len)
-        blob, index = to_blob(tensors)
-        meta["blob_bytes"] = blob.numel()
-        return {"blob": blob, "index": index, "meta": meta, "host": host}
+        """Everything the device step reads, as ONE pinned host buffer (packing.host_step_input).  A data
+        loader builds this once per batch (TensorBatch caches it; pipeline.BatchLoader builds it on worker
+        processes); to_device then issues a single copy."""
+        from .packing import host_step_input
+        return host_step_input(feed, self.config, getattr(self, "pin_text_cap", 0), getattr(self, "pin_img_cap", 0),
+                               self.params.touch_rows, self.params.touch_len)
 
     def to_device(self, feed, pack=None):
         """Host feed (or a cached host_step_input) -> device step input: one non-blocking copy of
@@ -322,16 +329,16 @@ class Model:
         drop = (lambda t: torch.nn.functional.dropout(t, 1.0 - cfg.keep_prob, True)) \
             if (is_train and cfg.keep_prob < 1.0) else (lambda t: t)
         # embeddings of the valid tokens only (padding never reaches a consumer: dynamic_rnn ignores it)
-        x_text = self._embed_tokens(f["text_tok_ids"], f.get("text_tok_cids"), f["existing_emb_mat"], is_train)
+        x_text = self._embed_tokens(f["text_tok_ids"], f.get("text_tok_cids"), self._table(f, "existing_emb_mat"), is_train)
         if cfg.use_image_trans:                                        # model_v2.py:634-645
             # lookup + linear (+tanh) as one product: the A rows are read in place from the fed table
-            x_img = ops.gather_linear(f["image_emb_mat"], f["img_tok_pidx"],
+            x_img = ops.gather_linear(self._table(f, "image_emb_mat"), f["img_tok_pidx"],
                                       v["emb/image/image_transform/image_trans_linear/W"],
                                       v["emb/image/image_transform/image_trans_linear/b"], cfg.add_tanh,
                                       *self._sink("emb/image/image_transform/image_trans_linear/W",
                                                   "emb/image/image_transform/image_trans_linear/b"))
         else:
-            x_img = ops.embed(f["image_emb_mat"], f["img_tok_pidx"])
+            x_img = ops.embed(self._table(f, "image_emb_mat"), f["img_tok_pidx"])
         # the eight reader call sites (model_v2.py:694-823) + the context tensor (:862-914)
         arena, last_t, last_i = ops.ReaderFn.apply(
             drop(x_text), drop(x_img), f["text_seq_off"], f["text_seq_len"], f["text_seq_out"],

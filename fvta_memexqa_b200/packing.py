@@ -130,6 +130,28 @@ def emb_touch_flags(feed, touch_rows, touch_len):
     return flags
 
 
+# tensors the device step consumes besides the packed reader inputs
+DEVICE_KEYS = ("q_mask", "y", "existing_emb_mat", "image_emb_mat")
+
+
+def host_step_input(feed, config, min_text_cap=0, min_img_cap=0, touch_rows=None, touch_len=0, pin=True):
+    """Everything the device step reads, as ONE host buffer (to_blob): the packed reader inputs, the
+    question mask, the labels, whichever embedding tables are fed and -- in training -- the flags of the
+    embedding rows this batch looks up.  Pure host work with no model state: an input-pipeline worker
+    process runs it (pipeline.BatchLoader); Model.host_step_input is this with the model's settings."""
+    host = {k: (torch.as_tensor(v) if not isinstance(v, torch.Tensor) and hasattr(v, "shape") else v)
+            for k, v in feed.items()}
+    tensors, meta = build_pack(host, config, min_text_cap=min_text_cap, min_img_cap=min_img_cap)
+    for k in DEVICE_KEYS:
+        if k in host and host[k] is not None:
+            tensors[k] = host[k]
+    if host.get("is_train", False) and touch_len:
+        tensors["emb_touch"] = emb_touch_flags(host, touch_rows, touch_len)
+    blob, index = to_blob(tensors, pin=pin)
+    meta["blob_bytes"] = blob.numel()
+    return {"blob": blob, "index": index, "meta": meta, "host": host}
+
+
 def to_blob(tensors, pin=True):
     """Concatenate CPU tensors into ONE (pinned) byte buffer so a step's inputs travel in a single
     host->device copy.  Returns (blob uint8 [nbytes], index: name -> (offset, shape, dtype))."""

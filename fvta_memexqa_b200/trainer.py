@@ -79,6 +79,10 @@ class Trainer:
         lay = tuple(sorted((k, int(o), tuple(shape), str(dtype)) for k, (o, shape, dtype) in index.items()))
         return (m, lay)
 
+    def _resident_key(self):
+        """Device-resident tables (Model.set_resident_tables) are baked into a captured step by address."""
+        return tuple(sorted((k, v.data_ptr(), tuple(v.shape)) for k, v in getattr(self.model, "resident", {}).items()))
+
     def _capture(self, dfeed):
         from . import _lib
         lib = _lib.load()
@@ -88,7 +92,7 @@ class Trainer:
         from .packing import blob_views
         hsi_index = {k: (v.data_ptr() - dfeed["_blob"].data_ptr(), tuple(v.shape), v.dtype)
                      for k, v in dfeed.items() if isinstance(v, torch.Tensor) and k != "_blob"}
-        key = self._graph_key(meta, hsi_index)
+        key = self._graph_key(meta, hsi_index) + (self._resident_key(),)
         while len(self._graphs) >= self.max_graphs:
             self._graphs.popitem(last=False)
         static_blob = dfeed["_blob"].clone()
@@ -166,11 +170,12 @@ class Trainer:
             key = feed.get("_graph_key")
             if key is None:          # cached on the host step input: computed once per batch object
                 key = feed["_graph_key"] = self._graph_key(feed["meta"], feed["index"])
+            key = key + (self._resident_key(),)
         else:
             dfeed = self.model.to_device(feed)
             index = {k: (v.data_ptr() - dfeed["_blob"].data_ptr(), tuple(v.shape), v.dtype)
                      for k, v in dfeed.items() if isinstance(v, torch.Tensor) and k != "_blob"}
-            key = self._graph_key(dfeed["_meta"], index)
+            key = self._graph_key(dfeed["_meta"], index) + (self._resident_key(),)
         entry = self._graphs.get(key)
         if entry is None:
             dfeed = dfeed if dfeed is not None else self.model.to_device(feed)

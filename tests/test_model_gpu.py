@@ -250,3 +250,95 @@ def test_two_gpu_step_equals_one_gpu_step(cuda_device, fused):
     for k, v in got.items():
         ref = model.params.view(k).detach().cpu()
         assert rel_err(v, ref) < 1e-4 or (v - ref).abs().max() < 1e-6, k
+
+
+def test_pipeline_feeds_and_resident_tables(cuda_device):
+    """A raw dataset in the reference's on-disk format through the input routes: the literal get_feed_dict
+    restatement (data.build_feed_dict) and the vectorised store must train to the same losses and
+    weights (same placeholders; the first loss bitwise); so must the store at pinned shapes with per-batch photo tables and the
+    loader (packed by worker processes, photo / GloVe tables resident on the device): same arithmetic,
+    only where the bytes live differs.  (Shrunk and pinned shapes are not compared with each other: the
+    padded sizes enter the model)"""
+    import numpy as np
+    from fvta_memexqa_b200.config import default_config, FVTA_FLAGS
+    from fvta_memexqa_b200.data import Dataset, make_synthetic_raw, add_vocab, update_config, build_feed_dict
+    from fvta_memexqa_b200.pipeline import TokenizedStore, BatchLoader, resident_photo_table
+
+    def setup():
+        cfg = default_config(**dict(FVTA_FLAGS, batch_size=4, is_train=True, image_feat_dim=16, hidden_size=8,
+                                    image_trans_dim=12, seed=3))
+        data, shared = make_synthetic_raw(12, num_albums=9, seed=3, feat_dim=16, emb_dim=100, vocab=60)
+        add_vocab(shared, cfg)
+        ds = Dataset(data, "train", shared=shared)
+        update_config(cfg, [ds])
+        torch.manual_seed(0)
+        model = get_model(cfg)
+        return cfg, ds, model, Trainer(model, cfg)
+
+    order = None
+    results = []
+    for route in ("literal", "store", "store-pinned", "loader"):
+        cfg, ds, model, trainer = setup()
+        store = TokenizedStore(ds, cfg)
+        loader = BatchLoader(store, model, 4, num_steps=3, shuffle=True, seed=5, workers=0 if route != "loader" else 2)
+        tasks = list(loader._tasks())
+        losses = []
+        if route == "loader":
+            model.set_resident_tables(image_emb_mat=resident_photo_table(store, model.device),
+                                      existing_emb_mat=store.existing_emb_mat)
+            loader.pin_caps()
+            for batch in loader:
+                losses.append(trainer.step(None, batch)[0])
+            loader.close()
+        else:
+            for step, idxs, seed, *_ in tasks:
+                rng = np.random.RandomState((seed * 1000003 + step) & 0x7fffffff)
+                if route == "literal":
+                    sub = next(b for i, b in _batches_by_idxs(ds, [idxs]))
+                    feed = build_feed_dict(model, sub, is_train=True, rng=rng)
+                else:
+                    feed = store.feed(idxs, is_train=True, rng=rng, pin_shapes=route == "store-pinned")
+                feed = {k: torch.as_tensor(v) for k, v in feed.items()}
+                losses.append(trainer.step(None, ((), TensorBatch(feed, len(idxs))))[0])
+        results.append((losses, model.params.flat.detach().cpu().clone()))
+    # (not bitwise: the attention backward accumulates with atomics, so two runs of the SAME inputs differ
+    # in the last bits after the first update)
+    for a, b in ((0, 1), (2, 3)):
+        assert results[a][0][0] == results[b][0][0], (results[a][0], results[b][0])     # first loss: forward only
+        for x, y in zip(results[a][0], results[b][0]):
+            assert abs(x - y) <= 1e-5 * abs(x), (results[a][0], results[b][0])
+        assert rel_err(results[a][1], results[b][1]) < 1e-5
+
+
+def _batches_by_idxs(ds, groups):
+    """Dataset.get_batches' batch construction (utils.py:117-198) for explicit index groups."""
+    from collections import defaultdict
+    import numpy as np
+    from fvta_memexqa_b200.data import Dataset
+    feat_dim = len(next(iter(ds.shared["pid2feat"].values())))
+    for idxs in groups:
+        bd = ds.get_by_idxs(idxs)
+        pid2idx = {}
+        for albumIds in bd["aid"]:
+            for a in albumIds:
+                for pid in ds.shared["albums"][a]["photo_ids"]:
+                    pid2idx.setdefault(pid, len(pid2idx))
+        feats = np.zeros((len(pid2idx), feat_dim), dtype="float32")
+        for pid, i in pid2idx.items():
+            feats[i] = ds.shared["pid2feat"][pid]
+        bd["pidx2feat"] = feats
+        cols = defaultdict(list)
+        for albumIds in bd["aid"]:
+            c = defaultdict(list)
+            for a in albumIds:
+                al = ds.shared["albums"][a]
+                for dst, src in (("album_title", "title"), ("album_description", "description"), ("where", "where"),
+                                 ("when", "when"), ("photo_titles", "photo_titles")):
+                    c[dst].append(al[src])
+                    c[dst + "_c"].append(al[src + "_c"])
+                c["photo_idxs"].append([pid2idx[p] for p in al["photo_ids"]])
+                c["photo_ids"].append(al["photo_ids"])
+            for k, v in c.items():
+                cols[k].append(v)
+        bd.update(cols)
+        yield idxs, Dataset(bd, ds.datatype, shared=ds.shared)
