@@ -35,10 +35,12 @@ UNIT = "samples/s"
 PER_GPU_BATCH = 32
 
 
-def workload_config(n_gpus):
-    return {"workload": "C2: FVTA training step (fwd+bwd+Adadelta), README.MD:222-226 flags, "
-                        "batch 32 per GPU, M=4 JI=8 JXP=8 JD=10 JXA=8 JT=4 JG=4 JQ=25 JA=5 W=16, hidden 50, "
-                        "idim 2537, K=6 T=256 D=100",
+def workload_config(n_gpus, strong=False):
+    name = ("C4 (strong scaling): the C2 training step at a FIXED global batch of %d split over the GPUs"
+            % (PER_GPU_BATCH * n_gpus)) if strong else "C2: FVTA training step (fwd+bwd+Adadelta)"
+    return {"workload": name + ", README.MD:222-226 flags, "
+                        "batch %d per GPU, M=4 JI=8 JXP=8 JD=10 JXA=8 JT=4 JG=4 JQ=25 JA=5 W=16, hidden 50, "
+                        "idim 2537, K=6 T=256 D=100" % PER_GPU_BATCH,
             "global_batch": PER_GPU_BATCH * n_gpus, "per_gpu_batch": PER_GPU_BATCH,
             "parallelism": "dp%d" % n_gpus,
             "l2": "flushed between steps (256 MiB memset between the per-step CUDA-event pairs; ms_per_step_incl_l2_flush brackets the whole loop)",
@@ -293,6 +295,15 @@ def attention_roofline(dev, iters=10, with_logits=False):
             "algorithmic_bytes": bytes_alg, "launch_ms": t * 1e3, "peak_source": how}
 
 
+def _traffic(name):
+    """dram bytes per launch of the kernel from its committed ncu --set full capture (profiles/)."""
+    tp = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(tp):
+        with open(tp) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    return None
+
+
 def attention_roofline_bwd(dev, iters=10):
     """Backward of the focal attention at the C3-max shape: fvta_attn_bwd as a whole (accumulator memset,
     per-modality scalars, the tensor-core tile kernel attn_bwd_tc, question / parameter gradient kernels)
@@ -354,7 +365,7 @@ def attention_roofline_bwd(dev, iters=10):
     bytes_alg = 8 * N * K * T * D + N * K * T + 8 * N * JQ * D + N * JQ + 8 * N * D
     peak, how = measured_peaks()
     return {"bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": bytes_alg / t / 1e9 / peak, "traffic": None,
+            "frac": bytes_alg / t / 1e9 / peak, "traffic": _traffic("attn_bwd_traffic.json"),
             "kernel": "fvta_attn_bwd, whole operator (%d launches; the tile kernel is attn_bwd_tc)" % launches,
             "launch_ms": t * 1e3, "launch_ms_min": min(ts) * 1e3, "algorithmic_bytes": bytes_alg,
             "workload": "C3-max: N=4 K=6 T=32768 D=100 JQ=32, mask density 1.0", "peak_source": how}
@@ -465,7 +476,16 @@ def run_own(args):
             pairs.append((e0, e1))
         b1.record()
         sync_all()
-        return sum(a.elapsed_time(b) for a, b in pairs) * 1e-3, b0.elapsed_time(b1) * 1e-3, out
+        per = [a.elapsed_time(b) for a, b in pairs]
+        timed_steps.last = per
+        return sum(per) * 1e-3, b0.elapsed_time(b1) * 1e-3, out
+
+    def spread(per):
+        """min / median / p90 of the per-step times and the mean of each fifth of the run (rank 0)."""
+        q = sorted(per)
+        k = max(1, len(per) // 5)
+        return {"min": q[0], "median": statistics.median(q), "p90": q[int(0.9 * (len(q) - 1))],
+                "block_means": [round(statistics.mean(per[i:i + k]), 4) for i in range(0, k * 5, k) if per[i:i + k]]}
 
     # ---- device-resident leg -------------------------------------------------------------
     for i in range(args.warmup):
@@ -475,6 +495,7 @@ def run_own(args):
     l0 = lib.fvta_launch_count()
     th0 = time.perf_counter()
     t_steps, t_bracket, loss = timed_steps(lambda i: device_step(dfeeds[i % len(dfeeds)]), args.steps)
+    dev_spread = spread(timed_steps.last)
     launches = lib.fvta_launch_count() - l0
     if not args.no_graph:
         launches = trainer.launches_per_step * args.steps   # replayed graph nodes
@@ -497,6 +518,7 @@ def run_own(args):
         trainer.prefetch(batches[0])
     t_steps, t_bracket, res = timed_steps(e2e_step, args.steps)
     loss_val = res[0]
+    e2e_spread = spread(timed_steps.last)
     t_e2e = dp.max_over_ranks(t_steps)
     t_e2e_bracket = dp.max_over_ranks(t_bracket)
     clocks = sampler.stop() if rank == 0 else None
@@ -508,11 +530,13 @@ def run_own(args):
     total = PER_GPU_BATCH * world * args.steps
     line = {"metric": METRIC, "value": total / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * t_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world), "clocks": clocks,
+            "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(world, bool(args.global_batch)), "clocks": clocks,
             "e2e": {"value": total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": 1000.0 * t_e2e / args.steps,
-                    "ms_per_step_incl_l2_flush": 1000.0 * t_e2e_bracket / args.steps},
+                    "ms_per_step_incl_l2_flush": 1000.0 * t_e2e_bracket / args.steps,
+                    "ms_per_step_spread_rank0": e2e_spread},
+            "ms_per_step_spread_rank0": dev_spread,
             "ms_per_step_incl_l2_flush": 1000.0 * t_dev_bracket / args.steps,
             "gpu_launches": int(launches), "final_loss": loss_val}
     # how the step ran (not part of `config`: the workload is the same for both arms)
@@ -641,7 +665,16 @@ def main():
                     help="e2e leg without Trainer.prefetch (the step input is copied in front of each step)")
     ap.add_argument("--nccl", action="store_true",
                     help="data parallel with ncclAllReduce + fvta_adadelta instead of the fused peer-memory kernel (A/B)")
+    ap.add_argument("--global-batch", dest="global_batch", type=int, default=0,
+                    help="strong scaling (SURVEY C4): fix the GLOBAL batch and give each GPU global/N QAs "
+                         "(default: weak scaling, 32 per GPU)")
     args = ap.parse_args()
+    if args.global_batch:
+        global PER_GPU_BATCH
+        n = max(1, args.gpus, int(os.environ.get("WORLD_SIZE", "1")))
+        if args.global_batch % n:
+            raise SystemExit("bench.py: --global-batch must divide by the GPU count")
+        PER_GPU_BATCH = args.global_batch // n
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
     if args.impl == "reference":

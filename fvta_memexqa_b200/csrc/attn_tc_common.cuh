@@ -68,7 +68,11 @@ inline bool tc_plan(const FvtaAttnDesc& d, TcPlan& p, size_t fixed_extra, int st
   p.stage_bytes = round_up(p.rows * d.D * 4, 128);
   p.smem = fixed + (size_t)p.stages * (p.stage_bytes + stage_extra);
   p.tiles = (d.T + p.TB - 1) / p.TB;
-  const int want = (148 + d.N - 1) / d.N;  // one CTA per SM
+#ifdef FVTA_TC_SLABS_CEIL
+  const int want = (148 + d.N - 1) / d.N;
+#else
+  const int want = 148 / d.N;              // one CTA per SM, ONE wave: a second, nearly empty wave costs a whole CTA lifetime
+#endif
   p.slabs = want < 1 ? 1 : (want > p.tiles ? p.tiles : want);
   return true;
 }

@@ -40,17 +40,24 @@ def main():
     ap.add_argument("out")
     ap.add_argument("--traffic")
     ap.add_argument("--algorithmic-bytes", type=int, default=0)
+    ap.add_argument("--all", action="store_true", help="every kernel of the report: the output is a list")
+    ap.add_argument("--kernel", default=None, help="name written into the traffic file")
     a = ap.parse_args()
     txt = subprocess.run(["ncu", "-i", a.rep, "--page", "raw", "--csv"], check=True, capture_output=True,
                          text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
-    names, units, vals = rows[0], rows[1], rows[2]
+    names, units = rows[0], rows[1]
     col = {n: i for i, n in enumerate(names)}
-    out = {"Kernel Name": {"value": vals[col["Kernel Name"]], "unit": ""}}
-    for k in KEEP:
-        if k in col:
-            out[k] = {"value": vals[col[k]], "unit": units[col[k]]}
-    out["source"] = "ncu --set full --clock-control none, %s" % a.rep
+
+    def one(vals):
+        o = {"Kernel Name": {"value": vals[col["Kernel Name"]], "unit": ""}}
+        for k in KEEP:
+            if k in col:
+                o[k] = {"value": vals[col[k]], "unit": units[col[k]]}
+        o["source"] = "ncu --set full --clock-control none, %s" % a.rep
+        return o
+    vals = rows[2]
+    out = [one(v) for v in rows[2:] if len(v) == len(names)] if a.all else one(vals)
     with open(a.out, "w") as f:
         json.dump(out, f, indent=1)
     if a.traffic:
@@ -58,10 +65,10 @@ def main():
             return int(float(vals[col[k]].replace(",", "")) * UNIT[units[col[k]]])
         rd, wr = b("dram__bytes_read.sum"), b("dram__bytes_write.sum")
         with open(a.traffic, "w") as f:
-            json.dump({"kernel": "attn_fwd_tc<false>", "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd,
+            json.dump({"kernel": a.kernel or vals[col["Kernel Name"]][:60], "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd,
                        "dram_bytes_write": wr, "algorithmic_bytes": a.algorithmic_bytes,
                        "source": "ncu --set full, %s (C3-max shape)" % a.rep}, f, indent=1)
-    print(json.dumps(out, indent=1))
+    print(json.dumps(out if not a.all else [o["Kernel Name"]["value"][:70] for o in out], indent=1))
 
 
 if __name__ == "__main__":
