@@ -13,6 +13,8 @@
 //      in rank order (the same order on every rank: bitwise identical weights everywhere, which NCCL's
 //      ring order does not give), scales by 1/W and applies Adadelta to its local replica.
 // One-shot all-reduce: each GPU reads (W-1) x 1.8 MB, ~20 us at 8 GPUs; no second barrier, no all-gather.
+// The W loads of an element are in flight together (see WT below): what bounds the phase is NVLink
+// bandwidth, not W round trips in a row.
 #include "common.cuh"
 #include "adadelta.cuh"
 
@@ -31,8 +33,10 @@ __device__ __forceinline__ float ld_peer1(const float* p) {
   asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+// (relaxed: ONE system-scope fence orders the staging writes before all W flag stores; a release per
+// store would wait for the previous store's NVLink round trip each time)
 __device__ __forceinline__ void st_flag_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_flag_sys(const uint32_t* p) {
   uint32_t v;
@@ -41,12 +45,15 @@ __device__ __forceinline__ uint32_t ld_flag_sys(const uint32_t* p) {
 }
 
 // state: [0] last completed epoch, [1] blocks that finished phase A, [2] blocks that finished phase C
+// WT: the world size when it is 2, 4 or 8 (the peer loads of an element are then issued together -- a loop
+// with a runtime trip count waits for each NVLink round trip, ~2.5 us, before asking for the next), else 0.
+template <int WT>
 __global__ void __launch_bounds__(512, 1) p2p_allreduce_adadelta_kernel(
     int world, int rank, long long n, long long n_tail, const float* __restrict__ grad_local,
     float* const* __restrict__ stage_ptrs, uint32_t* const* __restrict__ flag_ptrs, uint32_t* __restrict__ state,
     float* __restrict__ var, float* __restrict__ accum, float* __restrict__ accum_update,
     const float* __restrict__ mask, const int32_t* __restrict__ touch_index, float lr, float rho, float eps) {
-  __shared__ float touch_s[kP2pMaxTail];
+  __shared__ unsigned touch_s[kP2pMaxTail];      // != 0: some rank looked the row up
   __shared__ const float* stage_s[kP2pMaxWorld];
   const long long total = n + n_tail;                    // both multiples of 4
   const uint32_t epoch = state[0] + 1;
@@ -60,9 +67,13 @@ __global__ void __launch_bounds__(512, 1) p2p_allreduce_adadelta_kernel(
     const float4* src = reinterpret_cast<const float4*>(grad_local);
     for (long long i = tid; i < (total >> 2); i += nthr) dst[i] = src[i];
   }
-  __threadfence_system();
+  for (long long j = threadIdx.x; j < n_tail; j += blockDim.x) touch_s[j] = 0u;
   __syncthreads();
   if (threadIdx.x == 0) {
+    // fences are cumulative: after the barrier, this thread's fence orders the whole block's staging
+    // writes before its counter increment; the last block's system-scope fence then orders every
+    // block's writes before the flag stores
+    __threadfence();
     const uint32_t prev = atomicAdd(&state[1], 1u);
     if (prev == gridDim.x - 1) {                         // every block of this rank has published its slice
       state[1] = 0;
@@ -82,18 +93,35 @@ __global__ void __launch_bounds__(512, 1) p2p_allreduce_adadelta_kernel(
   }
   __syncthreads();
   // ---- C: reduce + update ----
-  for (long long j = threadIdx.x; j < n_tail; j += blockDim.x) {
-    float sacc = 0.f;
-    for (int r = 0; r < world; ++r) sacc += ld_peer1(stage_s[r] + n + j);
-    touch_s[j] = sacc;
+  // the "row was looked up" flags: only > 0 matters, so the W x n_tail loads run in parallel over the
+  // block's threads (one NVLink round trip, not W in a row) and meet in shared memory with an OR
+  {
+    const long long t4 = n_tail >> 2;
+    for (long long idx = threadIdx.x; idx < t4 * world; idx += blockDim.x) {
+      const int r = (int)(idx / t4);
+      const long long j4 = idx - (long long)r * t4;
+      const float4 x = ld_peer4(reinterpret_cast<const float4*>(stage_s[r] + n) + j4);
+      if (x.x > 0.f) atomicOr(&touch_s[4 * j4], 1u);
+      if (x.y > 0.f) atomicOr(&touch_s[4 * j4 + 1], 1u);
+      if (x.z > 0.f) atomicOr(&touch_s[4 * j4 + 2], 1u);
+      if (x.w > 0.f) atomicOr(&touch_s[4 * j4 + 3], 1u);
+    }
   }
   __syncthreads();
   const float gs = 1.f / (float)world;
   for (long long i = tid; i < (n >> 2); i += nthr) {
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; ++r) {
-      const float4 x = ld_peer4(reinterpret_cast<const float4*>(stage_s[r]) + i);
-      g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+    if (WT > 0) {
+      float4 x[WT > 0 ? WT : 1];
+#pragma unroll
+      for (int r = 0; r < WT; ++r) x[r] = ld_peer4(reinterpret_cast<const float4*>(stage_s[r]) + i);
+#pragma unroll
+      for (int r = 0; r < WT; ++r) { g.x += x[r].x; g.y += x[r].y; g.z += x[r].z; g.w += x[r].w; }   // rank order
+    } else {
+      for (int r = 0; r < world; ++r) {
+        const float4 x = ld_peer4(reinterpret_cast<const float4*>(stage_s[r]) + i);
+        g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+      }
     }
     float4 v = reinterpret_cast<float4*>(var)[i];
     float4 a = reinterpret_cast<float4*>(accum)[i];
@@ -101,10 +129,10 @@ __global__ void __launch_bounds__(512, 1) p2p_allreduce_adadelta_kernel(
     float4 m = mask ? reinterpret_cast<const float4*>(mask)[i] : make_float4(1.f, 1.f, 1.f, 1.f);
     if (touch_index != nullptr) {
       const int4 ti = reinterpret_cast<const int4*>(touch_index)[i];
-      if (ti.x >= 0 && !(touch_s[ti.x] > 0.f)) m.x = 0.f;
-      if (ti.y >= 0 && !(touch_s[ti.y] > 0.f)) m.y = 0.f;
-      if (ti.z >= 0 && !(touch_s[ti.z] > 0.f)) m.z = 0.f;
-      if (ti.w >= 0 && !(touch_s[ti.w] > 0.f)) m.w = 0.f;
+      if (ti.x >= 0 && touch_s[ti.x] == 0u) m.x = 0.f;
+      if (ti.y >= 0 && touch_s[ti.y] == 0u) m.y = 0.f;
+      if (ti.z >= 0 && touch_s[ti.z] == 0u) m.z = 0.f;
+      if (ti.w >= 0 && touch_s[ti.w] == 0u) m.w = 0.f;
     }
     adadelta_one(v.x, g.x, a.x, u.x, m.x, lr, rho, eps, gs);
     adadelta_one(v.y, g.y, a.y, u.y, m.y, lr, rho, eps, gs);
@@ -140,8 +168,11 @@ extern "C" int fvta_p2p_allreduce_adadelta(int32_t world, int32_t rank, int64_t 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long want = ((n >> 2) + 511) / 512;
   int blocks = (int)(want < 1 ? 1 : (want > sms ? sms : want));
-  fvta::p2p_allreduce_adadelta_kernel<<<blocks, 512, 0, (cudaStream_t)stream>>>(
-      world, rank, n, n_tail, grad_local, stage_ptrs_dev, flag_ptrs_dev, state, var, accum, accum_update,
-      update_mask, touch_index, lr, rho, eps);
+  auto kern = world == 2   ? fvta::p2p_allreduce_adadelta_kernel<2>
+              : world == 4 ? fvta::p2p_allreduce_adadelta_kernel<4>
+              : world == 8 ? fvta::p2p_allreduce_adadelta_kernel<8>
+                           : fvta::p2p_allreduce_adadelta_kernel<0>;
+  kern<<<blocks, 512, 0, (cudaStream_t)stream>>>(world, rank, n, n_tail, grad_local, stage_ptrs_dev, flag_ptrs_dev, state,
+                                                 var, accum, accum_update, update_mask, touch_index, lr, rho, eps);
   return fvta::check_launch("p2p_allreduce_adadelta_kernel");
 }
