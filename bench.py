@@ -304,7 +304,7 @@ def _traffic(name):
     return None
 
 
-def attention_roofline_bwd(dev, iters=10):
+def attention_roofline_bwd(dev, iters=10, path=None):
     """Backward of the focal attention at the C3-max shape: fvta_attn_bwd as a whole (accumulator memset,
     per-modality scalars, the tensor-core tile kernel attn_bwd_tc, question / parameter gradient kernels)
     against SURVEY 8(d)'s B_bwd = 8 N K T D (hall read, d_hall written) + masks + small."""
@@ -332,7 +332,7 @@ def attention_roofline_bwd(dev, iters=10):
     sinks = [torch.empty_like(a) for a in args]
 
     def call():
-        ops.attn_backward(fwd, dg1, *args, sinks=sinks, d_hall_out=d_hall, d_hq_out=d_hq)
+        ops.attn_backward(fwd, dg1, *args, sinks=sinks, d_hall_out=d_hall, d_hq_out=d_hq, path=path)
     for _ in range(3):
         call()
     torch.cuda.synchronize()
@@ -509,11 +509,12 @@ def run_own(args):
     sync_all()
     def e2e_step(i):
         # the reference-facing call with HOST buffers.  The input of step i+1 starts its host->device
-        # copy on a copy stream before step i is launched (Trainer.prefetch); step i then waits for ITS
-        # copy, issued one step earlier.  One H2D copy per step, all inside the bracketed region.
+        # copy on a copy stream while step i runs (Trainer.prefetch); step i waited for ITS copy,
+        # issued one step earlier.  One H2D copy per step, all inside the bracketed region.
+        loss = trainer.step_async(None, batches[i % len(batches)])
         if not args.no_prefetch and not args.no_graph:
-            trainer.prefetch(batches[(i + 1) % len(batches)])
-        return trainer.step(None, batches[i % len(batches)])
+            trainer.prefetch(batches[(i + 1) % len(batches)])      # runs under step i's kernels
+        return float(loss.detach()), None, None                    # the loss read-back ends the step
     if not args.no_prefetch and not args.no_graph:
         trainer.prefetch(batches[0])
     t_steps, t_bracket, res = timed_steps(e2e_step, args.steps)
@@ -600,11 +601,11 @@ def fresh_batch_leg(args, cfg, model, trainer, timed_steps, sync_all):
     state = {"cur": cur}
 
     def step(i):
-        nxt = next(it)                               # blocks if the workers have fallen behind
-        trainer.prefetch(nxt)
-        out = trainer.step(None, state["cur"])
+        loss = trainer.step_async(None, state["cur"])
+        nxt = next(it)                               # (blocks if the workers have fallen behind)
+        trainer.prefetch(nxt)                        # fetch + host->device copy run under this step's kernels
         state["cur"] = nxt
-        return out
+        return float(loss.detach()), None, None
     h2d = state["cur"][1].step_input(model, True)["blob"].numel()
     w0 = time.perf_counter()
     t_steps, t_bracket, res = timed_steps(step, args.steps)
@@ -620,8 +621,9 @@ def fresh_batch_leg(args, cfg, model, trainer, timed_steps, sync_all):
     sync_all()
 
     def cached_step(i):
+        loss = trainer.step_async(None, fixed[i % 2])
         trainer.prefetch(fixed[(i + 1) % 2])
-        return trainer.step(None, fixed[i % 2])
+        return float(loss.detach()), None, None
     trainer.prefetch(fixed[0])
     t_cached, _, _ = timed_steps(cached_step, args.steps)
     meta = keep["meta"]

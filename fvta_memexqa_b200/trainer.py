@@ -200,9 +200,10 @@ class Trainer:
         self.global_step = self.model.global_step
         return loss
 
-    def step(self, sess, batch, get_summary=False):
-        """trainer.py:30-40.  ``sess`` is accepted for signature parity (the reference asserts
-        a tf.Session; here it is an opaque context and may be None)."""
+    def step_async(self, sess, batch):
+        """Enqueue one training step and return its loss as a DEVICE tensor without waiting for it: the
+        caller fetches and prefetches the next batch while the step runs, then reads the loss
+        (``float(loss)``).  ``step`` is this plus the read-back."""
         batchIdx, batch_data = batch
         feed = self.model.get_feed_dict(batch_data, is_train=True)
         if getattr(self, "_graphs", None) is not None:
@@ -210,4 +211,10 @@ class Trainer:
         else:
             loss = self._device_step(self.model.to_device(feed))
         self.loss = loss
+        return loss
+
+    def step(self, sess, batch, get_summary=False):
+        """trainer.py:30-40.  ``sess`` is accepted for signature parity (the reference asserts
+        a tf.Session; here it is an opaque context and may be None)."""
+        loss = self.step_async(sess, batch)
         return float(loss.detach()), None, None   # (loss, summary, train_op)

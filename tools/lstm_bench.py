@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
-from fvta_memexqa_b200 import ops  # noqa: E402
+from fvta_memexqa_b200 import ops, _lib  # noqa: E402
 
 CASES = [("32 seqs x 25 steps (questions alone)", 32, 25, 25, 25),
          ("32 seqs x 8 steps", 32, 8, 8, 8),
@@ -29,26 +29,27 @@ def main():
         x = torch.randn(B, J, In, generator=g).to(dev)
         lens_d = lens.to(dev)
 
-        def fwd():
-            return ops.bilstm_forward(x, lens_d, kern, bias)
+        for pname, path in (("CUDA cores", _lib.LSTM_FFMA), ("tcgen05   ", _lib.LSTM_TC)):
+            def fwd():
+                return ops.bilstm_forward(x, lens_d, kern, bias, path=path)
 
-        with torch.no_grad():
-            for _ in range(3):
-                fwd()
-            torch.cuda.synchronize()
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
-                for _ in range(10):
+            with torch.no_grad():
+                for _ in range(3):
                     fwd()
-            gr.replay()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(5):
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    for _ in range(10):
+                        fwd()
                 gr.replay()
-            e1.record()
-            torch.cuda.synchronize()
-        print("%-45s fwd %7.1f us (projection GEMM + memset + recurrence)" % (name, e0.elapsed_time(e1) * 1000 / 50))
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    gr.replay()
+                e1.record()
+                torch.cuda.synchronize()
+            print("%-45s %s fwd %7.1f us (projection GEMM + memset + recurrence)" % (name, pname, e0.elapsed_time(e1) * 1000 / 50))
 
 
 if __name__ == "__main__":
