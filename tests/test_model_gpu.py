@@ -255,7 +255,7 @@ def test_two_gpu_step_equals_one_gpu_step(cuda_device, fused):
 def test_pipeline_feeds_and_resident_tables(cuda_device):
     """A raw dataset in the reference's on-disk format through the input routes: the literal get_feed_dict
     restatement (data.build_feed_dict) and the vectorised store must train to the same losses and
-    weights (same placeholders; the first loss bitwise); so must the store at pinned shapes with per-batch photo tables and the
+    weights (same placeholders); so must the store at pinned shapes with per-batch photo tables and the
     loader (packed by worker processes, photo / GloVe tables resident on the device): same arithmetic,
     only where the bytes live differs.  (Shrunk and pinned shapes are not compared with each other: the
     padded sizes enter the model)"""
@@ -301,10 +301,9 @@ def test_pipeline_feeds_and_resident_tables(cuda_device):
                 feed = {k: torch.as_tensor(v) for k, v in feed.items()}
                 losses.append(trainer.step(None, ((), TensorBatch(feed, len(idxs))))[0])
         results.append((losses, model.params.flat.detach().cpu().clone()))
-    # (not bitwise: the attention backward accumulates with atomics, so two runs of the SAME inputs differ
-    # in the last bits after the first update)
+    # (not bitwise: split-K products and the attention backward accumulate with atomics, so two runs of the
+    # SAME inputs differ in the last bits)
     for a, b in ((0, 1), (2, 3)):
-        assert results[a][0][0] == results[b][0][0], (results[a][0], results[b][0])     # first loss: forward only
         for x, y in zip(results[a][0], results[b][0]):
             assert abs(x - y) <= 1e-5 * abs(x), (results[a][0], results[b][0])
         assert rel_err(results[a][1], results[b][1]) < 1e-5
