@@ -28,6 +28,20 @@
 #include "tc_ptx.cuh"
 #include "attn_tc_common.cuh"
 
+#ifndef FVTA_BWD_SPIN
+#define FVTA_BWD_SPIN 0
+#endif
+#if FVTA_BWD_SPIN >= 1
+#define BT_WAIT_HOT(bar, par) mbar_wait(bar, par)
+#else
+#define BT_WAIT_HOT(bar, par) mbar_wait_relaxed(bar, par)
+#endif
+#if FVTA_BWD_SPIN >= 2
+#define BT_WAIT_WARM(bar, par) mbar_wait(bar, par)
+#else
+#define BT_WAIT_WARM(bar, par) mbar_wait_relaxed(bar, par)
+#endif
+
 namespace fvta {
 
 constexpr int kBtThreads = 896;
@@ -181,9 +195,9 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
         const uint32_t acc = tmem_base + (uint32_t)(b2 * 64);
         const uint32_t a_hi = tmem_base + (uint32_t)(pl.col_ahi + b2 * pl.w_ahi);
         const uint32_t a_lo = tmem_base + (uint32_t)(pl.col_alo + b2 * pl.w_alo);
-        mbar_wait_relaxed(&a_ready[b2], (i >> 1) & 1);
+        BT_WAIT_HOT(&a_ready[b2], (i >> 1) & 1);
         BT_TRACE(1, i, 0);
-        if (i >= 2) mbar_wait_relaxed(&ep_done[b2], ((i - 2) >> 1) & 1);
+        if (i >= 2) BT_WAIT_HOT(&ep_done[b2], ((i - 2) >> 1) & 1);
         BT_TRACE(1, i, 1);
         tc_fence_after();
         if (elect_one()) {
@@ -306,7 +320,7 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       // the previous tile of this group must have left the records and entry lists of this parity
       if (use >= 1) mbar_wait_relaxed(&bk_free[p], (use - 1) & 1);
       BT_TRACE(3, i, 2);
-      mbar_wait_relaxed(&acc_full[p], (i >> 1) & 1);
+      BT_WAIT_HOT(&acc_full[p], (i >> 1) & 1);
       tc_fence_after();
       BT_TRACE(3, i, 3);
 
@@ -559,7 +573,7 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
     for (int i = 0; i < ntile; ++i) {
       const int s = i % S, par = i & 1;
       BT_TRACE(4, i, 0);
-      mbar_wait_relaxed(&rec_ready[s], (i / S) & 1);
+      BT_WAIT_WARM(&rec_ready[s], (i / S) & 1);
       BT_TRACE(4, i, 1);
       float* tile = reinterpret_cast<float*>(ring + (size_t)s * pl.stage_bytes);
       const float4* rec = rec_s + par * 256;

@@ -38,6 +38,23 @@
 #include "tc_ptx.cuh"
 #include "attn_tc_common.cuh"
 
+// A/B hook: FVTA_FWD_SPIN = 1 makes the waits on the accumulator loop (split -> MMA -> softmax -> MMA)
+// spin instead of sleeping between polls, 2 the weighted-sum role's too.  Measured at C3-max: no
+// difference (97.5 / 97.8 / 98.4 us) -- the wake-up delay of nanosleep is not what sets the tile period.
+#ifndef FVTA_FWD_SPIN
+#define FVTA_FWD_SPIN 0
+#endif
+#if FVTA_FWD_SPIN >= 1
+#define TC_WAIT_HOT(bar, par) mbar_wait(bar, par)
+#else
+#define TC_WAIT_HOT(bar, par) mbar_wait_relaxed(bar, par)
+#endif
+#if FVTA_FWD_SPIN >= 2
+#define TC_WAIT_WARM(bar, par) mbar_wait(bar, par)
+#else
+#define TC_WAIT_WARM(bar, par) mbar_wait_relaxed(bar, par)
+#endif
+
 namespace fvta {
 
 #ifdef FVTA_TC_TRACE
@@ -195,8 +212,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
         const uint32_t acc = tmem_base + (uint32_t)(b2 * 64);
         const uint32_t a_hi = tmem_base + (uint32_t)(pl.col_ahi + b2 * pl.w_ahi);
         const uint32_t a_lo = tmem_base + (uint32_t)(pl.col_alo + b2 * pl.w_alo);
-        mbar_wait_relaxed(&a_ready[b2], (i >> 1) & 1);
-        if (i >= 2) mbar_wait_relaxed(&ep_done[b2], ((i - 2) >> 1) & 1);   // softmax(i-2) has drained accumulator b2
+        TC_WAIT_HOT(&a_ready[b2], (i >> 1) & 1);
+        if (i >= 2) TC_WAIT_HOT(&ep_done[b2], ((i - 2) >> 1) & 1);   // softmax(i-2) has drained accumulator b2
         TC_TRACE(1, i, 0);
         tc_fence_after();
         if (elect_one()) {
@@ -307,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
       row_coefs(d, g, lin, quad, c1, c0v);
       const float p_c0 = cosine ? 0.f : c0v;
       const float s_scale = tanh_on ? kTanhScale : 1.f;
-      mbar_wait_relaxed(&acc_full[p], (i >> 1) & 1);
+      TC_WAIT_HOT(&acc_full[p], (i >> 1) & 1);
       TC_TRACE(3, i, 1);
       tc_fence_after();
       float a[32];
@@ -421,7 +438,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attn_fwd_tc(
     for (int i = 0; i < (warp - kWarpWsum0 < ws_warps ? ntile : 0); ++i) {      // warps without work skip the pipeline
       const int s = i % S;
       TC_TRACE(4, i, 0);
-      mbar_wait_relaxed(&wg_ready[s], (i / S) & 1);
+      TC_WAIT_WARM(&wg_ready[s], (i / S) & 1);
       TC_TRACE(4, i, 1);
       if (ws_on) {
         const float* hp = reinterpret_cast<const float*>(ring + (size_t)s * pl.stage_bytes) + ws_off;
