@@ -47,7 +47,7 @@ namespace fvta {
 constexpr int kBtThreads = 896;
 // warp 0 TMA, 1 MMA, 2-3 idle, 4-11 update, 12-19 split, 20-27 row warpgroups
 constexpr int kBwTma = 0, kBwMma = 1, kBwUpd0 = 4, kBwSplit0 = 12, kBwRow0 = 20;
-constexpr int kBtRegRow = 96, kBtRegUpd = 64, kBtRegIssue = 40, kBtRegLaunch = 72;   // split keeps the launch value
+constexpr int kBtRegRow = 80, kBtRegUpd = 80, kBtRegIssue = 40, kBtRegLaunch = 72;   // split keeps the launch value
 // setmaxnreg.inc waits until the pool holds the registers: a split that does not fit the file deadlocks
 static_assert(128 * kBtRegIssue + 256 * (kBtRegLaunch + kBtRegRow + kBtRegUpd) <= 65536, "register file");
 static_assert(kBtThreads * kBtRegLaunch <= 65536, "launch registers");
@@ -279,12 +279,6 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
     uint16_t* nxt = next_s + p * 384;
     float4* rec = rec_s + p * 256;
     float dzc_acc = 0.f;
-    // d qeff accumulators of this group: pairs (column j, float4 group d4), idx = r + 128 q, for the whole slab
-    constexpr int kPairQ = DT > 0 ? (kTcJQP * (DT / 4) + 127) / 128 : 8;      // D <= 128: at most 32 * 32 / 128
-    float4 accq[kPairQ];
-#pragma unroll
-    for (int q = 0; q < kPairQ; ++q) accq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int npair = kTcJQP * D4;
     uint8_t mh_next = 1;
     {
       const int t0 = (tile_begin + p) * TB + tt;
@@ -325,8 +319,6 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       const float2 c1c1 = make_float2(c1s, c1s), c0c0 = make_float2(c0s, c0s);
       // the previous tile of this group must have left the records and entry lists of this parity
       if (use >= 1) mbar_wait_relaxed(&bk_free[p], (use - 1) & 1);
-      if (r < 32) head[r] = kBtEnd;                   // this group's lists of its previous tile have been walked
-      named_bar_sync(1 + p, 128);
       BT_TRACE(3, i, 2);
       BT_WAIT_HOT(&acc_full[p], (i >> 1) & 1);
       tc_fence_after();
@@ -414,6 +406,7 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
         v0 = entry(jm, dm_each, Pm, m);
         if (v0 != 0.f) { j0 = jm; nrec = 1; push(0, jm); }
       }
+      BT_TRACE(3, i, 7);
 #ifdef FVTA_TC_TRACE
       { const unsigned bm = __ballot_sync(0xffffffffu, slow);
         if (lane == 0) { atomicAdd(&g_bt_count[0], 1); atomicAdd(&g_bt_count[1], bm != 0); atomicAdd(&g_bt_count[2], __popc(bm)); } }
@@ -532,49 +525,8 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       const uint32_t jbits = (uint32_t)j0 | ((uint32_t)j1 << 8) | ((uint32_t)j2 << 16) | ((uint32_t)(dense ? 0xff : nrec) << 24);
       rec[r * 2] = make_float4(v0, v1, v2, __uint_as_float(jbits));
       rec[r * 2 + 1] = make_float4(dlin, dquad, hcoef, dz);
-      named_bar_sync(1 + p, 128);                     // every record and list entry of the tile is in place
-      BT_TRACE(3, i, 5);
-      // ---- A: d qeff[j, 4 d4 ..] += sum over the entries listed under column j of v * h.  Done here, by
-      //      the group that built the lists (it idles half of the time), so that the update warps -- the
-      //      role that bounds the tile period -- only run pass B. ----
-      {
-        const float* tile = reinterpret_cast<const float*>(ring + (size_t)s * pl.stage_bytes);
-#pragma unroll
-        for (int q = 0; q < kPairQ; ++q) {
-          const int idx = r + 128 * q;
-          if (idx < npair) {
-            const int j = idx / D4, d4 = idx - j * D4;
-            float4 a = accq[q];
-            for (int e = head[j]; e != kBtEnd; e = nxt[e]) {
-              const int er = e & 127, slot = e >> 7;
-              const float4 ra = rec[er * 2];
-              const float vv = slot == 0 ? ra.x : (slot == 1 ? ra.y : ra.z);
-              const float4 h4 = *reinterpret_cast<const float4*>(tile + er * D + d4 * 4);
-              a.x = fmaf(vv, h4.x, a.x); a.y = fmaf(vv, h4.y, a.y); a.z = fmaf(vv, h4.z, a.z); a.w = fmaf(vv, h4.w, a.w);
-            }
-            accq[q] = a;
-          }
-        }
-      }
       mbar_arrive(&rec_ready[s]);
-      BT_TRACE(3, i, 7);
-    }
-    {
-      float* dq_n = dqeffT + (size_t)n * Dp * JQPg;
-#pragma unroll
-      for (int q = 0; q < kPairQ; ++q) {
-        const int idx = r + 128 * q;
-        if (idx < npair) {
-          const int j = idx / D4, d4 = idx - j * D4;
-          if (j < JQPg) {
-            float* dst = dq_n + (size_t)(d4 * 4) * JQPg + j;
-            if (accq[q].x != 0.f) atomicAdd(dst, accq[q].x);
-            if (accq[q].y != 0.f) atomicAdd(dst + JQPg, accq[q].y);
-            if (accq[q].z != 0.f) atomicAdd(dst + 2 * JQPg, accq[q].z);
-            if (accq[q].w != 0.f) atomicAdd(dst + 3 * JQPg, accq[q].w);
-          }
-        }
-      }
+      BT_TRACE(3, i, 5);
     }
     if (d.use_time_warp) {
 #pragma unroll
@@ -583,8 +535,13 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
     }
   } else {
     // ===== update warps =====
-    reg_dec<kBtRegUpd>();
+    reg_inc<kBtRegUpd>();
     const int u = threadIdx.x - kBwUpd0 * 32;          // 0..255
+    // pass A ownership: pairs (column j, float4 group d4), idx = u + 256 q
+    float4 accq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) accq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int npair = kTcJQP * D4;
     // pass B ownership: float4 group d4 = u % D4, rows u / D4, u / D4 + nph, ...
     const int nph = 256 / D4;
     const bool b_on = u < nph * D4;
@@ -620,11 +577,35 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       BT_TRACE(4, i, 1);
       float* tile = reinterpret_cast<float*>(ring + (size_t)s * pl.stage_bytes);
       const float4* rec = rec_s + par * 256;
+      const int* head = head_s + par * 32;
+      const uint16_t* nxt = next_s + par * 384;
+      // ---- A: d qeff[j, 4 d4 ..] += sum over the entries listed under column j of v * h ----
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int idx = u + 256 * q;
+        if (idx < npair) {
+          const int j = idx / D4, d4 = idx - j * D4;
+          float4 a = accq[q];
+          for (int e = head[j]; e != kBtEnd; e = nxt[e]) {
+            const int rr = e & 127, slot = e >> 7;
+            const float4 ra = rec[rr * 2];
+            const float vv = slot == 0 ? ra.x : (slot == 1 ? ra.y : ra.z);
+            const float4 h4 = *reinterpret_cast<const float4*>(tile + rr * D + d4 * 4);
+            a.x = fmaf(vv, h4.x, a.x); a.y = fmaf(vv, h4.y, a.y); a.z = fmaf(vv, h4.z, a.z); a.w = fmaf(vv, h4.w, a.w);
+          }
+          accq[q] = a;
+        }
+      }
+      BT_TRACE(4, i, 2);
+      named_bar_sync(3, 256);           // every reader of h is done: the tile may be overwritten
+      BT_TRACE(4, i, 3);
       // ---- B: d h in place, coefficient-vector sums.  Two rows per step: one warp issues a dependent
       //      instruction every ~5 cycles, so the role is bound by the length of its dependency chains, and
       //      two independent rows shorten that.  (Measured alternatives, cycles per 96-row tile: one row per
       //      step with the next row prefetched ~3900; this form 4300; all loads hoisted into two waves 5400;
-      //      sixteen threads per row with two float4 groups each 7300.) ----
+      //      sixteen threads per row with two float4 groups each 7300.  Moving pass A into the row warpgroups
+      //      -- they idle half of the time -- made the whole operator 407 us instead of 299: seven more float4
+      //      accumulators do not fit next to the row pass at 96 registers and the spills land in both loops.) ----
       if (b_on) {
         auto row_math = [&](const float4& ra, const float4& rb, const float4& h4, float* hp, int nrec) {
           const uint32_t jb = __float_as_uint(ra.w);
@@ -675,6 +656,10 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       fence_async_smem();               // the tile was written through the generic proxy; the TMA store reads it
       named_bar_sync(3, 256);
       BT_TRACE(4, i, 5);
+      if (u < 32) {
+        head_s[par * 32 + u] = kBtEnd;
+        __syncwarp();
+      }
       if (u == 0) {
         mbar_arrive(&bk_free[par]);
         tma_store_3d(&tmap_out, tile, 0, (tile_begin + i) * TB, n * d.K);
@@ -692,6 +677,21 @@ __global__ void __launch_bounds__(kBtThreads, 1) attn_bwd_tc(
       mbar_arrive(&empty[(ntile - 1) % S]);
     }
     // ---- slab sums -> global accumulators ----
+    float* dq_n = dqeffT + (size_t)n * Dp * JQPg;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = u + 256 * q;
+      if (idx < npair) {
+        const int j = idx / D4, d4 = idx - j * D4;
+        if (j < JQPg) {
+          float* dst = dq_n + (size_t)(d4 * 4) * JQPg + j;
+          if (accq[q].x != 0.f) atomicAdd(dst, accq[q].x);
+          if (accq[q].y != 0.f) atomicAdd(dst + JQPg, accq[q].y);
+          if (accq[q].z != 0.f) atomicAdd(dst + 2 * JQPg, accq[q].z);
+          if (accq[q].w != 0.f) atomicAdd(dst + 3 * JQPg, accq[q].w);
+        }
+      }
+    }
     if (b_on) {
       float* dc = dcoef + (size_t)n * 3 * Dp + bd4 * 4;
       atomicAdd(dc, du01.x); atomicAdd(dc + 1, du01.y); atomicAdd(dc + 2, du23.x); atomicAdd(dc + 3, du23.y);
