@@ -507,14 +507,24 @@ def run_own(args):
     for i in range(max(1, args.warmup // 2)):
         trainer.step(None, batches[i % len(batches)])
     sync_all()
+    pending = {}
+
     def e2e_step(i):
         # the reference-facing call with HOST buffers.  The input of step i+1 starts its host->device
         # copy on a copy stream while step i runs (Trainer.prefetch); step i waited for ITS copy,
-        # issued one step earlier.  One H2D copy per step, all inside the bracketed region.
-        loss = trainer.step_async(None, batches[i % len(batches)])
+        # issued one step earlier.  The loss of every step is copied back to pinned host memory right
+        # behind the step (Trainer.step_handle) and READ one step later, so the device does not idle
+        # while the interpreter enqueues the next step.  One H2D copy and one D2H read per step, all
+        # inside the bracketed region (the last read happens before the closing synchronisation).
+        h = trainer.step_handle(None, batches[i % len(batches)])
         if not args.no_prefetch and not args.no_graph:
             trainer.prefetch(batches[(i + 1) % len(batches)])      # runs under step i's kernels
-        return float(loss.detach()), None, None                    # the loss read-back ends the step
+        prev = pending.pop("h", None)
+        pending["h"] = h
+        out = (prev.result() if prev is not None else float("nan")), None, None
+        if i == args.steps - 1:
+            out = (pending.pop("h").result(), None, None)          # the final step's loss
+        return out
     if not args.no_prefetch and not args.no_graph:
         trainer.prefetch(batches[0])
     t_steps, t_bracket, res = timed_steps(e2e_step, args.steps)
@@ -601,11 +611,16 @@ def fresh_batch_leg(args, cfg, model, trainer, timed_steps, sync_all):
     state = {"cur": cur}
 
     def step(i):
-        loss = trainer.step_async(None, state["cur"])
+        h = trainer.step_handle(None, state["cur"])
         nxt = next(it)                               # (blocks if the workers have fallen behind)
         trainer.prefetch(nxt)                        # fetch + host->device copy run under this step's kernels
         state["cur"] = nxt
-        return float(loss.detach()), None, None
+        prev = state.pop("h", None)
+        state["h"] = h
+        out = (prev.result() if prev is not None else float("nan")), None, None     # loss read one step late
+        if i == args.steps - 1:
+            out = (state.pop("h").result(), None, None)
+        return out
     h2d = state["cur"][1].step_input(model, True)["blob"].numel()
     w0 = time.perf_counter()
     t_steps, t_bracket, res = timed_steps(step, args.steps)
@@ -621,9 +636,14 @@ def fresh_batch_leg(args, cfg, model, trainer, timed_steps, sync_all):
     sync_all()
 
     def cached_step(i):
-        loss = trainer.step_async(None, fixed[i % 2])
+        h = trainer.step_handle(None, fixed[i % 2])
         trainer.prefetch(fixed[(i + 1) % 2])
-        return float(loss.detach()), None, None
+        prev = state.pop("hc", None)
+        state["hc"] = h
+        out = (prev.result() if prev is not None else float("nan")), None, None
+        if i == args.steps - 1:
+            out = (state.pop("hc").result(), None, None)
+        return out
     trainer.prefetch(fixed[0])
     t_cached, _, _ = timed_steps(cached_step, args.steps)
     meta = keep["meta"]

@@ -95,6 +95,8 @@ class DataParallel:
         return 1.0 / self.world_size
 
     def mean_loss(self, loss):
+        """The loss a rank reports is its LOCAL batch mean (no collective on the step's critical path for a
+        number that is only logged); `global_mean` all-reduces it when a caller wants the global one."""
         return loss
 
     def global_mean(self, t):
@@ -114,9 +116,14 @@ class DataParallel:
             meta = model.get_feed_dict(b, is_train=True)["meta"]
             caps = [max(caps[0], meta["text_cap"]), max(caps[1], meta["img_cap"])]
         if self.world_size > 1:
-            t = torch.tensor(caps, dtype=torch.int64, device=self.device if self.device is not None else "cpu")
+            n = int(model.config.batch_size)
+            t = torch.tensor(caps + [n, -n], dtype=torch.int64, device=self.device if self.device is not None else "cpu")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            caps = [int(v) for v in t.tolist()]
+            caps = [int(v) for v in t.tolist()[:2]]
+            # the gradient average is sum / world: right only when every rank's loss is a mean over the same N
+            # (the static config.batch_size -- padded rows count in the mean, model_v2.py:1103)
+            if int(t[2]) != -int(t[3]):
+                raise ValueError("data parallel: every rank must use the same config.batch_size")
         model.pin_text_cap, model.pin_img_cap = caps
         return caps
 

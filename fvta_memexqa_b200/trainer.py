@@ -13,6 +13,18 @@ import torch
 from . import ops
 
 
+class StepHandle:
+    """The loss of an enqueued step: its device->host copy was issued right behind the step; ``result()``
+    waits for that copy only (not for whatever was enqueued after it)."""
+
+    def __init__(self, host, slot, event):
+        self._host, self._slot, self._event = host, slot, event
+
+    def result(self):
+        self._event.synchronize()
+        return float(self._host[self._slot])
+
+
 class Trainer:
     def __init__(self, model, config, dp=None):
         self.config = config
@@ -212,6 +224,21 @@ class Trainer:
             loss = self._device_step(self.model.to_device(feed))
         self.loss = loss
         return loss
+
+    def step_handle(self, sess, batch):
+        """``step_async`` plus an asynchronous read-back of the loss into pinned host memory: the training
+        loop can enqueue step i+1 before it looks at the loss of step i, so the device never waits for the
+        interpreter between steps.  Returns a StepHandle; up to four may be outstanding."""
+        loss = self.step_async(sess, batch)
+        if getattr(self, "_loss_host", None) is None:
+            self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+            self._loss_slot = 0
+        k = self._loss_slot
+        self._loss_slot = (k + 1) % 4
+        self._loss_host[k:k + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return StepHandle(self._loss_host, k, ev)
 
     def step(self, sess, batch, get_summary=False):
         """trainer.py:30-40.  ``sess`` is accepted for signature parity (the reference asserts

@@ -341,3 +341,26 @@ def _batches_by_idxs(ds, groups):
                 cols[k].append(v)
         bd.update(cols)
         yield idxs, Dataset(bd, ds.datatype, shared=ds.shared)
+
+
+def test_step_handle_reads_the_same_losses(cuda_device):
+    """Trainer.step_handle (loss copied back behind the step, read later) vs Trainer.step, with and without
+    the CUDA graph: same losses (1e-5: the step accumulates with atomics)."""
+    cfg = tiny_config()
+    feed = make_feed(cfg, seed=5, glove_vocab=10)
+    batch = ((), TensorBatch(feed, cfg.batch_size))
+    losses = {}
+    for mode in ("step", "handle", "handle+graph"):
+        torch.manual_seed(0)
+        trainer = Trainer(get_model(cfg), cfg)
+        if mode.endswith("graph"):
+            trainer.enable_graph()
+        if mode == "step":
+            losses[mode] = [trainer.step(None, batch)[0] for _ in range(4)]
+        else:
+            hs = [trainer.step_handle(None, batch) for _ in range(4)]     # four outstanding
+            losses[mode] = [h.result() for h in hs]
+    for mode in ("handle", "handle+graph"):
+        for a, b in zip(losses["step"], losses[mode]):
+            assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (mode, losses)
+    assert losses["step"][0] != losses["step"][3]          # the weights moved
