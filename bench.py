@@ -407,7 +407,7 @@ def run_own(args):
     import torch
     # a wedged collective must not hold N GPUs until someone else's timeout: give up after 5 min
     signal.signal(signal.SIGALRM, lambda *_: os._exit(17))
-    signal.alarm(300)
+    signal.alarm(300 if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 900)
     from fvta_memexqa_b200 import _lib
     from fvta_memexqa_b200.config import fvta_config
     from fvta_memexqa_b200.data import SyntheticDataset
@@ -533,7 +533,13 @@ def run_own(args):
     t_e2e = dp.max_over_ranks(t_steps)
     t_e2e_bracket = dp.max_over_ranks(t_bracket)
     clocks = sampler.stop() if rank == 0 else None
-    fresh = fresh_batch_leg(args, cfg, model, trainer, timed_steps, sync_all) if (world == 1 and not args.no_graph) else None
+    fresh = None
+    if world == 1 and not args.no_graph:
+        try:
+            fresh = fresh_batch_leg(args, cfg, model, trainer, timed_steps, sync_all)
+        except Exception as e:       # (worker processes / shared memory unavailable: the other legs stand)
+            fresh = {"error": "%s: %s" % (type(e).__name__, e)}
+            getattr(model, "resident", {}).clear()
 
     if rank != 0:
         _shutdown_dist(world)
