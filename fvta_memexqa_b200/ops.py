@@ -469,7 +469,19 @@ class FvtaAttentionFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------
 # packed reader: every text call site in one launch, outputs written in place into the arena
 # ---------------------------------------------------------------------------------------------
-def _reader_call(lib, x_tok, off, lens, outrow, kernel, bias, arena, Jmax):
+_READER_SIDE = {}
+
+
+def _reader_side_stream(device):
+    """The stream the image reader runs on, next to the text reader (one per device, created once --
+    before any CUDA-graph capture, by the warm-up steps)."""
+    key = torch.device(device).index
+    if key not in _READER_SIDE:
+        _READER_SIDE[key] = torch.cuda.Stream(device=device)
+    return _READER_SIDE[key]
+
+
+def _reader_alloc(lib, x_tok, lens, kernel, Jmax):
     from ._lib import FvtaReaderDesc
     f32 = torch.float32
     d = kernel.shape[1] // 4
@@ -479,10 +491,14 @@ def _reader_call(lib, x_tok, off, lens, outrow, kernel, bias, arena, Jmax):
     reserve = torch.empty(lib.fvta_reader_reserve_floats(ctypes.byref(desc)), dtype=f32, device=dev)
     ws_bytes = lib.fvta_reader_workspace_bytes(ctypes.byref(desc))
     ws = torch.empty(ws_bytes // 4, dtype=f32, device=dev)
+    return desc, last, reserve, ws, ws_bytes
+
+
+def _reader_launch(lib, bufs, x_tok, off, lens, outrow, kernel, bias, arena):
+    desc, last, reserve, ws, ws_bytes = bufs
     rc = lib.fvta_reader_fwd(ctypes.byref(desc), _ptr(x_tok), _ptr(off), _ptr(lens), _ptr(outrow), _ptr(kernel),
                              _ptr(bias), _ptr(arena), _ptr(last), _ptr(reserve), _ptr(ws), ws_bytes, _stream())
     check(rc, "fvta_reader_fwd")
-    return last, reserve, desc
 
 
 class ReaderFn(torch.autograd.Function):
@@ -499,8 +515,19 @@ class ReaderFn(torch.autograd.Function):
         kt, bt, ki, bi = (_req(v, f32, "reader weights") for v in (kt, bt, ki, bi))
         d = kt.shape[1] // 4
         arena = torch.zeros(arena_rows, 2 * d, dtype=f32, device=x_text.device)
-        last_t, res_t, desc_t = _reader_call(lib, x_text, t_off, t_len, t_out, kt, bt, arena, Jmax_t)
-        last_i, res_i, desc_i = _reader_call(lib, x_img, i_off, i_len, i_out, ki, bi, arena, Jmax_i)
+        # The two readers are independent (different cells, different arena rows) and both latency-bound
+        # -- a recurrence is ~2 us per step on a handful of CTAs -- so the image reader runs on a second
+        # stream under the text reader (inside a captured step: a parallel branch of the graph).  Every
+        # buffer is allocated on the calling stream, which waits for the side stream before returning.
+        bt_ = _reader_alloc(lib, x_text, t_len, kt, Jmax_t)
+        bi_ = _reader_alloc(lib, x_img, i_len, ki, Jmax_i)
+        main, side = torch.cuda.current_stream(), _reader_side_stream(x_text.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _reader_launch(lib, bi_, x_img, i_off, i_len, i_out, ki, bi, arena)
+        _reader_launch(lib, bt_, x_text, t_off, t_len, t_out, kt, bt, arena)
+        main.wait_stream(side)
+        (desc_t, last_t, res_t), (desc_i, last_i, res_i) = bt_[:3], bi_[:3]
         ctx.save_for_backward(x_text, x_img, t_off, t_len, t_out, i_off, i_len, i_out, kt, ki, res_t, res_i)
         ctx.descs = (desc_t, desc_i)
         ctx.sinks = sinks       # (g kernel_t, g bias_t, g kernel_i, g bias_i) views of the flat gradient
@@ -516,6 +543,8 @@ class ReaderFn(torch.autograd.Function):
         d_arena = _req(d_arena, f32, "d_arena") if d_arena is not None else None
         outs = []
         sinks = ctx.sinks
+        main, side = torch.cuda.current_stream(), _reader_side_stream(x_text.device)
+        calls = []
         for j, (x, off, ln, orow, k, res, desc, dl) in enumerate(
                 ((x_text, t_off, t_len, t_out, kt, res_t, desc_t, d_last_t),
                  (x_img, i_off, i_len, i_out, ki, res_i, desc_i, d_last_i))):
@@ -528,11 +557,21 @@ class ReaderFn(torch.autograd.Function):
             dl = _req(dl, f32, "d_last") if dl is not None else None
             ws_bytes = lib.fvta_reader_workspace_bytes(ctypes.byref(desc))
             ws = torch.empty(ws_bytes // 4, dtype=f32, device=x.device)
+            calls.append((desc, x, off, ln, orow, k, res, dl, dx, dk, db, ws, ws_bytes))
+            outs.append((dx, dk, db))
+
+        def launch(c):
+            desc, x, off, ln, orow, k, res, dl, dx, dk, db, ws, ws_bytes = c
             rc = lib.fvta_reader_bwd(ctypes.byref(desc), _ptr(x), _ptr(off), _ptr(ln), _ptr(orow), _ptr(k), _ptr(res),
                                      _ptr(d_arena), _ptr(dl), _ptr(dx), _ptr(dk), _ptr(db), _ptr(ws), ws_bytes,
                                      _stream())
             check(rc, "fvta_reader_bwd")
-            outs.append((dx, dk, db))
+        # image reader backward on the side stream, text reader backward on the calling one (see forward)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            launch(calls[1])
+        launch(calls[0])
+        main.wait_stream(side)
         (dxt, dkt, dbt), (dxi, dki, dbi) = outs
         if not ctx.needs_input_grad[1]:
             dxi = None
