@@ -329,19 +329,29 @@ class Model:
         drop = (lambda t: torch.nn.functional.dropout(t, 1.0 - cfg.keep_prob, True)) \
             if (is_train and cfg.keep_prob < 1.0) else (lambda t: t)
         # embeddings of the valid tokens only (padding never reaches a consumer: dynamic_rnn ignores it)
-        x_text = self._embed_tokens(f["text_tok_ids"], f.get("text_tok_cids"), self._table(f, "existing_emb_mat"), is_train)
-        if cfg.use_image_trans:                                        # model_v2.py:634-645
-            # lookup + linear (+tanh) as one product: the A rows are read in place from the fed table
-            x_img = ops.gather_linear(self._table(f, "image_emb_mat"), f["img_tok_pidx"],
-                                      v["emb/image/image_transform/image_trans_linear/W"],
-                                      v["emb/image/image_transform/image_trans_linear/b"], cfg.add_tanh,
-                                      *self._sink("emb/image/image_transform/image_trans_linear/W",
-                                                  "emb/image/image_transform/image_trans_linear/b"))
-        else:
-            x_img = ops.embed(self._table(f, "image_emb_mat"), f["img_tok_pidx"])
+        # The image side (lookup + transform) and the text side (char-CNN + word vectors) meet only in the
+        # reader: the image side is enqueued on the reader's second stream (ops.ReaderFn runs the image
+        # reader there too), so inside a captured step the two are parallel branches.  Autograd replays
+        # each op's backward on the stream its forward ran on, which parallelises the backward the same way.
+        main = torch.cuda.current_stream()
+        side = ops._reader_side_stream(self.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if cfg.use_image_trans:                                    # model_v2.py:634-645
+                # lookup + linear (+tanh) as one product: the A rows are read in place from the fed table
+                x_img = ops.gather_linear(self._table(f, "image_emb_mat"), f["img_tok_pidx"],
+                                          v["emb/image/image_transform/image_trans_linear/W"],
+                                          v["emb/image/image_transform/image_trans_linear/b"], cfg.add_tanh,
+                                          *self._sink("emb/image/image_transform/image_trans_linear/W",
+                                                      "emb/image/image_transform/image_trans_linear/b"))
+            else:
+                x_img = ops.embed(self._table(f, "image_emb_mat"), f["img_tok_pidx"])
+            x_img = drop(x_img)
+        x_text = drop(self._embed_tokens(f["text_tok_ids"], f.get("text_tok_cids"), self._table(f, "existing_emb_mat"), is_train))
+        main.wait_stream(side)
         # the eight reader call sites (model_v2.py:694-823) + the context tensor (:862-914)
         arena, last_t, last_i = ops.ReaderFn.apply(
-            drop(x_text), drop(x_img), f["text_seq_off"], f["text_seq_len"], f["text_seq_out"],
+            x_text, x_img, f["text_seq_off"], f["text_seq_len"], f["text_seq_out"],
             f["img_seq_off"], f["img_seq_len"], f["img_seq_out"],
             v["reader/text/utext/fw/basic_lstm_cell/kernel"], v["reader/text/utext/fw/basic_lstm_cell/bias"],
             v["reader/image/uimage/fw/basic_lstm_cell/kernel"], v["reader/image/uimage/fw/basic_lstm_cell/bias"],

@@ -46,6 +46,9 @@ class Trainer:
             ps.touch.copy_(dfeed["emb_touch"])
         loss, _, _ = m.forward(dfeed, is_train=True)
         loss.backward()
+        # the image side of the model runs on a second stream, forward and backward (Model.forward); its
+        # gradients land in the flat buffer through sinks, which autograd does not wait for: join here
+        torch.cuda.current_stream().wait_stream(ops._reader_side_stream(m.device))
         loss = loss.detach()
         m.release_graph()
         scale = 1.0
