@@ -596,6 +596,43 @@ static int lstm_fwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x
 }
 
 //   workspace: d gates [2][ntok][4d]
+__global__ void add_out4(size_t n4, float4* __restrict__ out, const float4* __restrict__ a, const float4* __restrict__ b) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const float4 x = a[i], y = b[i];
+    out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  }
+}
+
+// The three weight/input products of the backward (d kernel[In:], d x, d kernel[:In]) are independent once
+// the recurrence has produced the gate gradients; each fills a fraction of the 148 SMs for 15-25 us.  They
+// run as a fork/join over two auxiliary streams (created once per device, non-blocking; events carry the
+// dependencies, so inside a captured step they become parallel branches of the graph).  Two pairs alternate
+// between calls so that the text and the image reader, which the caller may run on different streams, do
+// not queue behind each other.  The only state the library keeps.
+struct LstmAux {
+  cudaStream_t s[4];
+  cudaEvent_t e[8];
+  int next;
+  int state;      // 0 = not tried, 1 = ready, -1 = unavailable (serial path)
+};
+static LstmAux g_lstm_aux[32];
+
+static LstmAux* lstm_aux() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+  LstmAux& a = g_lstm_aux[dev];
+  if (a.state == 0) {
+    a.state = 1;
+    for (int i = 0; i < 4 && a.state == 1; ++i)
+      if (cudaStreamCreateWithFlags(&a.s[i], cudaStreamNonBlocking) != cudaSuccess) a.state = -1;
+    for (int i = 0; i < 8 && a.state == 1; ++i)
+      if (cudaEventCreateWithFlags(&a.e[i], cudaEventDisableTiming) != cudaSuccess) a.state = -1;
+    if (a.state != 1) cudaGetLastError();
+  }
+  return a.state == 1 ? &a : nullptr;
+}
+
 static int lstm_bwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x, const int32_t* lens,
                          const float* kernel_fw, const float* kernel_bw, const float* reserve, const float* d_out,
                          const float* d_last, float* d_x, float* d_kernel_fw, float* d_bias_fw,
@@ -633,21 +670,60 @@ static int lstm_bwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x
     //   d_x = (dg_fw + dg_bw) @ Wx^T,   d kernel[:In] += x^T @ (dg_fw + dg_bw),
     // and h_prev / dg of the two directions are contiguous in memory, so
     //   d kernel[In:] += [h_prev_fw ; h_prev_bw]^T @ [dg_fw ; dg_bw]   is one product with K = 2*ntok.
-    rc = fvta_gemm(L.d, G, 2 * NT, reserve + 5 * L.d, kResW * L.d, 1, dg, G, 0, nullptr, 0,
-                   d_kernel_fw + (size_t)L.In * G, G, 1, stream);
-    if (rc) return rc;
-    const size_t n4 = ((size_t)NT * G) / 4;   // G = 4d: always a multiple of 4
-    add_inplace4<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, reinterpret_cast<float4*>(dg),
-                                                               reinterpret_cast<const float4*>(dgs[1]));
-    rc = check_launch("add_inplace4");
-    if (rc) return rc;
-    rc = fvta_gemm(NT, L.In, G, dg, G, 0, kernel_fw, G, 1, nullptr, 0, d_x, L.In, 0, stream);
-    if (rc) return rc;
-    rc = fvta_gemm(L.In, G, NT, x, L.In, 1, dg, G, 0, nullptr, 0, d_kernel_fw, G, 1, stream);
-    if (rc) return rc;
+    float* dsum = dg + (size_t)2 * NT * G;          // dg_fw + dg_bw (third slice of the workspace)
+    const size_t n4 = ((size_t)NT * G) / 4;         // G = 4d: always a multiple of 4
     dim3 cg((G + 31) / 32, 64);
-    colsum_accumulate<<<cg, 256, 0, st>>>(NT, G, dg, G, d_bias_fw);
-    return check_launch("colsum_accumulate");
+    LstmAux* ax = lstm_aux();
+    if (ax == nullptr) {                            // no auxiliary streams: the same work in a row
+      rc = fvta_gemm(L.d, G, 2 * NT, reserve + 5 * L.d, kResW * L.d, 1, dg, G, 0, nullptr, 0,
+                     d_kernel_fw + (size_t)L.In * G, G, 1, stream);
+      if (rc) return rc;
+      add_out4<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, reinterpret_cast<float4*>(dsum),
+                                                            reinterpret_cast<const float4*>(dgs[0]),
+                                                            reinterpret_cast<const float4*>(dgs[1]));
+      rc = check_launch("add_out4");
+      if (rc) return rc;
+      rc = fvta_gemm(NT, L.In, G, dsum, G, 0, kernel_fw, G, 1, nullptr, 0, d_x, L.In, 0, stream);
+      if (rc) return rc;
+      rc = fvta_gemm(L.In, G, NT, x, L.In, 1, dsum, G, 0, nullptr, 0, d_kernel_fw, G, 1, stream);
+      if (rc) return rc;
+      colsum_accumulate<<<cg, 256, 0, st>>>(NT, G, dsum, G, d_bias_fw);
+      return check_launch("colsum_accumulate");
+    }
+    const int pair = (ax->next++) & 1;
+    cudaStream_t sa = ax->s[2 * pair], sb = ax->s[2 * pair + 1];
+    cudaEvent_t* ev = ax->e + 4 * pair;
+    bool ok = cudaEventRecord(ev[0], st) == cudaSuccess && cudaStreamWaitEvent(sa, ev[0], 0) == cudaSuccess;
+    if (!ok) { set_last_error("bilstm bwd fork", cudaGetLastError()); return FVTA_E_LAUNCH; }
+    // branch a: d kernel[In:] += [h_prev_fw ; h_prev_bw]^T @ [dg_fw ; dg_bw]
+    rc = fvta_gemm(L.d, G, 2 * NT, reserve + 5 * L.d, kResW * L.d, 1, dg, G, 0, nullptr, 0,
+                   d_kernel_fw + (size_t)L.In * G, G, 1, sa);
+    int rc_a = rc;
+    ok = cudaEventRecord(ev[1], sa) == cudaSuccess;
+    // calling stream: dsum, then d x
+    add_out4<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(n4, reinterpret_cast<float4*>(dsum),
+                                                          reinterpret_cast<const float4*>(dgs[0]),
+                                                          reinterpret_cast<const float4*>(dgs[1]));
+    rc = check_launch("add_out4");
+    ok = ok && cudaEventRecord(ev[2], st) == cudaSuccess && cudaStreamWaitEvent(sb, ev[2], 0) == cudaSuccess;
+    int rc_b = FVTA_OK;
+    if (ok && rc == FVTA_OK) {
+      // branch b: d kernel[:In] += x^T @ dsum ; d bias += colsum(dsum)
+      rc_b = fvta_gemm(L.In, G, NT, x, L.In, 1, dsum, G, 0, nullptr, 0, d_kernel_fw, G, 1, sb);
+      if (rc_b == FVTA_OK) {
+        colsum_accumulate<<<cg, 256, 0, sb>>>(NT, G, dsum, G, d_bias_fw);
+        rc_b = check_launch("colsum_accumulate");
+      }
+      ok = cudaEventRecord(ev[3], sb) == cudaSuccess;
+      if (rc == FVTA_OK) rc = fvta_gemm(NT, L.In, G, dsum, G, 0, kernel_fw, G, 1, nullptr, 0, d_x, L.In, 0, stream);
+    }
+    // join (always: a forked stream left dangling would poison a capture)
+    cudaStreamWaitEvent(st, ev[1], 0);
+    if (ok) cudaStreamWaitEvent(st, ev[3], 0);
+    if (!ok) { set_last_error("bilstm bwd fork/join", cudaGetLastError()); return FVTA_E_LAUNCH; }
+    if (rc_a) return rc_a;
+    if (rc_b) return rc_b;
+    return rc;
   }
   // d_x = dg_fw @ Wx_fw^T + dg_bw @ Wx_bw^T
   rc = fvta_gemm(NT, L.In, G, dgs[0], G, 0, kernel_fw, G, 1, nullptr, 0, d_x, L.In, 0, stream);
@@ -671,10 +747,10 @@ static int lstm_bwd_impl(const FvtaLstmDesc& L, const SeqAddr& A, const float* x
   return FVTA_OK;
 }
 
-// workspace: xp_fw [B*J*4d], xp_bw [B*J*4d] (forward) or dgates [2][B*J*4d] (backward)
+// workspace: xp_fw [B*J*4d], xp_bw [B*J*4d] (forward) or dgates [2][B*J*4d] + their sum (backward)
 extern "C" size_t fvta_bilstm_workspace_bytes(const FvtaLstmDesc* L) {
   if (lstm_validate(L)) return 0;
-  return (size_t)2 * L->B * L->J * 4 * L->d * sizeof(float);
+  return (size_t)3 * L->B * L->J * 4 * L->d * sizeof(float);
 }
 extern "C" size_t fvta_bilstm_reserve_floats(const FvtaLstmDesc* L) {
   if (lstm_validate(L)) return 0;
@@ -724,7 +800,7 @@ static int reader_validate(const FvtaReaderDesc* R) {
 }
 extern "C" size_t fvta_reader_workspace_bytes(const FvtaReaderDesc* R) {
   if (reader_validate(R)) return 0;
-  return (size_t)2 * R->ntok * 4 * R->d * sizeof(float);
+  return (size_t)3 * R->ntok * 4 * R->d * sizeof(float);
 }
 extern "C" size_t fvta_reader_reserve_floats(const FvtaReaderDesc* R) {
   if (reader_validate(R)) return 0;
