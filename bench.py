@@ -568,7 +568,7 @@ def run_own(args):
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
-            n = 6
+            n = 36                      # ~12 s of CPU work on 16 cores
             cpu_reference_step(1, seed=99)
             t = cpu_reference_step(n)
             line["cpu_baseline"] = {
