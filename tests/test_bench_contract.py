@@ -55,11 +55,20 @@ def test_own_arm_refuses_to_run_without_cuda():
     assert "no CPU fallback" in (out.stderr + out.stdout)
 
 
-def test_committed_bench_line_is_complete():
-    """profiles/bench_r1_dev.json is a line the driver's checks would accept."""
-    with open(os.path.join(ROOT, "profiles", "bench_r1_dev.json")) as f:
+@pytest.mark.parametrize("name", ["bench_r1_dev.json", "bench_r2_dev.json"])
+def test_committed_bench_line_is_complete(name):
+    """profiles/bench_r*_dev.json are lines the driver's checks would accept."""
+    with open(os.path.join(ROOT, "profiles", name)) as f:
         line = json.loads(f.read().strip().splitlines()[-1])
     assert BASE_KEYS | {"clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"} <= set(line)
+    if name == "bench_r2_dev.json":
+        b = line["roofline_bwd"]
+        assert b["bound"] == "hbm" and abs(b["frac"] - b["achieved"] / b["peak"]) < 1e-9 and b["frac"] >= 0.3
+        assert line["roofline"]["frac"] >= 0.45 and line["roofline"]["parity"]["g1_all_rel_err"] < 1e-4
+        f2 = line["e2e_fresh_batches"]
+        assert "error" not in f2 and f2["h2d_bytes_per_step"] > 0
+        assert f2["ms_per_step"] <= 1.1 * f2["ms_per_step_same_workload_one_cached_batch"]   # the review's bar
+        assert {"min", "median", "p90", "block_means"} <= set(line["ms_per_step_spread_rank0"])
     r = line["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s"
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
@@ -69,11 +78,12 @@ def test_committed_bench_line_is_complete():
     assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
-def test_committed_launch_list_summarises():
-    """profiles/launches_r1_bench_eager.csv parses into one complete step whose time is dominated by
+@pytest.mark.parametrize("name", ["launches_r1_bench_eager.csv", "launches_r2_bench_eager.csv"])
+def test_committed_launch_list_summarises(name):
+    """profiles/launches_r*_bench_eager.csv parse into one complete step whose time is dominated by
     this library's kernels (the evidence that the step is not a torch fallback)."""
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"),
-                          os.path.join(ROOT, "profiles", "launches_r1_bench_eager.csv")],
+                          os.path.join(ROOT, "profiles", name)],
                          capture_output=True, text=True, cwd=ROOT, timeout=120)
     assert out.returncode == 0, out.stderr[-1000:]
     head = out.stdout.splitlines()[0]
@@ -81,3 +91,5 @@ def test_committed_launch_list_summarises():
     pct = int(head.rsplit("(", 1)[1].split("%")[0])
     assert pct >= 75, head
     assert "fvta::attn_fwd_tc" in out.stdout and "fvta::gemm_mma_kernel" in out.stdout
+    if "r2" in name:
+        assert "fvta::attn_bwd_tc" in out.stdout
