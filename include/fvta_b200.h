@@ -207,7 +207,11 @@ int fvta_reader_fwd(const FvtaReaderDesc* desc, const float* x_tok, const int32_
                     size_t workspace_bytes, void* stream);
 
 /* d_out_arena [rows,2d], d_last [B,2d] (nullable) -> d_x_tok [ntok,In] (overwritten),
- * d_kernel [In+d,4d], d_bias [4d] ACCUMULATED (+=). */
+ * d_kernel [In+d,4d], d_bias [4d] ACCUMULATED (+=).
+ * The three products behind the recurrence (d kernel[In:], d x, d kernel[:In] + d bias) are
+ * independent: this call and fvta_bilstm_bwd fork them over two auxiliary streams (a pool of four
+ * per device, created on the first call -- make that call outside a stream capture) and join on
+ * `stream` before returning, so the caller sees ordinary stream semantics. */
 int fvta_reader_bwd(const FvtaReaderDesc* desc, const float* x_tok, const int32_t* seq_tok_off,
                     const int32_t* seq_len, const int64_t* seq_out_row, const float* kernel,
                     const float* reserve, const float* d_out_arena, const float* d_last, float* d_x_tok,
