@@ -601,7 +601,8 @@ def fresh_batch_leg(args, cfg, model, trainer, timed_steps, sync_all):
     model.set_resident_tables(image_emb_mat=resident_photo_table(store, model.device),
                               existing_emb_mat=store.existing_emb_mat)
     warm = max(3, args.warmup)
-    workers = max(2, min(16, (os.cpu_count() or 4) - 2))
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+    workers = max(2, min(16, ncpu - 2))
     loader = BatchLoader(store, model, PER_GPU_BATCH, num_steps=warm + args.steps + 1, shuffle=True, seed=7,
                          workers=workers, depth=2 * workers)
     loader.pin_caps()
