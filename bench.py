@@ -504,8 +504,20 @@ def run_own(args):
     sampler.mark(th0, time.perf_counter())
 
     # ---- end-to-end leg: Trainer.step from pinned host tensors, loss read back -----------
-    for i in range(max(1, args.warmup // 2)):
-        trainer.step(None, batches[i % len(batches)])
+    # warm-up with the SAME pipelined pattern as the timed steps (copy stream, staging buffers, the pinned
+    # loss slots and the prefetch path are all created on first use)
+    use_prefetch = not args.no_prefetch and not args.no_graph
+    if use_prefetch:
+        trainer.prefetch(batches[0])
+    hs = []
+    for i in range(max(3, args.warmup)):
+        hs.append(trainer.step_handle(None, batches[i % len(batches)]))
+        if use_prefetch:
+            trainer.prefetch(batches[(i + 1) % len(batches)])
+        if len(hs) > 1:
+            hs.pop(0).result()
+    while hs:
+        hs.pop(0).result()
     sync_all()
     pending = {}
 
@@ -525,7 +537,7 @@ def run_own(args):
         if i == args.steps - 1:
             out = (pending.pop("h").result(), None, None)          # the final step's loss
         return out
-    if not args.no_prefetch and not args.no_graph:
+    if use_prefetch:
         trainer.prefetch(batches[0])
     t_steps, t_bracket, res = timed_steps(e2e_step, args.steps)
     loss_val = res[0]
